@@ -1,0 +1,371 @@
+"""AdaptiveChargingOptimization — same surface as reference
+adacharge/adaptive_charging_optimization.py ("aco.py"), solved on the GPU.
+
+What is kept: ``ObjectiveComponent(function, coefficient=1, kwargs={})`` (aco.py:12-15),
+``InfeasibilityException`` (aco.py:8-9), ``AdaptiveChargingOptimization(objective,
+interface, constraint_type, enforce_energy_equality, solver)`` and ``.solve(
+active_sessions, infrastructure, peak_limit, prev_peak, verbose)`` (aco.py:31-43,
+286-321), the objective function names (aco.py:336-408).
+
+What differs (documented, unavoidable without cvxpy):
+* ``solver`` is accepted and ignored.
+* objective functions are *numeric*: called with a numpy rates matrix they return the
+  value the reference's cvxpy expression would have; the solver recognises the
+  built-in ones by identity and packs them into the device objective.  A user
+  component must carry a ``kernel_spec(infrastructure, interface, T, **kwargs)``
+  attribute returning the same dict as the built-ins (see ``_SPECS``); anything else
+  is rejected loudly.
+* ``build_problem`` and the static constraint builders return packed descriptors
+  (numpy), not cvxpy objects.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import List, Optional, Union
+
+import numpy as np
+
+from .interface import Interface, SessionInfo, InfrastructureInfo
+from . import engine, _cabi
+
+
+class InfeasibilityException(Exception):
+    pass
+
+
+ObjectiveComponent = namedtuple("ObjectiveComponent", ["function", "coefficient", "kwargs"])
+ObjectiveComponent.__new__.__defaults__ = (1, {})
+
+
+# ---------------------------------------------------------------------------------
+#  Objective functions (numeric twins of aco.py:336-408)
+# ---------------------------------------------------------------------------------
+def charging_power(rates, infrastructure, **kwargs):
+    """rates (A) -> kW, aco.py:336-339."""
+    return np.asarray(rates, dtype=float) * (np.asarray(infrastructure.voltages, dtype=float)[:, None] / 1e3)
+
+
+def aggregate_power(rates, infrastructure, **kwargs):
+    return charging_power(rates, infrastructure).sum(axis=0)  # aco.py:342-344
+
+
+def get_period_energy(rates, infrastructure, period, **kwargs):
+    return charging_power(rates, infrastructure) * (period / 60)  # aco.py:347-351
+
+
+def aggregate_period_energy(rates, infrastructure, interface, **kwargs):
+    return get_period_energy(rates, infrastructure, interface.period).sum(axis=0)  # aco.py:354-360
+
+
+def quick_charge(rates, infrastructure, interface, **kwargs):
+    T = np.shape(rates)[1]
+    c = np.array([(T - t) / T for t in range(T)])
+    return float(c @ np.asarray(rates, dtype=float).sum(axis=0))  # aco.py:363-371
+
+
+def equal_share(rates, infrastructure, interface, **kwargs):
+    return -float((np.asarray(rates, dtype=float) ** 2).sum())  # aco.py:374-375
+
+
+def tou_energy_cost(rates, infrastructure, interface, **kwargs):
+    prices = np.asarray(interface.get_prices(np.shape(rates)[1]), dtype=float)
+    return -float(prices @ aggregate_period_energy(rates, infrastructure, interface))  # aco.py:378-380
+
+
+def total_energy(rates, infrastructure, interface, **kwargs):
+    return float(get_period_energy(rates, infrastructure, interface.period).sum())  # aco.py:383-384
+
+
+def peak(rates, infrastructure, interface, baseline_peak=0, **kwargs):
+    max_power = aggregate_power(rates, infrastructure).max()
+    prev_peak = interface.get_prev_peak() * infrastructure.voltages[0] / 1000  # aco.py:390
+    if baseline_peak > 0:
+        return float(max(max_power, baseline_peak, prev_peak))
+    return float(max(max_power, prev_peak))
+
+
+def demand_charge(rates, infrastructure, interface, baseline_peak=0, **kwargs):
+    return -interface.get_demand_charge() * peak(rates, infrastructure, interface, baseline_peak, **kwargs)  # aco.py:397-400
+
+
+def load_flattening(rates, infrastructure, interface, external_signal=None, **kwargs):
+    T = np.shape(rates)[1]
+    if external_signal is None:
+        external_signal = np.zeros(T)
+    return -float(((aggregate_power(rates, infrastructure) + np.asarray(external_signal, dtype=float)[:T]) ** 2).sum())  # aco.py:403-408
+
+
+def non_completion_penalty(rates, infrastructure, interface, norm=1, **kwargs):
+    """NOT in the reference snapshot; defined by this project as
+    -sum_s |remaining_demand_s - E_s(rates)| (kWh) over ``interface.active_sessions()``,
+    E_s = energy planned inside the session window.  Under the energy rows
+    E_s <= remaining_demand_s this is linear in rates.  ``norm=2`` (sum of squares) is
+    accepted by the numeric function and by the oracle, not yet by the device solver."""
+    R = np.asarray(rates, dtype=float)
+    tot = 0.0
+    for s in interface.active_sessions():
+        i = infrastructure.get_station_index(s.station_id)
+        w = infrastructure.voltages[i] * interface.period / 1e3 / 60
+        unmet = s.remaining_demand - w * R[i, s.arrival_offset : s.arrival_offset + s.remaining_time].sum()
+        tot += abs(unmet) if norm == 1 else unmet**2
+    return -float(tot)
+
+
+# kernel specs: contribution of ONE unit of the (maximised) component to the packed
+# minimisation objective  sum (alpha_t + k_i beta_t) r + qd |r|^2 + gamma (u+ext)^2 + w max(max u, p0)
+def _spec_quick_charge(infra, interface, T, **kw):
+    return dict(alpha=-np.array([(T - t) / T for t in range(T)]))
+
+
+def _spec_equal_share(infra, interface, T, **kw):
+    return dict(qd=1.0)
+
+
+def _spec_tou(infra, interface, T, **kw):
+    return dict(beta=np.asarray(interface.get_prices(T), dtype=float) * (interface.period / 60))
+
+
+def _spec_total_energy(infra, interface, T, **kw):
+    return dict(beta=-np.full(T, interface.period / 60))
+
+
+def _peak_p0(infra, interface, baseline_peak=0, **kw):
+    prev = interface.get_prev_peak() * infra.voltages[0] / 1000
+    return max(prev, baseline_peak) if baseline_peak > 0 else prev
+
+
+def _spec_peak(infra, interface, T, baseline_peak=0, **kw):
+    return dict(peak_w=-1.0, peak_p0=_peak_p0(infra, interface, baseline_peak))
+
+
+def _spec_demand_charge(infra, interface, T, baseline_peak=0, **kw):
+    return dict(peak_w=float(interface.get_demand_charge()), peak_p0=_peak_p0(infra, interface, baseline_peak))
+
+
+def _spec_load_flattening(infra, interface, T, external_signal=None, **kw):
+    ext = np.zeros(T) if external_signal is None else np.asarray(external_signal, dtype=float)[:T]
+    return dict(gamma=1.0, ext=ext)
+
+
+def _spec_ncp(infra, interface, T, norm=1, **kw):
+    if norm != 1:
+        raise NotImplementedError("non_completion_penalty(norm=2) is not implemented on the device path yet")
+    return dict(beta=-np.full(T, interface.period / 60))
+
+
+_SPECS = {
+    quick_charge: _spec_quick_charge,
+    equal_share: _spec_equal_share,
+    tou_energy_cost: _spec_tou,
+    total_energy: _spec_total_energy,
+    peak: _spec_peak,
+    demand_charge: _spec_demand_charge,
+    load_flattening: _spec_load_flattening,
+    non_completion_penalty: _spec_ncp,
+}
+
+
+def pack_objective(objective: List[ObjectiveComponent], infrastructure, interface, T, **caller_kwargs) -> dict:
+    """build_objective (aco.py:200-218) into packed form; component kwargs override
+    caller kwargs (aco.py:203-217)."""
+    out = dict(alpha=np.zeros(T), beta=np.zeros(T), qd=0.0, gamma=0.0, ext=None, peak_w=0.0, peak_p0=0.0)
+    ext_acc = np.zeros(T)
+    peaks = []
+    for comp in objective:
+        fn, coef, kw = comp.function, comp.coefficient, dict(caller_kwargs)
+        kw.update(comp.kwargs or {})
+        spec_fn = _SPECS.get(fn) or getattr(fn, "kernel_spec", None)
+        if spec_fn is None:
+            raise TypeError(
+                f"objective component {getattr(fn, '__name__', fn)!r} has no device kernel spec; built-ins are "
+                f"{sorted(f.__name__ for f in _SPECS)}; custom components must define `kernel_spec`."
+            )
+        sp = spec_fn(infrastructure, interface, T, **kw)
+        if "alpha" in sp:
+            out["alpha"] += coef * np.asarray(sp["alpha"], dtype=float)
+        if "beta" in sp:
+            out["beta"] += coef * np.asarray(sp["beta"], dtype=float)
+        if "qd" in sp:
+            out["qd"] += coef * sp["qd"]
+        if "gamma" in sp:
+            g = coef * sp["gamma"]
+            if g < 0:
+                raise ValueError("load_flattening with a negative coefficient is not concave")
+            out["gamma"] += g
+            ext_acc += g * np.asarray(sp.get("ext", np.zeros(T)), dtype=float)
+        if "peak_w" in sp:
+            w = coef * sp["peak_w"]
+            if w < 0:
+                raise ValueError("peak/demand_charge with this sign is not concave (cvxpy would raise a DCP error)")
+            peaks.append((w, sp["peak_p0"]))
+    if out["qd"] < 0:
+        raise ValueError("equal_share with a negative total coefficient is not concave")
+    if out["gamma"] > 0:
+        out["ext"] = ext_acc / out["gamma"]
+    if peaks:
+        p0s = {round(p, 12) for _, p in peaks}
+        if len(p0s) > 1:
+            raise NotImplementedError("peak terms with different baselines are not supported on the device path")
+        out["peak_w"] = sum(w for w, _ in peaks)
+        out["peak_p0"] = peaks[0][1]
+    return out
+
+
+class AdaptiveChargingOptimization:
+    """Base class for all MPC based charging algorithms (aco.py:18-43).
+
+    Args:
+        objective (List[ObjectiveComponent]): components of the optimisation objective.
+        interface (Interface): information source.
+        constraint_type (str): 'SOC' or 'LINEAR'.
+        enforce_energy_equality (bool): energy delivered must equal (True) or not
+            exceed (False) the request.
+        solver: accepted for signature compatibility, ignored.
+        solver_options (dict): fields of ``acb_options`` (eps_rel, eps_abs, viol_tol,
+            max_iter, rho0, ...).
+    """
+
+    def __init__(self, objective: List[ObjectiveComponent], interface: Interface, constraint_type="SOC",
+                 enforce_energy_equality=False, solver="ECOS", solver_options: Optional[dict] = None, device=None):
+        self.interface = interface
+        self.constraint_type = constraint_type
+        self.enforce_energy_equality = enforce_energy_equality
+        self.solver = solver
+        self.objective_configuration = objective
+        self.solver_options = dict(solver_options or {})
+        self.device = device
+        self.last_info = None
+
+    # ---- descriptors in place of the reference's cvxpy constraint builders -----------
+    @staticmethod
+    def charging_rate_bounds(rates_shape, active_sessions: List[SessionInfo], evse_index: List[str]):
+        """lb / ub arrays of aco.py:45-79 (numpy; the device twin is acb_charging_rate_bounds)."""
+        lb, ub = np.zeros(rates_shape), np.zeros(rates_shape)
+        for session in active_sessions:
+            i = evse_index.index(session.station_id)
+            a, e = session.arrival_offset, session.arrival_offset + session.remaining_time
+            lb[i, a:e] = session.min_rates
+            ub[i, a:e] = session.max_rates
+        ub[ub < lb] = lb[ub < lb]
+        return {"charging_rate_bounds.lb": lb, "charging_rate_bounds.ub": ub}
+
+    @staticmethod
+    def energy_constraints(active_sessions, infrastructure, period, enforce_energy_equality=False):
+        """{name: (row, start, stop, kWh_per_A_period, remaining_demand, '=='|'<=')} — aco.py:81-124."""
+        out = {}
+        for s in active_sessions:
+            i = infrastructure.get_station_index(s.station_id)
+            out[f"energy_constraints.{s.session_id}"] = (
+                i, s.arrival_offset, s.arrival_offset + s.remaining_time,
+                infrastructure.voltages[i] * period / 1e3 / 60, s.remaining_demand,
+                "==" if enforce_energy_equality else "<=",
+            )
+        return out
+
+    @staticmethod
+    def infrastructure_constraints(infrastructure, constraint_type="SOC"):
+        """{name: (rows, limit)}: rows is (2, N) [v cos; v sin] for SOC, (N,) |v| for LINEAR — aco.py:126-179."""
+        cm = infrastructure.constraint_matrix
+        if cm is None or np.asarray(cm).shape == (0, 0):
+            return {}
+        out = {}
+        if constraint_type == "SOC":
+            if infrastructure.phases is None:
+                raise ValueError("phases is required when using SOC infrastructure constraints.")
+            ph = np.deg2rad(infrastructure.phases)
+            for j, v in enumerate(np.asarray(cm)):
+                out[f"infrastructure_constraints.{infrastructure.constraint_ids[j]}"] = (
+                    np.stack([v * np.cos(ph), v * np.sin(ph)]), infrastructure.constraint_limits[j])
+        elif constraint_type == "LINEAR":
+            for j, v in enumerate(np.asarray(cm)):
+                out[f"infrastructure_constraints.{infrastructure.constraint_ids[j]}"] = (np.abs(v), infrastructure.constraint_limits[j])
+        else:
+            raise ValueError(
+                "Invalid infrastructure constraint type: {0}. Valid options are SOC or AFFINE.".format(constraint_type))
+        return out
+
+    @staticmethod
+    def peak_constraint(peak_limit):
+        return {} if peak_limit is None else {"peak_constraint": peak_limit}  # aco.py:181-198
+
+    def build_objective(self, infrastructure, T, **kwargs):
+        return pack_objective(self.objective_configuration, infrastructure, self.interface, T, **kwargs)
+
+    # ---- the path --------------------------------------------------------------------
+    def build_instance(self, active_sessions, infrastructure, peak_limit=None, prev_peak=0) -> engine.Instance:
+        T = max(s.arrival_offset + s.remaining_time for s in active_sessions)  # aco.py:243-245
+        ps = engine.pack_sessions(active_sessions, infrastructure, self.interface.period)
+        ob = self.build_objective(infrastructure, T, prev_peak=prev_peak)
+        pl = None
+        if peak_limit is not None:
+            pl = np.broadcast_to(np.asarray(peak_limit, dtype=float), (T,)).copy() if np.ndim(peak_limit) == 0 else np.asarray(peak_limit, dtype=float)[:T]
+            if len(pl) < T:
+                raise ValueError("peak_limit is shorter than the optimisation horizon")
+        return engine.Instance(
+            T=T, sess_row=np.array(ps["sess_row"]), sess_start=np.array(ps["sess_start"]), sess_len=np.array(ps["sess_len"]),
+            sess_energy=np.array(ps["sess_energy"]), min_rates=ps["min_rates"], max_rates=ps["max_rates"],
+            alpha=ob["alpha"], beta=ob["beta"], qd=ob["qd"], gamma=ob["gamma"], ext=ob["ext"],
+            peak_w=ob["peak_w"], peak_p0=ob["peak_p0"], peak_limit=pl, sess_order=ps["order"],
+        )
+
+    def build_problem(self, active_sessions, infrastructure, peak_limit=None, prev_peak: float = 0):
+        """Packed twin of aco.py:220-284: {'objective', 'constraints', 'variables'}."""
+        T = max(s.arrival_offset + s.remaining_time for s in active_sessions)
+        N = len(infrastructure.station_ids)
+        constraints = {}
+        constraints.update(self.charging_rate_bounds((N, T), active_sessions, infrastructure.station_ids))
+        constraints.update(self.energy_constraints(active_sessions, infrastructure, self.interface.period, self.enforce_energy_equality))
+        constraints.update(self.infrastructure_constraints(infrastructure, self.constraint_type))
+        constraints.update(self.peak_constraint(peak_limit))
+        return {
+            "objective": self.build_objective(infrastructure, T, prev_peak=prev_peak),
+            "constraints": constraints,
+            "variables": {"rates": (N, T)},
+        }
+
+    def _site_for(self, infrastructure, inst: engine.Instance) -> engine.Site:
+        use_u = inst.gamma > 0 or inst.peak_w > 0
+        return engine.get_site(infrastructure, self.constraint_type, inst.peak_limit is not None, use_u, self.device)
+
+    def _options(self):
+        return _cabi.default_options(equality=int(bool(self.enforce_energy_equality)), **self.solver_options)
+
+    def solve(self, active_sessions: List[SessionInfo], infrastructure: InfrastructureInfo,
+              peak_limit: Union[float, List[float], np.ndarray] = None, prev_peak=0, verbose: bool = False):
+        """Returns an (N, T) float64 array of charging rates, rows ordered like
+        infrastructure.station_ids (aco.py:286-321)."""
+        if len(active_sessions) == 0:
+            return np.zeros((infrastructure.num_stations, 1))  # aco.py:310-311
+        inst = self.build_instance(active_sessions, infrastructure, peak_limit, prev_peak)
+        site = self._site_for(infrastructure, inst)
+        pb = engine.PackedBatch(site, [inst]).upload().solve(self._options())
+        rates = pb.rates[0, :, : inst.T].to("cpu", non_blocking=False).numpy().astype(np.float64)
+        status = int(pb.status[0].item())
+        stats = pb.stats[0].cpu().numpy()
+        self.last_info = dict(status=status, iters=int(pb.iters[0].item()), r_prim=float(stats[0]), r_dual=float(stats[1]),
+                              gap=float(stats[2]), violation=float(stats[3]), rho=float(stats[4]))
+        if verbose:
+            print(self.last_info)
+        check_status(status, self.last_info)
+        return rates
+
+
+_STATUS_NAME = {0: "optimal", 1: "iteration_limit", 2: "infeasible", 3: "numerical_error"}
+
+
+def check_status(status: int, info: dict):
+    """Solve failed -> InfeasibilityException, as aco.py:319-320 does for anything but
+    OPTIMAL / OPTIMAL_INACCURATE.  An iteration-limit exit whose residuals are within
+    100x of the tolerance counts as 'inaccurate' and is returned."""
+    if status == _cabi.ACB_SOLVED:
+        return
+    if status == _cabi.ACB_MAX_ITER and max(info["r_prim"], info["r_dual"]) <= 1e-2 and info["violation"] <= 1e-3:
+        return
+    raise InfeasibilityException(f"Solve failed with status {_STATUS_NAME.get(status, status)}")
+
+
+__all__ = [
+    "InfeasibilityException", "ObjectiveComponent", "AdaptiveChargingOptimization", "charging_power", "aggregate_power",
+    "get_period_energy", "aggregate_period_energy", "quick_charge", "equal_share", "tou_energy_cost", "total_energy",
+    "peak", "demand_charge", "load_flattening", "non_completion_penalty", "pack_objective", "check_status",
+]

@@ -1,0 +1,63 @@
+// Shared definitions of the adacharge_b200 native library (see include/adacharge_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/adacharge_b200.h"
+
+#define ACB_VERSION 100
+#define ACB_OPP 8          // outputs per column-pass work item
+#define ACB_NRED 16        // floats per warp in the reduction scratch
+#define ACB_MAX_WARPS 32
+
+// Device view of a site (all pointers device).  Row layout of the scaled coupling
+// matrix Khat (R x N): 2*nDisc SOC rows (cos, sin pairs), nLin linear rows, then the
+// optional peak-limit row (1/sqrt(N)) and the optional aggregate-power row (k/|k|).
+struct SiteDev {
+    int N, M, R, NG, NP, nDisc, nLin, has_pl, has_u;
+    int TPW;        // EVSE rows per warp
+    int nRowWarps;  // warps that own EVSE rows
+    int nSlots;     // nRowWarps * TPW
+    int nAllow;     // total allowable pilots
+    const int* slot_row;    // [nSlots] EVSE index or -1
+    const int* slot_grp;    // [nSlots]
+    const int* slot_prow;   // [nSlots] partial-row id
+    const int* slot_first;  // [nSlots] 1 = first contributor to its partial row
+    const int* pg_off;      // [NG+1] partial rows of group g
+    const float* ngrp;      // [NG] EVSEs per group
+    const float* kg;        // [NG] kW per A
+    const float* C;         // [R*NG] distinct scaled columns of Khat
+    const float* U;         // [R*R] eigenvectors of Khat Khat' (U[r*R+e])
+    const float* lam;       // [R] eigenvalues
+    const float* row_scale; // [R]
+    const float* lim;       // [R] limit / row_scale (disc rows: both entries; 0 for pl/u rows)
+    // float64 postprocessing constants (unscaled)
+    const double* a_cos;    // [M*N] A_ji cos(phi_i)
+    const double* a_sin;    // [M*N]
+    const double* limits;   // [M]
+    const double* max_pilot;// [N]
+    const int* allow_off;   // [N+1]
+    const double* allow_vals;
+};
+
+struct acb_site {
+    int device;
+    SiteDev d;
+    std::vector<void*> allocs;
+    int constraint_type;
+    size_t smem_fixed;   // bytes of shared memory independent of Tp
+    size_t smem_per_col; // bytes per padded column
+};
+
+void acb_set_error(const std::string& s);
+#define ACB_CUDA(x)                                                                   \
+    do {                                                                              \
+        cudaError_t e_ = (x);                                                         \
+        if (e_ != cudaSuccess) {                                                      \
+            acb_set_error(std::string(#x) + ": " + cudaGetErrorString(e_));          \
+            return ACB_E_CUDA;                                                        \
+        }                                                                             \
+    } while (0)
+
+size_t acb_solve_smem_bytes(const SiteDev& s, int Tp, int S_max, int nwarps);

@@ -1,0 +1,270 @@
+// Site construction: turns the InfrastructureInfo arrays into the constants the kernels
+// use (scaled coupling matrix, electrically-distinct EVSE groups, row -> warp slots,
+// eigen-decomposition of Khat Khat', float64 postprocessing rows).
+// Replaces the per-call Python work of reference
+// adacharge/adaptive_charging_optimization.py:152-172 and adacharge/utils.py:6-8.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include "acb_common.cuh"
+
+static thread_local std::string g_err;
+void acb_set_error(const std::string& s) { g_err = s; }
+extern "C" const char* acb_last_error(void) { return g_err.c_str(); }
+extern "C" int acb_version(void) { return ACB_VERSION; }
+
+extern "C" void acb_default_options(acb_options* o) {
+    o->eps_abs = 1e-5f;
+    o->eps_rel = 1e-4f;
+    o->viol_tol = 1e-5f;
+    o->rho0 = 0.1f;
+    o->kappa = 1.0f;
+    o->alpha = 1.6f;
+    o->max_iter = 20000;
+    o->check_every = 25;
+    o->equality = 0;
+    o->adapt_rho = 1;
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major), double.
+static void jacobi_eigh(std::vector<double>& A, int n, std::vector<double>& V, std::vector<double>& w) {
+    V.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) off += A[(size_t)p * n + q] * A[(size_t)p * n + q];
+        if (off < 1e-30) break;
+        for (int p = 0; p < n; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                double apq = A[(size_t)p * n + q];
+                if (std::fabs(apq) < 1e-300) continue;
+                double app = A[(size_t)p * n + p], aqq = A[(size_t)q * n + q];
+                double theta = (aqq - app) / (2 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+                double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+                    A[(size_t)k * n + p] = c * akp - s * akq;
+                    A[(size_t)k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+                    A[(size_t)p * n + k] = c * apk - s * aqk;
+                    A[(size_t)q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+                    V[(size_t)k * n + p] = c * vkp - s * vkq;
+                    V[(size_t)k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    w.resize(n);
+    for (int i = 0; i < n; ++i) w[i] = std::max(0.0, A[(size_t)i * n + i]);
+}
+
+template <typename T>
+static int upload(acb_site* s, const std::vector<T>& h, const T** dptr) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(1, h.size()) * sizeof(T);
+    ACB_CUDA(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    if (!h.empty()) ACB_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dptr = (const T*)p;
+    return ACB_OK;
+}
+
+extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const double* cm,
+                               const double* phases_deg, const double* limits, const double* voltages,
+                               int constraint_type, int use_peak_row, int use_agg_row,
+                               const double* max_pilot, const int32_t* allow_off, const double* allow_vals) {
+    if (!out || N <= 0 || M < 0 || !voltages || (M > 0 && (!cm || !limits))) {
+        acb_set_error("acb_site_create: bad arguments");
+        return ACB_E_INVALID;
+    }
+    if (constraint_type != ACB_SOC && constraint_type != ACB_LINEAR) {
+        acb_set_error("acb_site_create: constraint_type must be ACB_SOC or ACB_LINEAR");
+        return ACB_E_INVALID;
+    }
+    if (M > 0 && constraint_type == ACB_SOC && !phases_deg) {
+        acb_set_error("phases is required when using SOC infrastructure constraints.");
+        return ACB_E_INVALID;
+    }
+    ACB_CUDA(cudaSetDevice(device));
+    acb_site* s = new acb_site();
+    s->device = device;
+    s->constraint_type = constraint_type;
+    SiteDev& d = s->d;
+    memset(&d, 0, sizeof(d));
+    d.N = N;
+    d.M = M;
+    d.nDisc = (constraint_type == ACB_SOC) ? M : 0;
+    d.nLin = (constraint_type == ACB_LINEAR) ? M : 0;
+    d.has_pl = use_peak_row ? 1 : 0;
+    d.has_u = use_agg_row ? 1 : 0;
+    const int R = 2 * d.nDisc + d.nLin + d.has_pl + d.has_u;
+    d.R = R;
+
+    // float64 rows exactly as the reference forms them (utils.py:6-8)
+    std::vector<double> acos_((size_t)M * N, 0.0), asin_((size_t)M * N, 0.0);
+    if (M > 0 && phases_deg) {
+        for (int j = 0; j < M; ++j)
+            for (int i = 0; i < N; ++i) {
+                double rad = phases_deg[i] * (M_PI / 180.0);
+                acos_[(size_t)j * N + i] = cm[(size_t)j * N + i] * std::cos(rad);
+                asin_[(size_t)j * N + i] = cm[(size_t)j * N + i] * std::sin(rad);
+            }
+    }
+    // scaled coupling matrix
+    std::vector<double> K((size_t)R * N, 0.0), scale(R, 1.0), lim(R, 0.0), kv(N);
+    for (int i = 0; i < N; ++i) kv[i] = voltages[i] / 1e3;
+    int r = 0;
+    for (int j = 0; j < d.nDisc; ++j, r += 2) {
+        double ss = 0;
+        for (int i = 0; i < N; ++i)
+            ss += acos_[(size_t)j * N + i] * acos_[(size_t)j * N + i] + asin_[(size_t)j * N + i] * asin_[(size_t)j * N + i];
+        double sc = std::sqrt(ss / 2);
+        if (!(sc > 0)) sc = 1;
+        for (int i = 0; i < N; ++i) {
+            K[(size_t)r * N + i] = acos_[(size_t)j * N + i] / sc;
+            K[(size_t)(r + 1) * N + i] = asin_[(size_t)j * N + i] / sc;
+        }
+        scale[r] = scale[r + 1] = sc;
+        lim[r] = lim[r + 1] = limits[j] / sc;
+    }
+    for (int j = 0; j < d.nLin; ++j, ++r) {
+        double ss = 0;
+        for (int i = 0; i < N; ++i) ss += cm[(size_t)j * N + i] * cm[(size_t)j * N + i];
+        double sc = std::sqrt(ss);
+        if (!(sc > 0)) sc = 1;
+        for (int i = 0; i < N; ++i) K[(size_t)r * N + i] = std::fabs(cm[(size_t)j * N + i]) / sc;
+        scale[r] = sc;
+        lim[r] = limits[j] / sc;
+    }
+    if (d.has_pl) {
+        double sc = std::sqrt((double)N);
+        for (int i = 0; i < N; ++i) K[(size_t)r * N + i] = 1.0 / sc;
+        scale[r] = sc;
+        ++r;
+    }
+    if (d.has_u) {
+        double ss = 0;
+        for (int i = 0; i < N; ++i) ss += kv[i] * kv[i];
+        double sc = std::sqrt(ss);
+        for (int i = 0; i < N; ++i) K[(size_t)r * N + i] = kv[i] / sc;
+        scale[r] = sc;
+        ++r;
+    }
+    // electrically distinct groups: identical Khat column and identical kW/A
+    std::map<std::vector<double>, int> gmap;
+    std::vector<int> grp(N), gfirst;
+    for (int i = 0; i < N; ++i) {
+        std::vector<double> key(R + 1);
+        for (int q = 0; q < R; ++q) key[q] = K[(size_t)q * N + i];
+        key[R] = kv[i];
+        auto it = gmap.find(key);
+        if (it == gmap.end()) {
+            int g = (int)gfirst.size();
+            gmap[key] = g;
+            gfirst.push_back(i);
+            grp[i] = g;
+        } else
+            grp[i] = it->second;
+    }
+    const int NG = (int)gfirst.size();
+    d.NG = NG;
+    // slots: EVSEs ordered by group, TPW per warp
+    int TPW = 2;
+    if (const char* e = getenv("ACB_TPW")) TPW = std::max(1, atoi(e));
+    while ((N + TPW - 1) / TPW > ACB_MAX_WARPS) ++TPW;
+    d.TPW = TPW;
+    d.nRowWarps = (N + TPW - 1) / TPW;
+    d.nSlots = d.nRowWarps * TPW;
+    std::vector<int> order(N);
+    for (int i = 0; i < N; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return grp[a] < grp[b]; });
+    std::vector<int> slot_row(d.nSlots, -1), slot_grp(d.nSlots, 0), slot_prow(d.nSlots, 0), slot_first(d.nSlots, 0);
+    std::vector<int> pg_off(NG + 1, 0);
+    int np = 0;
+    for (int sl = 0; sl < d.nSlots; ++sl) {
+        if (sl >= N) continue;
+        int i = order[sl], g = grp[i];
+        slot_row[sl] = i;
+        slot_grp[sl] = g;
+        bool newp = (sl % TPW == 0) || slot_grp[sl - 1] != g;
+        if (newp) {
+            slot_first[sl] = 1;
+            slot_prow[sl] = np++;
+            pg_off[g + 1]++;
+        } else
+            slot_prow[sl] = slot_prow[sl - 1];
+    }
+    for (int g = 0; g < NG; ++g) pg_off[g + 1] += pg_off[g];
+    d.NP = np;
+    std::vector<float> ngrp(NG, 0.f), kg(NG), Cf((size_t)R * NG), Uf((size_t)R * R), lamf(R), scf(R), limf(R);
+    for (int i = 0; i < N; ++i) ngrp[grp[i]] += 1.f;
+    for (int g = 0; g < NG; ++g) {
+        kg[g] = (float)kv[gfirst[g]];
+        for (int q = 0; q < R; ++q) Cf[(size_t)q * NG + g] = (float)K[(size_t)q * N + gfirst[g]];
+    }
+    std::vector<double> KKt((size_t)R * R, 0.0), V, w;
+    for (int a = 0; a < R; ++a)
+        for (int b = 0; b < R; ++b) {
+            double acc = 0;
+            for (int i = 0; i < N; ++i) acc += K[(size_t)a * N + i] * K[(size_t)b * N + i];
+            KKt[(size_t)a * R + b] = acc;
+        }
+    jacobi_eigh(KKt, R, V, w);
+    for (int a = 0; a < R; ++a) {
+        lamf[a] = (float)w[a];
+        scf[a] = (float)scale[a];
+        limf[a] = (float)lim[a];
+        for (int b = 0; b < R; ++b) Uf[(size_t)a * R + b] = (float)V[(size_t)a * R + b];
+    }
+    std::vector<double> lim64(limits, limits + M), mp(N, 0.0);
+    if (max_pilot) mp.assign(max_pilot, max_pilot + N);
+    std::vector<int> aoff(N + 1, 0);
+    std::vector<double> avals;
+    if (allow_off && allow_vals) {
+        aoff.assign(allow_off, allow_off + N + 1);
+        avals.assign(allow_vals, allow_vals + allow_off[N]);
+    }
+    d.nAllow = (int)avals.size();
+    int rc = ACB_OK;
+#define UP(vec, field) if ((rc = upload(s, vec, &d.field)) != ACB_OK) { acb_site_destroy(s); return rc; }
+    UP(slot_row, slot_row) UP(slot_grp, slot_grp) UP(slot_prow, slot_prow) UP(slot_first, slot_first)
+    UP(pg_off, pg_off) UP(ngrp, ngrp) UP(kg, kg) UP(Cf, C) UP(Uf, U) UP(lamf, lam) UP(scf, row_scale) UP(limf, lim)
+    UP(acos_, a_cos) UP(asin_, a_sin) UP(lim64, limits) UP(mp, max_pilot) UP(aoff, allow_off) UP(avals, allow_vals)
+#undef UP
+    *out = s;
+    return ACB_OK;
+}
+
+extern "C" void acb_site_destroy(acb_site* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void* p : s->allocs) cudaFree(p);
+    delete s;
+}
+
+extern "C" int acb_site_dims(const acb_site* s, int* N, int* M, int* R, int* NG, int* NP) {
+    if (!s) return ACB_E_INVALID;
+    if (N) *N = s->d.N;
+    if (M) *M = s->d.M;
+    if (R) *R = s->d.R;
+    if (NG) *NG = s->d.NG;
+    if (NP) *NP = s->d.NP;
+    return ACB_OK;
+}
+
+extern "C" int acb_site_max_horizon(const acb_site* s) {
+    if (!s) return 0;
+    int best = 0;
+    for (int Tp = 32; Tp <= 288; Tp += 32)
+        if (acb_solve_smem_bytes(s->d, Tp, 64, 32) <= 232448) best = Tp;
+    return best;
+}

@@ -1,0 +1,783 @@
+// Batched MPC solve: one thread block per instance, all solver state on chip.
+//
+// Replaces AdaptiveChargingOptimization.build_problem + solve (reference
+// adacharge/adaptive_charging_optimization.py:220-321, i.e. cvxpy canonicalisation and
+// the ECOS interior-point solve) and the objective library (:363-408) by an
+// over-relaxed ADMM with residual-balanced penalty on the split
+//     minimise  c'r + qd|r|^2 + g(Khat r_t)   s.t.  r in B,
+// B = charging-rate box (aco.py:61-79) intersected with the per-session energy rows
+// (aco.py:105-123), Khat = scaled [A cos(phi); A sin(phi)] / |A| rows (aco.py:156-172),
+// the peak-limit row (aco.py:196-197) and the aggregate-power row used by
+// peak / demand_charge / load_flattening (aco.py:387-408).
+//
+// Per iteration (DESIGN.md "solve kernel"):
+//   column pass  : per period t, group sums of q = 2 z - v over electrically identical
+//                  EVSEs, then ONE (NG+R) x (NG+R) matrix apply that yields both
+//                  Khat'h (per group) and Khat x (per coupling row).
+//   row pass     : per EVSE row (one warp, lanes over t): x, over-relaxed v update,
+//                  projection onto box ∩ energy row by a warm-started safeguarded
+//                  Newton on the multiplier (warp reductions);
+//                  per coupling row: v update; disc / half-line projections; peak
+//                  epigraph level by Newton.
+// State: v (N x Tp) in registers, coupling v (R x Tp), bounds and partial sums in
+// shared memory; HBM is touched at load and store only.
+#include <algorithm>
+#include <cfloat>
+#include "acb_common.cuh"
+
+struct BatchDev {
+    acb_batch b;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// projection of (a, b) onto the disc of radius lim
+__device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za, float& zb) {
+    float n2 = a * a + b * b;
+    float f = (n2 > lim * lim) ? lim * rsqrtf(n2) : 1.0f;
+    za = a * f;
+    zb = b * f;
+}
+
+// shared-memory layout (floats), computed identically on host and device
+struct SmemLayout {
+    int LB, UB, PART, VC, VOUT, HG, ALPHA, BETA, PLIM, EBAR, MFT, CS, SINV, XS, SESS_A, SESS_B, SESS_E, SESS_MU,
+        SLOT, PGOFF, NGRP, KG, LIM, SCALE, RED, SCAL, total;
+    int OP;  // padded output count of MFT
+};
+__host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps) {
+    SmemLayout L;
+    int o = 0;
+    auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
+    L.OP = ((NG + R + ACB_OPP - 1) / ACB_OPP) * ACB_OPP;
+    L.LB = take(N * Tp);
+    L.UB = take(N * Tp);
+    L.PART = take(NP * Tp);
+    L.VC = take(R * Tp);
+    L.VOUT = take(R * Tp);
+    L.HG = take(NG * Tp);
+    L.ALPHA = take(Tp);
+    L.BETA = take(Tp);
+    L.PLIM = take(Tp);
+    L.EBAR = take(Tp);
+    L.MFT = take((NG + R) * L.OP);
+    L.CS = take(R * NG);
+    L.SINV = take(R * R);
+    L.XS = take(R * NG);
+    L.SESS_A = take(S_max);
+    L.SESS_B = take(S_max);
+    L.SESS_E = take(S_max);
+    L.SESS_MU = take(S_max);
+    L.SLOT = take(nSlots * 6);  // row, grp, prow, first, sess_first, sess_cnt
+    L.PGOFF = take(NG + 1);
+    L.NGRP = take(NG);
+    L.KG = take(NG);
+    L.LIM = take(R);
+    L.SCALE = take(R);
+    L.RED = take(nwarps * ACB_NRED);
+    L.SCAL = take(32);
+    L.total = o;
+    return L;
+}
+size_t acb_solve_smem_bytes(const SiteDev& s, int Tp, int S_max, int nwarps) {
+    return (size_t)make_layout(s.N, s.R, s.NG, s.NP, s.nSlots, Tp, S_max, nwarps).total * sizeof(float);
+}
+
+// indices into the SCAL scratch
+enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_EVALS };
+// reduction slots per warp
+enum { RD_E1 = 0, RD_E2, RD_XMAX, RD_ZMAX, RD_YMAX, RD_CX, RD_XX, RD_YZ, RD_RPC, RD_VIOL, RD_HD, RD_NAN, RD_EV };
+
+template <int Q, int TPW>
+__global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch B, acb_options opt) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    const int Tp = B.Tp, N = S.N, R = S.R, NG = S.NG, NP = S.NP;
+    const SmemLayout L = make_layout(N, R, NG, NP, S.nSlots, Tp, B.S_max, nwarps);
+    float* LB = sm + L.LB; float* UB = sm + L.UB; float* PART = sm + L.PART; float* VC = sm + L.VC;
+    float* VOUT = sm + L.VOUT; float* HG = sm + L.HG; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
+    float* PLIM = sm + L.PLIM; float* EBAR = sm + L.EBAR; float* MFT = sm + L.MFT; float* CS = sm + L.CS;
+    float* SINV = sm + L.SINV; float* XS = sm + L.XS;
+    int* SESS_A = (int*)(sm + L.SESS_A); int* SESS_B = (int*)(sm + L.SESS_B);
+    float* SESS_E = sm + L.SESS_E; float* SESS_MU = sm + L.SESS_MU;
+    int* SLOT = (int*)(sm + L.SLOT); int* PGOFF = (int*)(sm + L.PGOFF);
+    float* NGRP = sm + L.NGRP; float* KG = sm + L.KG; float* LIM = sm + L.LIM; float* SCALE = sm + L.SCALE;
+    float* RED = sm + L.RED; float* SCAL = sm + L.SCAL;
+    const int OP = L.OP, NIN = NG + R;
+
+    const int b = blockIdx.x;
+    const int Tb = B.T[b];
+    const int nS = B.n_sessions[b];
+    const int nDisc = S.nDisc, nLin = S.nLin;
+    const int rPL = 2 * nDisc + nLin, rU = rPL + S.has_pl;
+    const int nCT = nDisc + nLin + S.has_pl + S.has_u;  // coupling tasks
+
+    // ------------------------------------------------------------------ prologue
+    for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
+    for (int i = tid; i < R * Tp; i += nthreads) {
+        VC[i] = B.warm_vc ? B.warm_vc[(size_t)b * R * Tp + i] : 0.f;
+        VOUT[i] = 0.f;
+    }
+    for (int i = tid; i < R * NG; i += nthreads) CS[i] = S.C[i];
+    for (int i = tid; i < R; i += nthreads) { LIM[i] = S.lim[i]; SCALE[i] = S.row_scale[i]; }
+    for (int i = tid; i <= NG; i += nthreads) PGOFF[i] = S.pg_off[i];
+    for (int i = tid; i < NG; i += nthreads) { NGRP[i] = S.ngrp[i]; KG[i] = S.kg[i]; }
+    for (int i = tid; i < S.nSlots; i += nthreads) {
+        SLOT[i * 6 + 0] = S.slot_row[i]; SLOT[i * 6 + 1] = S.slot_grp[i];
+        SLOT[i * 6 + 2] = S.slot_prow[i]; SLOT[i * 6 + 3] = S.slot_first[i];
+        SLOT[i * 6 + 4] = 0; SLOT[i * 6 + 5] = 0;
+    }
+    for (int i = tid; i < B.S_max; i += nthreads) {
+        bool ok = i < nS;
+        size_t k = (size_t)b * B.S_max + i;
+        SESS_A[i] = ok ? B.sess_start[k] : 0;
+        SESS_B[i] = ok ? B.sess_start[k] + B.sess_len[k] : 0;
+        SESS_E[i] = ok ? B.sess_energy[k] : 0.f;
+        SESS_MU[i] = (ok && B.warm_mu) ? B.warm_mu[k] : 0.f;
+    }
+    for (int t = tid; t < Tp; t += nthreads) {
+        bool ok = t < Tb;
+        ALPHA[t] = ok ? B.alpha[(size_t)b * Tp + t] : 0.f;
+        BETA[t] = ok ? B.beta[(size_t)b * Tp + t] : 0.f;
+        EBAR[t] = (ok && B.ext) ? B.ext[(size_t)b * Tp + t] : 0.f;
+        PLIM[t] = (ok && B.peak_limit && S.has_pl) ? B.peak_limit[(size_t)b * Tp + t] / S.row_scale[rPL] : 3.0e38f;
+    }
+    __syncthreads();
+    // sessions -> bounds (charging_rate_bounds incl. the ub<lb patch) and per-slot session lists.
+    // Sessions arrive sorted by EVSE row (host packer), so each row's sessions are contiguous.
+    for (int s = warp; s < nS; s += nwarps) {
+        size_t k = (size_t)b * B.S_max + s;
+        int row = B.sess_row[k], a = SESS_A[s], len = SESS_B[s] - a, off = B.sess_rate_off[k];
+        for (int j = lane; j < len; j += 32) {
+            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
+            if (a + j < Tp) { LB[row * Tp + a + j] = lo; UB[row * Tp + a + j] = fmaxf(hi, lo); }
+        }
+    }
+    if (tid < S.nSlots) {
+        int row = SLOT[tid * 6 + 0], first = -1, cnt = 0;
+        if (row >= 0)
+            for (int s = 0; s < nS; ++s)
+                if (B.sess_row[(size_t)b * B.S_max + s] == row) { if (first < 0) first = s; ++cnt; }
+        SLOT[tid * 6 + 4] = first < 0 ? 0 : first;
+        SLOT[tid * 6 + 5] = cnt;
+    }
+    // cost scale = 1 / max |alpha_t + k_g beta_t|
+    {
+        float m = 0.f;
+        for (int i = tid; i < NG * Tp; i += nthreads) {
+            int g = i / Tp, t = i - g * Tp;
+            m = fmaxf(m, fabsf(ALPHA[t] + KG[g] * BETA[t]));
+        }
+        m = warp_max(m);
+        if (lane == 0) RED[warp * ACB_NRED] = m;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float m = 0.f;
+        for (int w = 0; w < nwarps; ++w) m = fmaxf(m, RED[w * ACB_NRED]);
+        SCAL[SC_CS] = (m > 1e-20f) ? 1.0f / m : 1.0f;
+        SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : opt.rho0;
+        SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
+        SCAL[SC_FLAG] = 0.f;
+        SCAL[SC_EVALS] = 0.f;
+    }
+    __syncthreads();
+    const float cs = SCAL[SC_CS];
+    for (int t = tid; t < Tp; t += nthreads) { ALPHA[t] *= cs; BETA[t] *= cs; }
+    const float qd = B.qd[b] * cs, Gamma = B.gamma[b] * cs, pk_w = B.peak_w[b] * cs, pk_p0 = B.peak_p0[b];
+    const float alpha = opt.alpha, kappa = opt.kappa;
+    float rho = SCAL[SC_RHO];
+    float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
+    const float su = S.has_u ? S.row_scale[rU] : 1.f;
+
+    // per-lane state: v for this warp's EVSE rows
+    float v1[TPW][Q];
+    const bool rowWarp = warp < S.nRowWarps;
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) {
+        int row = rowWarp ? SLOT[(warp * TPW + k) * 6] : -1;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            int t = lane + 32 * q;
+            float v = 0.f;
+            if (row >= 0 && t < Tp) {
+                if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
+                else v = clampf(0.f, LB[row * Tp + t], UB[row * Tp + t]);
+            }
+            v1[k][q] = v;
+        }
+    }
+
+    // ---- helpers --------------------------------------------------------------
+    // element multiplier of row slot `sl` at period t
+    // (rows with a single session use its multiplier everywhere: outside the window lb = ub = 0)
+    auto mu_at = [&](int sfirst, int scnt, int t) -> float {
+        float m = 0.f;
+        for (int s = sfirst; s < sfirst + scnt; ++s)
+            if (t >= SESS_A[s] && t < SESS_B[s]) m = SESS_MU[s];
+        return m;
+    };
+#define MU_ELEM(sf, scn, mu0, t) ((scn) <= 1 ? (mu0) : mu_at(sf, scn, t))
+    // (NG+R)^2 matrix of the column pass for the current rho:
+    //   Sinv = U diag(1/(d/rho + lam)) U',  X = Sinv C,
+    //   hg = -C'X sa + (d/rho) X' g,   v = X sa + (I - (d/rho) Sinv) g
+    auto build_matrix = [&]() {
+        const float dr = dd / rho;
+        for (int i = tid; i < R * R; i += nthreads) {
+            int r = i / R, c = i - r * R;
+            float acc = 0.f;
+            for (int e = 0; e < R; ++e) acc += __ldg(S.U + r * R + e) * __ldg(S.U + c * R + e) / (dr + __ldg(S.lam + e));
+            SINV[i] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < R * NG; i += nthreads) {
+            int r = i / NG, g = i - r * NG;
+            float acc = 0.f;
+            for (int c = 0; c < R; ++c) acc += SINV[r * R + c] * CS[c * NG + g];
+            XS[i] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < NIN * OP; i += nthreads) {
+            int c = i / OP, o = i - c * OP;
+            float m = 0.f;
+            if (o < NIN) {
+                if (o < NG && c < NG) {
+                    for (int r = 0; r < R; ++r) m -= CS[r * NG + o] * XS[r * NG + c];
+                } else if (o < NG) {
+                    m = dr * XS[(c - NG) * NG + o];
+                } else if (c < NG) {
+                    m = XS[(o - NG) * NG + c];
+                } else {
+                    int r = o - NG, j = c - NG;
+                    m = (r == j ? 1.f : 0.f) - dr * SINV[r * R + j];
+                }
+            }
+            MFT[i] = m;
+        }
+        __syncthreads();
+    };
+    // coupling-row projection inputs for column t: z of row r given stored v
+    auto agg_a = [&](float v, int t) -> float {  // unconstrained minimiser of the aggregate-power prox (kW)
+        float rp = rho / (su * su);
+        return (rp * (v * su) - 2.f * Gamma * EBAR[t]) / (rp + 2.f * Gamma);
+    };
+    // write partial sums of (mode 0) q = 2z - v or (mode 1) z for this warp's rows
+    auto write_part = [&](int mode) {
+        if (!rowWarp) return;
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int* sl = SLOT + (warp * TPW + k) * 6;
+            int row = sl[0];
+            if (row < 0) continue;
+            int prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
+            const float mu0 = scn ? SESS_MU[sf] : 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                int t = lane + 32 * q;
+                if (t >= Tp) continue;
+                float z = clampf(v1[k][q] - MU_ELEM(sf, scn, mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
+                float val = mode ? z : 2.f * z - v1[k][q];
+                if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
+            }
+        }
+    };
+
+    build_matrix();
+    write_part(0);
+    __syncthreads();
+
+    int it = 0, status = ACB_MAX_ITER;
+    float last_rp = 0.f, last_rd = 0.f, last_gap = 0.f, last_viol = 0.f;
+    const int nParts = (NIN + ACB_OPP - 1) / ACB_OPP;
+    for (it = 1; it <= opt.max_iter; ++it) {
+        const float plevel = SCAL[SC_PLEVEL];
+        // ------------------------------------------------------------ column pass
+        for (int wk = tid; wk < nParts * Tp; wk += nthreads) {
+            const int part = wk / Tp, t = wk - part * Tp;
+            const int obase = part * ACB_OPP;
+            float out[ACB_OPP];
+#pragma unroll
+            for (int k = 0; k < ACB_OPP; ++k) out[k] = 0.f;
+            const float al = ALPHA[t], be = BETA[t];
+            auto accum = [&](int c, float in) {
+                const float4 m0 = *reinterpret_cast<const float4*>(MFT + c * OP + obase);
+                const float4 m1 = *reinterpret_cast<const float4*>(MFT + c * OP + obase + 4);
+                out[0] += m0.x * in; out[1] += m0.y * in; out[2] += m0.z * in; out[3] += m0.w * in;
+                out[4] += m1.x * in; out[5] += m1.y * in; out[6] += m1.z * in; out[7] += m1.w * in;
+            };
+            for (int g = 0; g < NG; ++g) {
+                float acc = 0.f;
+                for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) acc += PART[p * Tp + t];
+                accum(g, rho1 * acc - NGRP[g] * (al + KG[g] * be));
+            }
+            int r = 0;
+            for (int j = 0; j < nDisc; ++j, r += 2) {
+                float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
+                proj_disc(a, bb, LIM[r], za, zb);
+                accum(NG + r, rho * (2.f * za - a));
+                accum(NG + r + 1, rho * (2.f * zb - bb));
+            }
+            for (int j = 0; j < nLin; ++j, ++r) {
+                float v = VC[r * Tp + t], z = fminf(v, LIM[r]);
+                accum(NG + r, rho * (2.f * z - v));
+            }
+            if (S.has_pl) {
+                float v = VC[r * Tp + t], z = fminf(v, PLIM[t]);
+                accum(NG + r, rho * (2.f * z - v));
+                ++r;
+            }
+            if (S.has_u) {
+                float v = VC[r * Tp + t], a = agg_a(v, t);
+                float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+                accum(NG + r, rho * (2.f * z - v));
+                ++r;
+            }
+            const float inv_rho = 1.f / rho;
+#pragma unroll
+            for (int k = 0; k < ACB_OPP; ++k) {
+                int o = obase + k;
+                if (o < NG) HG[o * Tp + t] = out[k] - (al + KG[o] * be);
+                else if (o < NIN) VOUT[(o - NG) * Tp + t] = out[k] * inv_rho;
+            }
+        }
+        __syncthreads();
+        const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter);
+        float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rCx = 0.f, rXx = 0.f, rYz = 0.f, rRpc = 0.f, rNan = 0.f;
+        float nEv = 0.f;
+        // --------------------------------------------------------------- row pass
+        if (rowWarp) {
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                const int* sl = SLOT + (warp * TPW + k) * 6;
+                const int row = sl[0];
+                if (row < 0) continue;
+                const int g = sl[1], prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
+                const float kgc = KG[g];
+                const float mu0 = scn ? SESS_MU[sf] : 0.f;
+                float lb[Q], ub[Q], zo[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    int t = lane + 32 * q;
+                    bool in = t < Tp;
+                    lb[q] = in ? LB[row * Tp + t] : 0.f;
+                    ub[q] = in ? UB[row * Tp + t] : 0.f;
+                    float vo = v1[k][q];
+                    float z = clampf(vo - MU_ELEM(sf, scn, mu0, t), lb[q], ub[q]);
+                    float hg = in ? HG[g * Tp + t] : 0.f;
+                    float x = (rho1 * (2.f * z - vo) + hg) * inv_d;
+                    v1[k][q] = vo + alpha * (x - z);
+                    zo[q] = z;
+                    if (chk) {
+                        float c = in ? (ALPHA[t] + kgc * BETA[t]) : 0.f;
+                        rE1 = fmaxf(rE1, fabsf(x - z));
+                        rXm = fmaxf(rXm, fabsf(x));
+                        rCx += c * x;
+                        rXx += x * x;
+                    }
+                }
+                // projection onto box ∩ energy rows: one multiplier per session
+                for (int s = sf; s < sf + scn; ++s) {
+                    const int a = SESS_A[s], e = SESS_B[s];
+                    const float Eb = SESS_E[s];
+                    const float tol = 2e-6f * (Eb + 1.f);
+                    float mu = SESS_MU[s];
+                    // inequality rows: lo = -1 marks "mu = 0 not evaluated yet" (mu itself stays >= 0)
+                    float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
+                    if (!opt.equality) mu = fmaxf(mu, 0.f);
+                    for (int step = 0; step < 16; ++step) {
+                        float E = 0.f;
+                        int nf = 0;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            int t = lane + 32 * q;
+                            if (t >= a && t < e) {
+                                float w = v1[k][q] - mu;
+                                E += clampf(w, lb[q], ub[q]);
+                                nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
+                            }
+                        }
+                        E = warp_sum(E);
+                        nf = __reduce_add_sync(0xffffffffu, nf);
+                        nEv += 1.f;
+                        float rr = E - Eb;
+                        if (fabsf(rr) <= tol) break;
+                        if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
+                        if (rr > 0.f) lo = mu; else hi = mu;
+                        float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
+                        if (!opt.equality) mun = fmaxf(mun, 0.f);
+                        if (!(mun > lo && mun < hi)) {
+                            if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
+                            else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
+                            else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
+                            if (!opt.equality) mun = fmaxf(mun, 0.f);
+                        }
+                        mu = mun;
+                    }
+                    if (lane == 0) SESS_MU[s] = mu;
+                    __syncwarp();
+                }
+                const float mu1 = scn ? SESS_MU[sf] : 0.f;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    int t = lane + 32 * q;
+                    if (t >= Tp) continue;
+                    float vn = v1[k][q];
+                    float zn = clampf(vn - MU_ELEM(sf, scn, mu1, t), lb[q], ub[q]);
+                    float val = chk ? zn : 2.f * zn - vn;
+                    if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
+                    if (chk) {
+                        rE2 = fmaxf(rE2, fabsf(zn - zo[q]));
+                        rZm = fmaxf(rZm, fabsf(zn));
+                        float y = rho1 * (vn - zn);
+                        rYm = fmaxf(rYm, fabsf(y));
+                        rYz += y * zn;
+                        if (!(fabsf(vn) < 1.0e30f)) rNan = 1.f;
+                    }
+                }
+            }
+        }
+        // ---------------------------------------------------------- coupling rows
+        for (int c = 0; c < nCT; ++c) {
+            if (warp != nwarps - 1 - (c % nwarps)) continue;
+            if (c < nDisc) {
+                const int r = 2 * c;
+                const float lim = LIM[r];
+                for (int t = lane; t < Tp; t += 32) {
+                    float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
+                    proj_disc(a, bb, lim, za, zb);
+                    float ka = VOUT[r * Tp + t], kb = VOUT[(r + 1) * Tp + t];
+                    float an = a + alpha * (ka - za), bn = bb + alpha * (kb - zb);
+                    VC[r * Tp + t] = an; VC[(r + 1) * Tp + t] = bn;
+                    if (chk) {
+                        float zan, zbn;
+                        proj_disc(an, bn, lim, zan, zbn);
+                        rRpc = fmaxf(rRpc, fmaxf(fabsf(ka - zan), fabsf(kb - zbn)));
+                        rXm = fmaxf(rXm, fmaxf(fabsf(ka), fabsf(kb)));
+                        VOUT[r * Tp + t] = rho * ((alpha - 1.f) * (ka - za) + (za - zan));
+                        VOUT[(r + 1) * Tp + t] = rho * ((alpha - 1.f) * (kb - zb) + (zb - zbn));
+                        rYz += rho * ((an - zan) * zan + (bn - zbn) * zbn);
+                    }
+                }
+            } else if (c < nDisc + nLin + S.has_pl) {
+                const int r = 2 * nDisc + (c - nDisc);
+                const bool isPL = (c == nDisc + nLin);
+                for (int t = lane; t < Tp; t += 32) {
+                    float cap = isPL ? PLIM[t] : LIM[r];
+                    float v = VC[r * Tp + t], z = fminf(v, cap), kx = VOUT[r * Tp + t];
+                    float vn = v + alpha * (kx - z);
+                    VC[r * Tp + t] = vn;
+                    if (chk) {
+                        float zn = fminf(vn, cap);
+                        rRpc = fmaxf(rRpc, fabsf(kx - zn));
+                        rXm = fmaxf(rXm, fabsf(kx));
+                        VOUT[r * Tp + t] = rho * ((alpha - 1.f) * (kx - z) + (z - zn));
+                        rYz += rho * (vn - zn) * zn;
+                    }
+                }
+            } else {
+                // aggregate-power row: quadratic (load flattening) + peak epigraph
+                const int r = rU;
+                const float rp = rho / (su * su), cur = rp + 2.f * Gamma;
+                float amax = -3.0e38f;
+                float pre[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    int t = lane + 32 * q;
+                    pre[q] = 0.f;
+                    if (t >= Tp) continue;
+                    float v = VC[r * Tp + t], a = agg_a(v, t);
+                    float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+                    float kx = VOUT[r * Tp + t];
+                    float vn = v + alpha * (kx - z);
+                    VC[r * Tp + t] = vn;
+                    pre[q] = (alpha - 1.f) * (kx - z) + z;
+                    if (t < Tb) amax = fmaxf(amax, agg_a(vn, t));
+                }
+                amax = warp_max(amax);
+                float pl = fmaxf(amax, pk_p0);
+                if (pk_w > 0.f && amax > pk_p0) {
+                    // minimise pk_w*max(p,p0) + cur/2 sum (a_t - p)_+^2 over p
+                    float F0 = 0.f;
+                    for (int t = lane; t < Tb; t += 32) F0 += fmaxf(agg_a(VC[r * Tp + t], t) - pk_p0, 0.f);
+                    F0 = warp_sum(F0) * cur;
+                    if (F0 <= pk_w) pl = pk_p0;
+                    else {
+                        float p = fminf(fmaxf(plevel, pk_p0), amax), lo = pk_p0, hi = amax;
+                        for (int step = 0; step < 24; ++step) {
+                            float F = 0.f;
+                            int na = 0;
+                            for (int t = lane; t < Tb; t += 32) {
+                                float a = agg_a(VC[r * Tp + t], t);
+                                if (a > p) { F += a - p; ++na; }
+                            }
+                            F = warp_sum(F) * cur - pk_w;
+                            na = __reduce_add_sync(0xffffffffu, na);
+                            if (fabsf(F) <= 1e-6f * pk_w) break;
+                            if (F > 0.f) lo = p; else hi = p;
+                            float pn = (na > 0) ? p + F / (cur * (float)na) : 0.5f * (lo + hi);
+                            if (!(pn > lo && pn < hi)) pn = 0.5f * (lo + hi);
+                            p = pn;
+                        }
+                        pl = p;
+                    }
+                }
+                if (lane == 0) SCAL[SC_PLEVEL] = pl;
+                if (chk) {
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        int t = lane + 32 * q;
+                        if (t >= Tp) continue;
+                        float vn = VC[r * Tp + t], an = agg_a(vn, t);
+                        float zn = ((pk_w > 0.f) ? fminf(an, pl) : an) / su;
+                        float kx = VOUT[r * Tp + t];
+                        rRpc = fmaxf(rRpc, fabsf(kx - zn));
+                        rXm = fmaxf(rXm, fabsf(kx));
+                        VOUT[r * Tp + t] = rho * (pre[q] - zn);
+                        rYz += rho * (vn - zn) * zn;
+                    }
+                }
+            }
+        }
+        if (!chk) { __syncthreads(); continue; }
+        // ------------------------------------------------------------- check path
+        rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm);
+        rRpc = warp_max(rRpc); rNan = warp_max(rNan);
+        rCx = warp_sum(rCx); rXx = warp_sum(rXx); rYz = warp_sum(rYz);
+        if (lane == 0) {
+            float* r = RED + warp * ACB_NRED;
+            r[RD_E1] = rE1; r[RD_E2] = rE2; r[RD_XMAX] = rXm; r[RD_ZMAX] = rZm; r[RD_YMAX] = rYm; r[RD_CX] = rCx;
+            r[RD_XX] = rXx; r[RD_YZ] = rYz; r[RD_RPC] = rRpc; r[RD_NAN] = rNan; r[RD_VIOL] = -1.f; r[RD_HD] = 0.f;
+            r[RD_EV] = nEv;
+        }
+        __syncthreads();
+        // violation of the candidate schedule z and |C' delta_c| (columns)
+        {
+            float viol = -1.f, hd = 0.f;
+            for (int t = tid; t < Tp; t += nthreads) {
+                // group sums of z (HG is free here and serves as scratch)
+                for (int g = 0; g < NG; ++g) {
+                    float sz = 0.f;
+                    for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) sz += PART[p * Tp + t];
+                    HG[g * Tp + t] = sz;
+                }
+                int r = 0;
+                for (int j = 0; j < nDisc; ++j, r += 2) {
+                    float ka = 0.f, kb = 0.f;
+                    for (int g = 0; g < NG; ++g) {
+                        float sz = HG[g * Tp + t];
+                        ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz;
+                    }
+                    if (LIM[r] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / LIM[r] - 1.f);
+                }
+                for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
+                    float ka = 0.f;
+                    for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
+                    float cap = (j == nLin) ? PLIM[t] : LIM[r];
+                    if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
+                }
+                for (int g = 0; g < NG; ++g) {
+                    float acc = 0.f;
+                    for (int rr = 0; rr < R; ++rr) acc += CS[rr * NG + g] * VOUT[rr * Tp + t];
+                    hd = fmaxf(hd, fabsf(acc));
+                }
+            }
+            viol = warp_max(viol); hd = warp_max(hd);
+            if (lane == 0) { RED[warp * ACB_NRED + RD_VIOL] = viol; RED[warp * ACB_NRED + RD_HD] = hd; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, cx = 0, xx = 0, yz = 0, rpc = 0, vi = -1.f, hd = 0, nn = 0, ev = 0;
+            for (int w = lane; w < nwarps; w += 32) {
+                const float* r = RED + w * ACB_NRED;
+                e1 = fmaxf(e1, r[RD_E1]); e2 = fmaxf(e2, r[RD_E2]); xm = fmaxf(xm, r[RD_XMAX]); zm = fmaxf(zm, r[RD_ZMAX]);
+                ym = fmaxf(ym, r[RD_YMAX]); cx += r[RD_CX]; xx += r[RD_XX]; yz += r[RD_YZ]; rpc = fmaxf(rpc, r[RD_RPC]);
+                vi = fmaxf(vi, r[RD_VIOL]); hd = fmaxf(hd, r[RD_HD]); nn = fmaxf(nn, r[RD_NAN]); ev += r[RD_EV];
+            }
+            e1 = warp_max(e1); e2 = warp_max(e2); xm = warp_max(xm); zm = warp_max(zm); ym = warp_max(ym);
+            rpc = warp_max(rpc); vi = warp_max(vi); hd = warp_max(hd); nn = warp_max(nn);
+            cx = warp_sum(cx); xx = warp_sum(xx); yz = warp_sum(yz); ev = warp_sum(ev);
+            if (lane == 0) {
+                float rp = fmaxf(e1 + e2, rpc);
+                float rd = rho1 * (fabsf(alpha - 1.f) * e1 + e2) + hd;
+                float pn = fmaxf(fmaxf(xm, zm), 1e-6f);
+                float dn = fmaxf(fmaxf(1.0f, ym), 1e-6f);  // |c|_inf = 1 after cost scaling
+                float gap = 2.f * qd * xx + cx + yz;
+                float gsc = fmaxf(fabsf(qd * xx + cx), fabsf(qd * xx + yz));
+                float rp_rel = rp / (opt.eps_abs / opt.eps_rel + pn);
+                float rd_rel = rd / (opt.eps_abs / opt.eps_rel + dn);
+                float gap_rel = fabsf(gap) / (opt.eps_abs / opt.eps_rel + gsc);
+                SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel; SCAL[SC_GAP] = gap_rel; SCAL[SC_VIOL] = vi;
+                SCAL[SC_EVALS] += ev;
+                float flag = 0.f;
+                if (nn > 0.f || !(rp == rp) || !(rd == rd)) flag = 3.f;
+                else if (rp_rel <= opt.eps_rel && rd_rel <= opt.eps_rel && gap_rel <= opt.eps_rel && vi <= opt.viol_tol) flag = 1.f;
+                else if (opt.adapt_rho) {
+                    float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
+                    if (ratio > 5.f || ratio < 0.2f) {
+                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * ratio, 1e-4f), 1e4f);
+                        flag = 2.f;
+                    }
+                }
+                SCAL[SC_FLAG] = flag;
+            }
+        }
+        __syncthreads();
+        const float flag = SCAL[SC_FLAG];
+        last_rp = SCAL[SC_RP]; last_rd = SCAL[SC_RD]; last_gap = SCAL[SC_GAP]; last_viol = SCAL[SC_VIOL];
+        if (flag == 1.f) { status = ACB_SOLVED; break; }
+        if (flag == 3.f) { status = ACB_NUMERICAL; break; }
+        if (it == opt.max_iter) break;
+        if (flag == 2.f) {
+            // keep y: v <- z + (rho/rho_new)(v - z), then rebuild the column matrix
+            const float rn = SCAL[SC_NEWRHO], f = rho / rn;
+            if (rowWarp) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    const int* sl = SLOT + (warp * TPW + k) * 6;
+                    int row = sl[0];
+                    if (row < 0) continue;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        int t = lane + 32 * q;
+                        if (t >= Tp) continue;
+                        float z = clampf(v1[k][q] - mu_at(sl[4], sl[5], t), LB[row * Tp + t], UB[row * Tp + t]);
+                        v1[k][q] = z + f * (v1[k][q] - z);
+                    }
+                }
+            }
+            const float pl = SCAL[SC_PLEVEL];
+            for (int t = tid; t < Tp; t += nthreads) {
+                int r = 0;
+                for (int j = 0; j < nDisc; ++j, r += 2) {
+                    float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
+                    proj_disc(a, bb, LIM[r], za, zb);
+                    VC[r * Tp + t] = za + f * (a - za); VC[(r + 1) * Tp + t] = zb + f * (bb - zb);
+                }
+                for (int j = 0; j < nLin; ++j, ++r) { float v = VC[r * Tp + t], z = fminf(v, LIM[r]); VC[r * Tp + t] = z + f * (v - z); }
+                if (S.has_pl) { float v = VC[r * Tp + t], z = fminf(v, PLIM[t]); VC[r * Tp + t] = z + f * (v - z); ++r; }
+                if (S.has_u) {
+                    float v = VC[r * Tp + t], a = agg_a(v, t);
+                    float z = ((pk_w > 0.f) ? fminf(a, pl) : a) / su;
+                    // y = rho (v - z) must be preserved under the new rho
+                    VC[r * Tp + t] = z + f * (v - z);
+                }
+            }
+            __syncthreads();
+            rho = rn; rho1 = kappa * rho; dd = 2.f * qd + rho1; inv_d = 1.f / dd;
+            if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_FLAG] = 0.f; }
+            build_matrix();
+        }
+        write_part(0);
+        __syncthreads();
+    }
+    if (it > opt.max_iter) it = opt.max_iter;
+
+    // ------------------------------------------------------------------ epilogue
+    if (rowWarp) {
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int* sl = SLOT + (warp * TPW + k) * 6;
+            int row = sl[0];
+            if (row < 0) continue;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                int t = lane + 32 * q;
+                if (t >= Tp) continue;
+                float z = clampf(v1[k][q] - mu_at(sl[4], sl[5], t), LB[row * Tp + t], UB[row * Tp + t]);
+                B.rates[((size_t)b * N + row) * Tp + t] = z;
+                if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
+            }
+        }
+    }
+    if (B.out_vc) for (int i = tid; i < R * Tp; i += nthreads) B.out_vc[(size_t)b * R * Tp + i] = VC[i];
+    if (B.out_mu) for (int i = tid; i < B.S_max; i += nthreads) B.out_mu[(size_t)b * B.S_max + i] = SESS_MU[i];
+    if (tid == 0) {
+        if (B.out_scal) { B.out_scal[b * 2] = rho; B.out_scal[b * 2 + 1] = SCAL[SC_PLEVEL]; }
+        B.status[b] = status;
+        B.iters[b] = it;
+        float* st = B.stats + (size_t)b * ACB_NSTATS;
+        st[0] = last_rp; st[1] = last_rd; st[2] = last_gap; st[3] = last_viol; st[4] = rho; st[5] = cs;
+        st[6] = SCAL[SC_EVALS]; st[7] = 0.f;
+    }
+}
+
+// charging_rate_bounds as a standalone kernel (parity tests; the solve kernel fuses it)
+__global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) {
+    const int b = blockIdx.x, N = S.N, Tp = B.Tp;
+    const int nS = B.n_sessions[b];
+    float* lbb = lb + (size_t)b * N * Tp;
+    float* ubb = ub + (size_t)b * N * Tp;
+    for (int i = threadIdx.x; i < N * Tp; i += blockDim.x) { lbb[i] = 0.f; ubb[i] = 0.f; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int s = warp; s < nS; s += nwarps) {
+        size_t k = (size_t)b * B.S_max + s;
+        int row = B.sess_row[k], a = B.sess_start[k], len = B.sess_len[k], off = B.sess_rate_off[k];
+        for (int j = lane; j < len; j += 32) {
+            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
+            if (a + j < Tp) { lbb[row * Tp + a + j] = lo; ubb[row * Tp + a + j] = fmaxf(hi, lo); }
+        }
+    }
+}
+
+template <int Q, int TPW>
+static int launch_solve(acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads, size_t smem, cudaStream_t st) {
+    auto kern = acb_solve_kernel<Q, TPW>;
+    ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<batch->B, nthreads, smem, st>>>(site->d, *batch, *opt);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* opt_in, void* stream) {
+    if (!site || !batch || batch->B <= 0 || batch->Tp <= 0 || batch->Tp % 32 != 0) {
+        acb_set_error("acb_solve_batch: bad arguments (Tp must be a positive multiple of 32)");
+        return ACB_E_INVALID;
+    }
+    if ((site->d.has_pl && !batch->peak_limit)) {
+        acb_set_error("acb_solve_batch: site was created with use_peak_row but batch.peak_limit is NULL");
+        return ACB_E_INVALID;
+    }
+    acb_options opt;
+    if (opt_in) opt = *opt_in; else acb_default_options(&opt);
+    ACB_CUDA(cudaSetDevice(site->device));
+    const SiteDev& d = site->d;
+    const int Q = batch->Tp / 32;
+    const int nParts = (d.NG + d.R + ACB_OPP - 1) / ACB_OPP;
+    // threads: enough warps for the EVSE rows, and for one column-pass sweep if possible
+    const int nCT = d.nDisc + d.nLin + d.has_pl + d.has_u;
+    int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
+    int nthreads = std::min(1024, ((want + 31) / 32) * 32);
+    if (d.nRowWarps * 32 > 1024) { acb_set_error("acb_solve_batch: too many EVSE rows for the on-chip path"); return ACB_E_TOO_LARGE; }
+    size_t smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
+    if (smem > 232448) {
+        acb_set_error("acb_solve_batch: instance needs " + std::to_string(smem) + " B of shared memory (> 232448); not supported by the on-chip path");
+        return ACB_E_TOO_LARGE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+#define CASE(QQ, TT) if (Q <= QQ && d.TPW == TT) return launch_solve<QQ, TT>(site, batch, opt_ptr, nthreads, smem, st);
+    const acb_options* opt_ptr = &opt;
+    CASE(1, 2) CASE(5, 2) CASE(9, 2)
+#undef CASE
+    acb_set_error("acb_solve_batch: no kernel instantiation for Tp=" + std::to_string(batch->Tp) + " TPW=" + std::to_string(d.TPW));
+    return ACB_E_TOO_LARGE;
+}
+
+extern "C" int acb_charging_rate_bounds(acb_site* site, const acb_batch* batch, float* lb, float* ub, void* stream) {
+    if (!site || !batch || !lb || !ub) { acb_set_error("acb_charging_rate_bounds: bad arguments"); return ACB_E_INVALID; }
+    ACB_CUDA(cudaSetDevice(site->device));
+    acb_bounds_kernel<<<batch->B, 256, 0, (cudaStream_t)stream>>>(site->d, *batch, lb, ub);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}

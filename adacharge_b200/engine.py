@@ -1,0 +1,356 @@
+"""Host side of the device path: site handles, packing of sessions / objectives into
+staging tensors, and the batched solve / postprocess calls through the C ABI.
+
+PyTorch is used only for device memory, pinned staging buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import Batch, Options
+
+
+def _dev_index(device) -> int:
+    if device is None:
+        return torch.cuda.current_device()
+    d = torch.device(device)
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("adacharge_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device_index: int):
+    return C.c_void_p(torch.cuda.current_stream(device_index).cuda_stream)
+
+
+class Site:
+    """Device-resident constants of one charging site for one problem shape
+    (constraint type, whether a peak-limit row / an aggregate-power row is present)."""
+
+    def __init__(self, infrastructure, constraint_type="SOC", use_peak_row=False, use_agg_row=False, device=None):
+        _require_cuda()
+        L = _cabi.lib()
+        if constraint_type not in ("SOC", "LINEAR"):
+            raise ValueError(
+                "Invalid infrastructure constraint type: {0}. Valid options are SOC or AFFINE.".format(constraint_type)
+            )
+        self.device = _dev_index(device)
+        cm = infrastructure.constraint_matrix
+        has_infra = not (cm is None or np.asarray(cm).shape == (0, 0))  # aco.py:146-150
+        N = len(infrastructure.station_ids)
+        self.N = N
+        if has_infra:
+            cm = np.ascontiguousarray(np.asarray(cm, dtype=np.float64))
+            M = cm.shape[0]
+            limits = np.ascontiguousarray(np.asarray(infrastructure.constraint_limits, dtype=np.float64))
+            if constraint_type == "SOC" and infrastructure.phases is None:
+                raise ValueError("phases is required when using SOC infrastructure constraints.")
+            phases = None if infrastructure.phases is None else np.ascontiguousarray(np.asarray(infrastructure.phases, dtype=np.float64))
+        else:
+            M, cm, limits, phases = 0, None, None, None
+        volt = np.ascontiguousarray(np.asarray(infrastructure.voltages, dtype=np.float64))
+        mp = getattr(infrastructure, "max_pilot", None)
+        mp = None if mp is None else np.ascontiguousarray(np.asarray(mp, dtype=np.float64))
+        ap = getattr(infrastructure, "allowable_pilots", None)
+        off = vals = None
+        if ap is not None and all(a is not None for a in ap) and len(ap) == N:
+            off = np.zeros(N + 1, dtype=np.int32)
+            off[1:] = np.cumsum([len(a) for a in ap])
+            vals = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64) for a in ap]))
+        self.M = M
+        self._keep = (cm, limits, phases, volt, mp, off, vals)
+        h = C.c_void_p()
+
+        def p(a):
+            return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+        _cabi.check(
+            L.acb_site_create(C.byref(h), self.device, N, M, p(cm), p(phases), p(limits), p(volt),
+                              _cabi.ACB_SOC if constraint_type == "SOC" else _cabi.ACB_LINEAR,
+                              int(use_peak_row), int(use_agg_row), p(mp), p(off), p(vals)),
+            "acb_site_create",
+        )
+        self.handle = h
+        dims = [C.c_int() for _ in range(5)]
+        L.acb_site_dims(h, *[C.byref(d) for d in dims])
+        _, _, self.R, self.NG, self.NP = [d.value for d in dims]
+        self.constraint_type = constraint_type
+        self.use_peak_row, self.use_agg_row = bool(use_peak_row), bool(use_agg_row)
+        self.voltages = volt
+        self.has_pilots = off is not None
+
+    def max_horizon(self) -> int:
+        return _cabi.lib().acb_site_max_horizon(self.handle)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            _cabi.lib().acb_site_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_site_cache: Dict = {}
+
+
+def _infra_key(infra):
+    cm = infra.constraint_matrix
+    cmb = b"" if cm is None else np.ascontiguousarray(np.asarray(cm, dtype=np.float64)).tobytes()
+    ph = b"" if infra.phases is None else np.asarray(infra.phases, dtype=np.float64).tobytes()
+    ap = getattr(infra, "allowable_pilots", None)
+    apb = b"" if ap is None or any(a is None for a in ap) else b"|".join(np.asarray(a, dtype=np.float64).tobytes() for a in ap)
+    mp = getattr(infra, "max_pilot", None)
+    return hash((
+        cmb, ph, np.asarray(infra.constraint_limits, dtype=np.float64).tobytes(),
+        np.asarray(infra.voltages, dtype=np.float64).tobytes(), apb,
+        b"" if mp is None else np.asarray(mp, dtype=np.float64).tobytes(), tuple(infra.station_ids),
+    ))
+
+
+def get_site(infra, constraint_type="SOC", use_peak_row=False, use_agg_row=False, device=None) -> Site:
+    key = (_infra_key(infra), constraint_type, bool(use_peak_row), bool(use_agg_row), _dev_index(device) if torch.cuda.is_available() else -1)
+    s = _site_cache.get(key)
+    if s is None:
+        s = Site(infra, constraint_type, use_peak_row, use_agg_row, device)
+        _site_cache[key] = s
+    return s
+
+
+# ----------------------------------------------------------------------------- packing
+@dataclass
+class Instance:
+    """One MPC instance in host form (what build_problem derives from the reference's
+    arguments): sessions as (row, start, len, energy[A*periods], min_rates, max_rates),
+    objective pieces in minimisation form."""
+
+    T: int
+    sess_row: np.ndarray
+    sess_start: np.ndarray
+    sess_len: np.ndarray
+    sess_energy: np.ndarray
+    min_rates: List[np.ndarray]
+    max_rates: List[np.ndarray]
+    alpha: np.ndarray
+    beta: np.ndarray
+    qd: float = 0.0
+    gamma: float = 0.0
+    ext: Optional[np.ndarray] = None
+    peak_w: float = 0.0
+    peak_p0: float = 0.0
+    peak_limit: Optional[np.ndarray] = None
+    sess_order: Optional[np.ndarray] = None  # packed position -> index in the caller's session list
+
+
+def pack_sessions(sessions, infra, period) -> dict:
+    """Session table sorted by EVSE row (the kernel wants each row's sessions
+    contiguous).  Energy in A*periods: remaining_demand / (V_i * period / 1e3 / 60)
+    (aco.py:114-122)."""
+    rows = np.array([infra.get_station_index(s.station_id) for s in sessions], dtype=np.int64)
+    order = np.argsort(rows, kind="stable")
+    volt = np.asarray(infra.voltages, dtype=np.float64)
+    out = dict(sess_row=[], sess_start=[], sess_len=[], sess_energy=[], min_rates=[], max_rates=[], order=order)
+    for j in order:
+        s = sessions[j]
+        i = int(rows[j])
+        rt = int(s.remaining_time)
+        w = volt[i] * period / 1e3 / 60
+        out["sess_row"].append(i)
+        out["sess_start"].append(int(s.arrival_offset))
+        out["sess_len"].append(rt)
+        out["sess_energy"].append(float(s.remaining_demand) / w)
+        mn = np.broadcast_to(np.asarray(s.min_rates, dtype=np.float64), (rt,)) if np.ndim(s.min_rates) == 0 else np.asarray(s.min_rates, dtype=np.float64)[:rt]
+        mx = np.broadcast_to(np.asarray(s.max_rates, dtype=np.float64), (rt,)) if np.ndim(s.max_rates) == 0 else np.asarray(s.max_rates, dtype=np.float64)[:rt]
+        out["min_rates"].append(mn)
+        out["max_rates"].append(mx)
+    return out
+
+
+class PackedBatch:
+    """Pinned host staging + device tensors of a batch; owns the acb_batch struct."""
+
+    def __init__(self, site: Site, instances: Sequence[Instance], Tp: Optional[int] = None, S_max: Optional[int] = None,
+                 want_warm_out=False):
+        self.site = site
+        B = len(instances)
+        Tmax = max(i.T for i in instances)
+        self.Tp = Tp or ((Tmax + 31) // 32) * 32
+        self.S_max = S_max or max(4, max(len(i.sess_row) for i in instances))
+        self.B = B
+        Tp_, S_ = self.Tp, self.S_max
+        f32, i32 = np.float32, np.int32
+        h = {}
+        h["T"] = np.array([i.T for i in instances], dtype=i32)
+        h["n_sessions"] = np.array([len(i.sess_row) for i in instances], dtype=i32)
+        for name in ("sess_row", "sess_start", "sess_len"):
+            a = np.zeros((B, S_), dtype=i32)
+            for b, inst in enumerate(instances):
+                v = getattr(inst, name)
+                a[b, : len(v)] = v
+            h[name] = a
+        a = np.zeros((B, S_), dtype=f32)
+        offs = np.zeros((B, S_), dtype=i32)
+        mins, maxs, o = [], [], 0
+        for b, inst in enumerate(instances):
+            a[b, : len(inst.sess_energy)] = inst.sess_energy
+            for s, (mn, mx) in enumerate(zip(inst.min_rates, inst.max_rates)):
+                offs[b, s] = o
+                mins.append(mn)
+                maxs.append(mx)
+                o += len(mn)
+        h["sess_energy"], h["sess_rate_off"] = a, offs
+        h["min_rates"] = np.concatenate(mins).astype(f32) if mins else np.zeros(1, f32)
+        h["max_rates"] = np.minimum(np.concatenate(maxs), 3.0e38).astype(f32) if maxs else np.zeros(1, f32)
+        for name in ("alpha", "beta"):
+            a = np.zeros((B, Tp_), dtype=f32)
+            for b, inst in enumerate(instances):
+                a[b, : inst.T] = getattr(inst, name)[: inst.T]
+            h[name] = a
+        for name in ("qd", "gamma", "peak_w", "peak_p0"):
+            h[name] = np.array([getattr(i, name) for i in instances], dtype=f32)
+        if any(i.ext is not None for i in instances):
+            a = np.zeros((B, Tp_), dtype=f32)
+            for b, inst in enumerate(instances):
+                if inst.ext is not None:
+                    a[b, : inst.T] = inst.ext[: inst.T]
+            h["ext"] = a
+        if site.use_peak_row:
+            a = np.full((B, Tp_), 3.0e38, dtype=f32)
+            for b, inst in enumerate(instances):
+                if inst.peak_limit is None:
+                    raise ValueError("site was built with a peak-limit row but an instance has no peak_limit")
+                a[b, : inst.T] = np.broadcast_to(np.asarray(inst.peak_limit, dtype=np.float64), (inst.T,))
+            h["peak_limit"] = a
+        self.host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in h.items()}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
+        dev = torch.device("cuda", site.device)
+        self.dev: Dict[str, torch.Tensor] = {}
+        self.device = dev
+        N, R = site.N, site.R
+        self.rates = torch.empty((B, N, Tp_), dtype=torch.float32, device=dev)
+        self.status = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.iters = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.stats = torch.empty((B, _cabi.ACB_NSTATS), dtype=torch.float32, device=dev)
+        self.warm = None
+        self.warm_out = None
+        if want_warm_out:
+            self.warm_out = dict(
+                v1=torch.empty((B, N, Tp_), dtype=torch.float32, device=dev),
+                vc=torch.empty((B, max(R, 1), Tp_), dtype=torch.float32, device=dev),
+                mu=torch.empty((B, S_), dtype=torch.float32, device=dev),
+                scal=torch.empty((B, 2), dtype=torch.float32, device=dev),
+            )
+        self.struct = Batch()
+
+    def upload(self):
+        for k, t in self.host.items():
+            d = self.dev.get(k)
+            if d is None:
+                self.dev[k] = t.to(self.device, non_blocking=True)
+            else:
+                d.copy_(t, non_blocking=True)
+        return self
+
+    def _fill_struct(self):
+        s = self.struct
+        s.B, s.Tp, s.S_max = self.B, self.Tp, self.S_max
+        for name in ("T", "n_sessions", "sess_row", "sess_start", "sess_len", "sess_energy", "sess_rate_off",
+                     "min_rates", "max_rates", "alpha", "beta", "qd", "gamma", "ext", "peak_w", "peak_p0", "peak_limit"):
+            setattr(s, name, _ptr(self.dev.get(name)))
+        w = self.warm or {}
+        s.warm_v1, s.warm_vc, s.warm_mu, s.warm_scal = (_ptr(w.get(k)) for k in ("v1", "vc", "mu", "scal"))
+        o = self.warm_out or {}
+        s.out_v1, s.out_vc, s.out_mu, s.out_scal = (_ptr(o.get(k)) for k in ("v1", "vc", "mu", "scal"))
+        s.rates, s.status, s.iters, s.stats = _ptr(self.rates), _ptr(self.status), _ptr(self.iters), _ptr(self.stats)
+        return s
+
+    def solve(self, options: Optional[Options] = None):
+        """Enqueue the batched solve on the current stream (asynchronous)."""
+        if not self.dev:
+            self.upload()
+        opt = options or _cabi.default_options()
+        _cabi.check(
+            _cabi.lib().acb_solve_batch(self.site.handle, C.byref(self._fill_struct()), C.byref(opt), _stream_ptr(self.site.device)),
+            "acb_solve_batch",
+        )
+        return self
+
+    def bounds(self):
+        """charging_rate_bounds on device -> (lb, ub) tensors [B, N, Tp]."""
+        if not self.dev:
+            self.upload()
+        lb = torch.empty_like(self.rates)
+        ub = torch.empty_like(self.rates)
+        _cabi.check(
+            _cabi.lib().acb_charging_rate_bounds(self.site.handle, C.byref(self._fill_struct()), _ptr(lb), _ptr(ub), _stream_ptr(self.site.device)),
+            "acb_charging_rate_bounds",
+        )
+        return lb, ub
+
+
+# ------------------------------------------------------------------------ postprocessing
+def _as_dev_f64(site: Site, rates) -> torch.Tensor:
+    if isinstance(rates, torch.Tensor):
+        return rates.to(device=torch.device("cuda", site.device), dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(rates, dtype=np.float64))).to(torch.device("cuda", site.device))
+
+
+def project_continuous(site: Site, rates) -> torch.Tensor:
+    r = _as_dev_f64(site, rates)
+    r3 = r if r.dim() == 3 else r.unsqueeze(0)
+    out = torch.empty_like(r3)
+    _cabi.check(_cabi.lib().acb_project_continuous(site.handle, _ptr(r3), _ptr(out), r3.shape[0], r3.shape[2], _stream_ptr(site.device)), "acb_project_continuous")
+    return out if r.dim() == 3 else out[0]
+
+
+def project_discrete(site: Site, rates) -> torch.Tensor:
+    r = _as_dev_f64(site, rates)
+    r3 = r if r.dim() == 3 else r.unsqueeze(0)
+    out = torch.empty_like(r3)
+    _cabi.check(_cabi.lib().acb_project_discrete(site.handle, _ptr(r3), _ptr(out), r3.shape[0], r3.shape[2], _stream_ptr(site.device)), "acb_project_discrete")
+    return out if r.dim() == 3 else out[0]
+
+
+def reallocate(site: Site, mode: int, rates, n_sessions, sess_row, sess_start, sess_ramp, sess_max0, order=None, peak_limit=None) -> torch.Tensor:
+    """rates [B,N,T] float64; per-session arrays [B,S_max] (numpy).  Returns the device tensor."""
+    dev = torch.device("cuda", site.device)
+    r3 = _as_dev_f64(site, rates)
+    B, _, T = r3.shape
+    out = torch.empty_like(r3)
+
+    def up(a, dt):
+        return None if a is None else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).to(dev)
+
+    S_max = int(np.asarray(sess_row).shape[1])
+    t = dict(ns=up(n_sessions, np.int32), row=up(sess_row, np.int32), st=up(sess_start, np.int32), ramp=up(sess_ramp, np.float64),
+             mx=up(sess_max0, np.float64), order=up(order, np.int32), pk=up(peak_limit, np.float64))
+    _cabi.check(
+        _cabi.lib().acb_reallocate(site.handle, mode, _ptr(r3), _ptr(out), B, T, S_max, _ptr(t["ns"]), _ptr(t["row"]), _ptr(t["st"]),
+                                   _ptr(t["ramp"]), _ptr(t["mx"]), _ptr(t["order"]), _ptr(t["pk"]), _stream_ptr(site.device)),
+        "acb_reallocate",
+    )
+    return out
+
+
+def constraints_feasible(site: Site, rates, col=0) -> torch.Tensor:
+    r = _as_dev_f64(site, rates)
+    r3 = r if r.dim() == 3 else r.unsqueeze(0)
+    out = torch.empty((r3.shape[0],), dtype=torch.int32, device=r3.device)
+    _cabi.check(_cabi.lib().acb_constraints_feasible(site.handle, _ptr(r3), r3.shape[0], r3.shape[2], col, _ptr(out), _stream_ptr(site.device)), "acb_constraints_feasible")
+    return out

@@ -1,0 +1,153 @@
+/* adacharge_b200 — C ABI of the B200-native MPC solve + postprocessing path.
+ *
+ * The reference (caltech-netlab/adacharge) is pure Python; it has no FFI of its own.
+ * These entry points are what a binding for its hot path would call; each one names
+ * the reference function(s) it replaces (paths relative to the reference repo):
+ *
+ *   acb_site_create / acb_site_destroy
+ *       the per-site constants every reference call rebuilds from InfrastructureInfo:
+ *       a_j = [v cos(phi); v sin(phi)] rows   adacharge/adaptive_charging_optimization.py:152-164
+ *       |v| rows (LINEAR)                       adacharge/adaptive_charging_optimization.py:165-172
+ *       voltages -> kW per A                    adacharge/adaptive_charging_optimization.py:336-339
+ *       max_pilot / allowable_pilots            adacharge/postprocessing.py:92,114,176
+ *   acb_charging_rate_bounds
+ *       AdaptiveChargingOptimization.charging_rate_bounds        ...optimization.py:45-79
+ *   acb_solve_batch
+ *       build_problem + solve (cvxpy canonicalisation + ECOS)    ...optimization.py:220-321
+ *       objective library quick_charge ... load_flattening        ...optimization.py:363-408
+ *   acb_project_continuous      project_into_continuous_feasible_pilots   postprocessing.py:77-94
+ *   acb_project_discrete        project_into_discrete_feasible_pilots     postprocessing.py:97-118
+ *   acb_reallocate              index_based_reallocation / diff_based_reallocation
+ *                                                                 postprocessing.py:121-258
+ *   acb_constraints_feasible    infrastructure_constraints_feasible       utils.py:5-12
+ *
+ * Conventions: plain C, no exceptions; every function returns 0 on success or a
+ * negative ACB_E_* code (acb_last_error() gives text).  Unless a parameter is marked
+ * "host", data pointers are DEVICE pointers on the site's device; work is enqueued on
+ * the given cudaStream_t (passed as void*) and is asynchronous.  Re-entrant per
+ * (site, stream); no global mutable state except the last-error string.
+ */
+#ifndef ADACHARGE_B200_H
+#define ADACHARGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACB_OK 0
+#define ACB_E_INVALID -1   /* bad argument */
+#define ACB_E_CUDA -2      /* CUDA runtime error */
+#define ACB_E_TOO_LARGE -3 /* instance does not fit the on-chip solve path */
+
+#define ACB_SOC 0
+#define ACB_LINEAR 1
+
+/* per-instance solve status written to acb_batch.status */
+#define ACB_SOLVED 0
+#define ACB_MAX_ITER 1   /* iteration limit hit; residuals are in stats */
+#define ACB_INFEASIBLE 2 /* primal infeasibility detected */
+#define ACB_NUMERICAL 3  /* non-finite iterate */
+
+#define ACB_NSTATS 8 /* stats row: r_prim, r_dual, gap, violation, rho, cost_scale, newton_evals, reserved */
+
+typedef struct acb_site acb_site;
+
+/* Site constants (all pointers host).  constraint_matrix is M x N row-major and may be
+ * NULL when M == 0.  allow_off (N+1) / allow_vals is a CSR list of each EVSE's sorted
+ * allowable pilots (may be NULL if discrete postprocessing is not used).
+ * use_peak_row: the solve has a peak_limit (sum_i rates <= P_t).  use_agg_row: the
+ * objective uses aggregate power (peak / demand_charge / load_flattening). */
+int acb_site_create(acb_site** out, int device, int N, int M, const double* constraint_matrix,
+                    const double* phases_deg, const double* limits, const double* voltages,
+                    int constraint_type, int use_peak_row, int use_agg_row,
+                    const double* max_pilot, const int32_t* allow_off, const double* allow_vals);
+void acb_site_destroy(acb_site* site);
+/* R = coupling rows, NG = electrically distinct EVSE groups, NP = partial rows. */
+int acb_site_dims(const acb_site* site, int* N, int* M, int* R, int* NG, int* NP);
+/* Largest padded horizon (multiple of 32) that fits on chip for this site, 0 if none. */
+int acb_site_max_horizon(const acb_site* site);
+
+typedef struct acb_options {
+    float eps_abs;      /* absolute residual tolerance (scaled units), e.g. 1e-5 */
+    float eps_rel;      /* relative residual / gap tolerance, e.g. 1e-4 */
+    float viol_tol;     /* max relative infrastructure / peak violation of the returned schedule */
+    float rho0;         /* initial penalty */
+    float kappa;        /* identity-block penalty = kappa * rho */
+    float alpha;        /* over-relaxation in (0, 2) */
+    int32_t max_iter;
+    int32_t check_every; /* residual check period (iterations) */
+    int32_t equality;    /* enforce_energy_equality */
+    int32_t adapt_rho;   /* 1 = residual balancing */
+} acb_options;
+
+void acb_default_options(acb_options* o);
+
+/* One batch of independent MPC instances on one site.  Horizon arrays are padded to
+ * Tp (multiple of 32, >= every T[b]); session arrays to S_max.  Objective in
+ * minimisation form per instance:
+ *   sum_it (alpha_t + k_i beta_t) r_it + qd sum r_it^2 + gamma sum_t (u_t + ext_t)^2
+ *   + peak_w * max(max_t u_t, peak_p0),           u_t = sum_i k_i r_it  (kW)
+ */
+typedef struct acb_batch {
+    int32_t B, Tp, S_max;
+    const int32_t* T;            /* [B] horizon (reference: aco.py:243-245) */
+    const int32_t* n_sessions;   /* [B] */
+    const int32_t* sess_row;     /* [B*S_max] EVSE index */
+    const int32_t* sess_start;   /* [B*S_max] arrival_offset */
+    const int32_t* sess_len;     /* [B*S_max] remaining_time */
+    const float* sess_energy;    /* [B*S_max] remaining_demand in A*periods */
+    const int32_t* sess_rate_off;/* [B*S_max] offset into min_rates/max_rates */
+    const float* min_rates;      /* flat, per session remaining_time entries */
+    const float* max_rates;
+    const float* alpha;          /* [B*Tp] */
+    const float* beta;           /* [B*Tp] */
+    const float* qd;             /* [B] */
+    const float* gamma;          /* [B] */
+    const float* ext;            /* [B*Tp] or NULL */
+    const float* peak_w;         /* [B] */
+    const float* peak_p0;        /* [B] */
+    const float* peak_limit;     /* [B*Tp] or NULL (required iff use_peak_row) */
+    /* warm start (all optional, NULL = cold).  Layout: v1 [B][N][Tp], vc [B][R][Tp],
+     * mu [B][S_max], scal [B][2] = {rho, peak level}. */
+    const float* warm_v1; const float* warm_vc; const float* warm_mu; const float* warm_scal;
+    float* out_v1; float* out_vc; float* out_mu; float* out_scal;
+    /* results */
+    float* rates;                /* [B][N][Tp] */
+    int32_t* status;             /* [B] */
+    int32_t* iters;              /* [B] */
+    float* stats;                /* [B][ACB_NSTATS] */
+} acb_batch;
+
+int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* opt, void* stream);
+
+/* lb/ub [B][N][Tp] from the session tables of a batch (only the session fields, B, Tp,
+ * S_max, T and n_sessions are read). */
+int acb_charging_rate_bounds(acb_site* site, const acb_batch* batch, float* lb, float* ub, void* stream);
+
+/* Postprocessing, float64 like the reference.  rates_* are [B][N][T] row-major. */
+int acb_project_continuous(acb_site* site, const double* rates_in, double* rates_out, int B, int T, void* stream);
+int acb_project_discrete(acb_site* site, const double* rates_in, double* rates_out, int B, int T, void* stream);
+
+/* Greedy first-period reallocation.  mode 0 = index based (rates modified in place,
+ * order[] given by the caller, peak_limit[b] given); mode 1 = diff based (rates_in is
+ * the continuous schedule, rates_out receives the rounded + reallocated schedule, order
+ * and peak limit are derived on device).  Per-session arrays are [B][S_max]:
+ * sess_row, sess_start (arrival_offset), sess_ramp (interface.remaining_amp_periods),
+ * sess_max0 (max_rates[0]); order [B][S_max] holds session indices (mode 0 only). */
+int acb_reallocate(acb_site* site, int mode, const double* rates_in, double* rates_out, int B, int T,
+                   int S_max, const int32_t* n_sessions, const int32_t* sess_row, const int32_t* sess_start,
+                   const double* sess_ramp, const double* sess_max0, const int32_t* order,
+                   const double* peak_limit, void* stream);
+
+/* feasible[b] = 1 iff every SOC line current of column `col` is <= limit + 1e-7. */
+int acb_constraints_feasible(acb_site* site, const double* rates, int B, int T, int col, int32_t* feasible, void* stream);
+
+const char* acb_last_error(void);
+int acb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -24,8 +24,8 @@ Objective components are identified by the reference function names; the
 coefficient/kwargs semantics are those of ObjectiveComponent (aco.py:12-15) with
 component kwargs overriding caller kwargs (aco.py:203-217).
 ``non_completion_penalty`` does not exist in the reference (SURVEY.md §8(a) A14);
-it is defined by this project as  -sum_s (remaining_demand_s - E_s(R))^2  (kWh^2),
-or  -sum_s |remaining_demand_s - E_s(R)|  with kwarg ``norm=1``.
+it is defined by this project as  -sum_s |remaining_demand_s - E_s(R)|  (kWh)
+(default, ``norm=1``; linear under the energy rows) or the sum of squares with ``norm=2``.
 """
 from __future__ import annotations
 
@@ -118,7 +118,7 @@ def objective_terms(objective, infra, interface, T, sessions=None, prev_peak=0):
         elif fn == "non_completion_penalty":  # project-defined, see module docstring
             if coef < 0:
                 raise ValueError("non_completion_penalty with negative coefficient is not concave")
-            out["ncp"].append((coef, int(kw.get("norm", 2))))
+            out["ncp"].append((coef, int(kw.get("norm", 1))))
         else:
             raise ValueError(f"unknown objective component {fn}")
     if out["diag_q"] < 0:
