@@ -1,0 +1,159 @@
+"""CUDA MPC solve (AdaptiveChargingOptimization.solve -> C ABI) against the reference's
+solver scenarios, the oracle and oracle-produced golden vectors.
+
+Tolerances (BASELINE.json north_star): objective within 1e-4 relative, rates within
+1e-3 A where the optimum is unique, constraint violation <= 1e-5 of each limit."""
+import numpy as np
+import pytest
+
+import adacharge_b200 as ab
+from adacharge_b200 import engine
+from adacharge_b200.generators import config_c1, config_c2, caltech_acn_infrastructure
+from oracle import mpc
+from tests.scenarios import SCENARIOS, INFEASIBLE, make_interface, check_properties
+
+pytestmark = pytest.mark.gpu
+OBJ_TOL, VIOL_TOL, RATE_TOL = 1e-4, 1e-5, 1e-3
+
+
+def _components(spec):
+    return [ab.ObjectiveComponent(getattr(ab, n), c, k) for n, c, k in spec]
+
+
+def _solve(sc, **opts):
+    iface = make_interface(sc)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    aco = ab.AdaptiveChargingOptimization(_components(sc["objective"]), iface, sc.get("constraint_type", "SOC"),
+                                          sc.get("equality", False), solver_options=opts)
+    R = aco.solve(S, I, peak_limit=sc.get("peak_limit"))
+    return R, iface, S, I, aco
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_reference_scenarios(require_gpu, name):
+    sc = SCENARIOS[name]
+    R, iface, S, I, aco = _solve(sc)
+    assert R.dtype == np.float64 and R.shape == (I.num_stations, mpc.horizon(S))
+    check_properties(R, sc, iface)
+    v = mpc.violations(R, S, I, iface, sc.get("constraint_type", "SOC"), sc.get("peak_limit"), sc.get("equality", False))
+    assert v["infrastructure_rel"] <= VIOL_TOL and v.get("peak_rel", 0) <= VIOL_TOL and v["lb"] <= 0 and v["ub"] <= 0, v
+    # objective parity with the oracle
+    Ro = mpc.solve_mpc(sc["objective"], S, I, iface, sc.get("constraint_type", "SOC"), sc.get("equality", False), sc.get("peak_limit"), 0)
+    f, fo = (mpc.evaluate_objective(X, sc["objective"], I, iface) for X in (R, Ro))
+    assert abs(f - fo) <= OBJ_TOL * max(abs(fo), 1e-9), (f, fo, aco.last_info)
+
+
+@pytest.mark.parametrize("name", list(INFEASIBLE))
+def test_infeasible_raises(require_gpu, name):
+    with pytest.raises(ab.InfeasibilityException):
+        _solve(INFEASIBLE[name], max_iter=4000)
+
+
+def test_kat1_rates(require_gpu):
+    R, *_ = _solve(SCENARIOS["tiny_feasible"], eps_rel=1e-5)
+    need = 3.3 / (208 * 5 / 1e3 / 60)
+    row = np.array([32.0] * 5 + [need - 160] + [0.0] * 6)
+    assert np.abs(R - np.stack([row, row])).max() <= RATE_TOL
+
+
+def _golden_case(g):
+    d = config_c1(g["seed"]) if g["config"] == "c1" else config_c2(g["seed"], infra=caltech_acn_infrastructure(transformer_cap=g["transformer_cap"]))
+    iface = ab.TestingInterface(d)
+    return iface, iface.active_sessions(), iface.infrastructure_info()
+
+
+def test_oracle_golden_objective_and_feasibility(require_gpu, mpc_golden):
+    for g in mpc_golden:
+        iface, S, I = _golden_case(g)
+        obj = [tuple(o) for o in g["objective"]]
+        aco = ab.AdaptiveChargingOptimization(_components(obj), iface)
+        R = aco.solve(S, I, prev_peak=iface.get_prev_peak())
+        f = mpc.evaluate_objective(R, obj, I, iface, S, iface.get_prev_peak())
+        fo = g["oracle_objective"]
+        assert abs(f - fo) <= OBJ_TOL * abs(fo), (g["config"], g["seed"], f, fo, aco.last_info)
+        v = mpc.violations(R, S, I, iface)
+        assert v["infrastructure_rel"] <= VIOL_TOL and v["energy"] <= 1e-4 and v["lb"] <= 0 and v["ub"] <= 0, v
+
+
+def test_unique_optimum_rates_within_1e3(require_gpu, mpc_golden):
+    """quick_charge + 1e-3 equal_share is strictly concave: the optimum is unique and the
+    schedule itself must match the oracle."""
+    for g in [g for g in mpc_golden if g["config"] == "c1"]:
+        iface, S, I = _golden_case(g)
+        obj = [tuple(o) for o in g["objective"]]
+        aco = ab.AdaptiveChargingOptimization(_components(obj), iface, solver_options=dict(eps_rel=2e-6, eps_abs=1e-7, max_iter=60000))
+        R = aco.solve(S, I)
+        assert np.abs(R - np.array(g["rates"])).max() <= RATE_TOL, (np.abs(R - np.array(g["rates"])).max(), aco.last_info)
+
+
+def test_bounds_kernel_matches_reference_rule(require_gpu):
+    # two sessions on one EVSE, a min rate above the max rate (ub < lb patch, aco.py:75)
+    from adacharge_b200.generators import session_generator, single_phase_single_constraint
+
+    sessions = session_generator(3, [0, 14, 2], [12, 20, 9], [3.3] * 3, [3.3] * 3, [32, 4, 16], min_rates=[0, 6, 8], station_ids=["0", "0", "2"])
+    iface = ab.TestingInterface({"active_sessions": sessions, "infrastructure_info": single_phase_single_constraint(3, 64), "current_time": 0, "period": 5})
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    aco = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(ab.quick_charge)], iface)
+    inst = aco.build_instance(S, I)
+    pb = engine.PackedBatch(aco._site_for(I, inst), [inst])
+    lb, ub = pb.bounds()
+    lbo, ubo = mpc.bounds(S, I.station_ids, inst.T)
+    np.testing.assert_array_equal(lb[0, :, : inst.T].cpu().numpy(), lbo.astype(np.float32))
+    np.testing.assert_array_equal(ub[0, :, : inst.T].cpu().numpy(), ubo.astype(np.float32))
+    assert not lb[0, :, inst.T:].any() and not ub[0, :, inst.T:].any()
+
+
+def test_batch_equals_single_and_is_deterministic(require_gpu):
+    obj = [ab.ObjectiveComponent(ab.tou_energy_cost), ab.ObjectiveComponent(ab.total_energy, 0.3), ab.ObjectiveComponent(ab.demand_charge, 1 / 30)]
+    insts, singles = [], []
+    for seed in range(6):
+        iface = ab.TestingInterface(config_c2(seed))
+        S, I = iface.active_sessions(), iface.infrastructure_info()
+        aco = ab.AdaptiveChargingOptimization(obj, iface)
+        insts.append(aco.build_instance(S, I, None, iface.get_prev_peak()))
+        singles.append(aco.solve(S, I, prev_peak=iface.get_prev_peak()))
+    pb = engine.PackedBatch(aco._site_for(I, insts[0]), insts).upload().solve()
+    a = pb.rates.cpu().numpy().copy()
+    pb.solve()
+    np.testing.assert_array_equal(a, pb.rates.cpu().numpy())
+    assert (pb.status.cpu().numpy() == 0).all()
+    for b, inst in enumerate(insts):
+        np.testing.assert_array_equal(a[b, :, : inst.T].astype(np.float64), singles[b])
+
+
+def test_full_size_properties_all_objectives(require_gpu):
+    """54 x 288 CaltechACN instance, every built-in objective component at once, with a
+    peak limit: size-independent properties (bounds, windows, energy caps, limits)."""
+    d = config_c2(31, infra=caltech_acn_infrastructure(transformer_cap=60))
+    iface = ab.TestingInterface(d)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    T = mpc.horizon(S)
+    ext = 30 + 20 * np.sin(np.arange(T) / 20.0)
+    spec = [("quick_charge", 1e-3, {}), ("equal_share", 1e-4, {}), ("tou_energy_cost", 1, {}), ("total_energy", 0.3, {}),
+            ("demand_charge", 1 / 30, {}), ("load_flattening", 1e-4, {"external_signal": ext}), ("non_completion_penalty", 0.05, {})]
+    aco = ab.AdaptiveChargingOptimization(_components(spec), iface)
+    R = aco.solve(S, I, peak_limit=250.0, prev_peak=iface.get_prev_peak())
+    v = mpc.violations(R, S, I, iface, "SOC", 250.0)
+    assert v["lb"] <= 0 and v["ub"] <= 0 and v["energy"] <= 1e-4 and v["infrastructure_rel"] <= VIOL_TOL and v["peak_rel"] <= VIOL_TOL, v
+    Ro = mpc.solve_mpc(spec, S, I, iface, "SOC", False, 250.0, iface.get_prev_peak())
+    f, fo = (mpc.evaluate_objective(X, spec, I, iface, S, iface.get_prev_peak()) for X in (R, Ro))
+    assert abs(f - fo) <= OBJ_TOL * abs(fo), (f, fo, aco.last_info)
+
+
+def test_schedule_adapter_end_to_end(require_gpu):
+    """AdaptiveSchedulingAlgorithm.schedule: continuous, quantised and reallocated modes
+    (ada.py:135-193) on a CaltechACN step; pilots must be allowable and the network feasible."""
+    d = config_c2(41, infra=caltech_acn_infrastructure(transformer_cap=50))
+    iface = ab.TestingInterface(d)
+    obj = [ab.ObjectiveComponent(ab.quick_charge), ab.ObjectiveComponent(ab.equal_share, 1e-6)]
+    for kw in (dict(), dict(quantize=True), dict(quantize=True, reallocate=True)):
+        alg = ab.AdaptiveSchedulingAlgorithm(obj, **kw)
+        alg.register_interface(iface)
+        sched = alg.run()
+        I = iface.infrastructure_info()
+        assert set(sched) == set(I.station_ids)
+        first = np.array([sched[s][0] for s in I.station_ids])
+        assert ab.infrastructure_constraints_feasible(first * (1 - 2e-5), I)
+        if kw:
+            for i, s in enumerate(I.station_ids):
+                assert np.isin(sched[s], I.allowable_pilots[i]).all()

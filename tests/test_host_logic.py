@@ -1,0 +1,169 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol of
+include/adacharge_b200.h, objective / session packing, API error rules, fixtures."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import adacharge_b200 as ab
+from adacharge_b200 import _cabi, engine
+from adacharge_b200.generators import (
+    session_generator, single_phase_single_constraint, three_phase_balanced_network, caltech_acn_infrastructure,
+    hierarchical_three_phase_network, config_c1, config_c2, config_c5,
+)
+from oracle import mpc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "adacharge_b200.h")).read()
+    declared = set(re.findall(r"\b(acb_[a-z_]+)\s*\(", hdr))
+    assert declared >= set(_cabi.EXPORTS)
+    L = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _cabi.lib().acb_version() >= 100
+
+
+def test_default_options_struct_layout():
+    o = _cabi.default_options(max_iter=123, equality=1)
+    assert o.max_iter == 123 and o.equality == 1 and abs(o.eps_rel - 1e-4) < 1e-9
+    with pytest.raises(TypeError):
+        _cabi.default_options(bogus=1)
+
+
+def test_pack_objective_matches_oracle_terms():
+    d = config_c2(3)
+    iface = ab.TestingInterface(d)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    T = mpc.horizon(S)
+    ext = np.linspace(0, 40, T)
+    obj = [ab.ObjectiveComponent(ab.quick_charge, 2.0), ab.ObjectiveComponent(ab.equal_share, 0.1),
+           ab.ObjectiveComponent(ab.tou_energy_cost, 1.5), ab.ObjectiveComponent(ab.total_energy, 3.0),
+           ab.ObjectiveComponent(ab.demand_charge, 0.7), ab.ObjectiveComponent(ab.load_flattening, 0.2, {"external_signal": ext}),
+           ab.ObjectiveComponent(ab.non_completion_penalty, 0.4)]
+    p = ab.pack_objective(obj, I, iface, T, prev_peak=iface.get_prev_peak())
+    terms = mpc.objective_terms([(c.function.__name__, c.coefficient, c.kwargs) for c in obj], I, iface, T, S, iface.get_prev_peak())
+    k = np.asarray(I.voltages) / 1e3
+    lin = p["alpha"][None, :] + k[:, None] * p["beta"][None, :]
+    # non_completion_penalty(norm=1) is linear: the oracle keeps it separate, add it here
+    lin_oracle = terms["lin"] - 0.4 * (k * 5 / 60)[:, None]
+    assert np.allclose(lin, lin_oracle, rtol=1e-12, atol=1e-12)
+    assert p["qd"] == pytest.approx(terms["diag_q"])
+    assert p["gamma"] == pytest.approx(0.2) and np.allclose(p["ext"], ext)
+    assert p["peak_w"] == pytest.approx(0.7 * 15.51) and p["peak_p0"] == pytest.approx(terms["peaks"][0][1])
+
+
+def test_numeric_objectives_equal_oracle_evaluation():
+    d = config_c2(4)
+    iface = ab.TestingInterface(d)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    T = mpc.horizon(S)
+    R = np.random.default_rng(1).uniform(0, 32, (54, T))
+    for fn in (ab.quick_charge, ab.equal_share, ab.tou_energy_cost, ab.total_energy, ab.demand_charge, ab.load_flattening,
+               ab.non_completion_penalty):
+        assert fn(R, I, iface) == pytest.approx(mpc.evaluate_objective(R, [(fn.__name__, 1, {})], I, iface, S), rel=1e-12)
+
+
+def test_unknown_objective_is_rejected_loudly():
+    iface = ab.TestingInterface(config_c1(0))
+    with pytest.raises(TypeError, match="kernel spec"):
+        ab.pack_objective([ab.ObjectiveComponent(lambda rates, infra, iface, **kw: 0.0)], iface.infrastructure_info(), iface, 10)
+
+
+def test_nonconcave_components_are_rejected():
+    iface = ab.TestingInterface(config_c2(0))
+    I = iface.infrastructure_info()
+    with pytest.raises(ValueError):
+        ab.pack_objective([ab.ObjectiveComponent(ab.peak, 1.0)], I, iface, 10)
+    with pytest.raises(ValueError):
+        ab.pack_objective([ab.ObjectiveComponent(ab.equal_share, -1.0)], I, iface, 10)
+
+
+def test_component_kwargs_override_caller_kwargs():  # aco.py:203-217
+    iface = ab.TestingInterface(config_c2(0))
+    I = iface.infrastructure_info()
+    p = ab.pack_objective([ab.ObjectiveComponent(ab.demand_charge, 1.0, {"baseline_peak": 500.0})], I, iface, 10, baseline_peak=1.0)
+    assert p["peak_p0"] == 500.0
+
+
+def test_pack_sessions_sorted_by_row_and_units():
+    d = config_c2(7)
+    iface = ab.TestingInterface(d)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    ps = engine.pack_sessions(S, I, iface.period)
+    assert list(ps["sess_row"]) == sorted(ps["sess_row"])
+    j = ps["order"][0]
+    assert ps["sess_energy"][0] == pytest.approx(S[j].remaining_demand / (208 * 5 / 1e3 / 60))
+
+
+def test_session_info_semantics():
+    s = ab.SessionInfo("a", "b", 10, 4, arrival=3, departure=20, current_time=5, max_rates=32)
+    assert (s.arrival_offset, s.remaining_time, s.remaining_demand) == (0, 15, 6)
+    assert len(s.max_rates) == 15
+    s = ab.SessionInfo("a", "b", 10, 4, arrival=8, departure=20, current_time=5)
+    assert (s.arrival_offset, s.remaining_time) == (3, 12)
+
+
+def test_solve_without_sessions_returns_zero_column():  # aco.py:310-311 (no GPU needed)
+    iface = ab.TestingInterface(config_c1(0))
+    out = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(ab.quick_charge)], iface).solve([], iface.infrastructure_info())
+    assert out.shape == (30, 1) and not out.any()
+
+
+def test_schedule_without_sessions_and_ctor_rules():  # ada.py:101-113, 137-138
+    alg = ab.AdaptiveSchedulingAlgorithm([ab.ObjectiveComponent(ab.quick_charge)])
+    assert alg.schedule([]) == {}
+    with pytest.raises(ValueError):
+        ab.AdaptiveSchedulingAlgorithm([], quantize=False, reallocate=True)
+    with pytest.warns(UserWarning):
+        a = ab.AdaptiveSchedulingAlgorithm([], quantize=True, max_recompute=5)
+    assert a.max_recompute == 1
+
+
+def test_offline_schedule_lookup_and_errors():  # ada.py:278-294, t_int.py:290-308
+    from unittest.mock import Mock
+
+    alg = ab.AdaptiveChargingAlgorithmOffline([])
+    with pytest.raises(ValueError):
+        alg.schedule([])
+    alg.internal_schedule = {"s1": np.arange(10.0), "s2": np.arange(10.0) * 2}
+    alg.session_ids = {"a", "b"}
+    iface = Mock(); iface.current_time = 3
+    alg.register_interface(iface)
+    evs = [Mock(station_id="s1", session_id="a"), Mock(station_id="s2", session_id="b")]
+    assert alg.schedule(evs) == {"s1": [3.0], "s2": [6.0]}
+    with pytest.raises(ValueError):
+        alg.schedule([Mock(station_id="s1", session_id="zzz")])
+
+
+def test_fixture_networks():
+    infra = three_phase_balanced_network(1, 16.51 * np.sqrt(3))
+    a = mpc.soc_rows(ab.TestingInterface({"infrastructure_info": infra, "active_sessions": [], "period": 5}).infrastructure_info())
+    cur = lambda r: np.hypot(a[:, 0] @ r, a[:, 1] @ r).max()
+    assert cur(np.array([16.0, 16, 16])) == pytest.approx(27.7128, abs=1e-3)
+    assert cur(np.array([17.0, 16, 16])) == pytest.approx(28.583, abs=1e-3)
+    assert cur(np.array([17.0, 17, 16])) > 16.51 * np.sqrt(3)
+    c = caltech_acn_infrastructure()
+    assert c["constraint_matrix"].shape == (8, 54) and c["constraint_limits"][0] == pytest.approx(416.667, abs=1e-3)
+    assert c["constraint_limits"][3] == pytest.approx(180.505, abs=1e-3)
+    h = hierarchical_three_phase_network(1000)
+    assert h["constraint_matrix"].shape == (50 + 30 + 6, 1000)
+
+
+def test_generators_are_seeded_and_shaped():
+    for cfg, T in ((config_c1, 144), (config_c2, 288), (config_c5, 288)):
+        a, b = cfg(3), cfg(3)
+        assert a["active_sessions"] == b["active_sessions"]
+        iface = ab.TestingInterface(a)
+        assert mpc.horizon(iface.active_sessions()) == T
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.NativeLibraryMissing):
+        _cabi.lib()
