@@ -172,6 +172,28 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
         SLOT[tid * 6 + 4] = first < 0 ? 0 : first;
         SLOT[tid * 6 + 5] = cnt;
     }
+    if (tid == 0) SCAL[SC_FLAG] = 0.f;
+    __syncthreads();
+    // row-level infeasibility: a session whose window cannot hold its energy equality, or whose
+    // minimum rates already exceed its energy cap (the reference would get INFEASIBLE from ECOS)
+    for (int s = warp; s < nS; s += nwarps) {
+        int row = B.sess_row[(size_t)b * B.S_max + s];
+        float slo = 0.f, shi = 0.f;
+        for (int t = SESS_A[s] + lane; t < min(SESS_B[s], Tp); t += 32) { slo += LB[row * Tp + t]; shi += UB[row * Tp + t]; }
+        slo = warp_sum(slo); shi = warp_sum(shi);
+        const float Eb = SESS_E[s], tol = 1e-5f * (fabsf(Eb) + 1.f);
+        if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) SCAL[SC_FLAG] = 1.f;
+    }
+    __syncthreads();
+    if (SCAL[SC_FLAG] != 0.f) {
+        for (int i = tid; i < N * Tp; i += nthreads) B.rates[(size_t)b * N * Tp + i] = 0.f;
+        if (tid == 0) {
+            B.status[b] = ACB_INFEASIBLE;
+            B.iters[b] = 0;
+            for (int k = 0; k < ACB_NSTATS; ++k) B.stats[(size_t)b * ACB_NSTATS + k] = 0.f;
+        }
+        return;
+    }
     // cost scale = 1 / max |alpha_t + k_g beta_t|
     {
         float m = 0.f;

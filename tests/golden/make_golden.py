@@ -166,12 +166,13 @@ def main():
 
     obj1 = [("quick_charge", 1, {}), ("equal_share", 1e-3, {})]
     obj2 = [("tou_energy_cost", 1, {}), ("total_energy", 0.3, {}), ("demand_charge", 1 / 30, {})]
+    obj1s = [("quick_charge", 1, {}), ("equal_share", 0.05, {})]  # strongly concave: well-conditioned unique optimum
     gold = []
-    for cfg, seed, cap in (("c1", 0, None), ("c1", 1, None), ("c2", 1, 150), ("c2", 2, 40), ("c2", 3, 60)):
-        d = config_c1(seed) if cfg == "c1" else config_c2(seed, infra=caltech_acn_infrastructure(transformer_cap=cap))
+    for cfg, seed, cap in (("c1", 0, None), ("c1", 1, None), ("c1s", 0, None), ("c1s", 2, None), ("c2", 1, 150), ("c2", 2, 40), ("c2", 3, 60)):
+        d = config_c1(seed) if cfg.startswith("c1") else config_c2(seed, infra=caltech_acn_infrastructure(transformer_cap=cap))
         iface = shim.TestingInterface(d)
         S, I = iface.active_sessions(), iface.infrastructure_info()
-        obj = obj1 if cfg == "c1" else obj2
+        obj = obj1 if cfg == "c1" else (obj1s if cfg == "c1s" else obj2)
         R = mpc.solve_mpc(obj, S, I, iface, prev_peak=iface.get_prev_peak())
         gold.append(dict(config=cfg, seed=seed, transformer_cap=cap, objective=obj,
                          oracle_objective=mpc.evaluate_objective(R, obj, I, iface, S, iface.get_prev_peak()), rates=R))
