@@ -29,7 +29,7 @@ class Options(C.Structure):
     _fields_ = [
         ("eps_abs", C.c_float), ("eps_rel", C.c_float), ("viol_tol", C.c_float), ("rho0", C.c_float),
         ("kappa", C.c_float), ("alpha", C.c_float), ("max_iter", C.c_int32), ("check_every", C.c_int32),
-        ("equality", C.c_int32), ("adapt_rho", C.c_int32),
+        ("equality", C.c_int32), ("adapt_rho", C.c_int32), ("restart", C.c_int32), ("avg_every", C.c_int32),
     ]
 
 
@@ -42,7 +42,7 @@ class Batch(C.Structure):
         ("T", _P), ("n_sessions", _P), ("sess_row", _P), ("sess_start", _P), ("sess_len", _P),
         ("sess_energy", _P), ("sess_rate_off", _P), ("min_rates", _P), ("max_rates", _P),
         ("alpha", _P), ("beta", _P), ("qd", _P), ("gamma", _P), ("ext", _P), ("peak_w", _P), ("peak_p0", _P),
-        ("peak_limit", _P),
+        ("peak_limit", _P), ("work", _P),
         ("warm_v1", _P), ("warm_vc", _P), ("warm_mu", _P), ("warm_scal", _P),
         ("out_v1", _P), ("out_vc", _P), ("out_mu", _P), ("out_scal", _P),
         ("rates", _P), ("status", _P), ("iters", _P), ("stats", _P),

@@ -343,7 +343,8 @@ class AdaptiveChargingOptimization:
         status = int(pb.status[0].item())
         stats = pb.stats[0].cpu().numpy()
         self.last_info = dict(status=status, iters=int(pb.iters[0].item()), r_prim=float(stats[0]), r_dual=float(stats[1]),
-                              gap=float(stats[2]), violation=float(stats[3]), rho=float(stats[4]))
+                              gap=float(stats[2]), violation=float(stats[3]), rho=float(stats[4]), restarts=int(stats[6]),
+                              averaged=bool(stats[7]))
         if verbose:
             print(self.last_info)
         check_status(status, self.last_info)
@@ -355,11 +356,12 @@ _STATUS_NAME = {0: "optimal", 1: "iteration_limit", 2: "infeasible", 3: "numeric
 
 def check_status(status: int, info: dict):
     """Solve failed -> InfeasibilityException, as aco.py:319-320 does for anything but
-    OPTIMAL / OPTIMAL_INACCURATE.  An iteration-limit exit whose residuals are within
-    100x of the tolerance counts as 'inaccurate' and is returned."""
+    OPTIMAL / OPTIMAL_INACCURATE.  An iteration-limit exit whose certified relative gap is
+    below 1e-2 and whose coupling violation is below 1e-3 counts as 'inaccurate' and is
+    returned."""
     if status == _cabi.ACB_SOLVED:
         return
-    if status == _cabi.ACB_MAX_ITER and max(info["r_prim"], info["r_dual"]) <= 1e-2 and info["violation"] <= 1e-3:
+    if status == _cabi.ACB_MAX_ITER and info["gap"] <= 1e-2 and info["violation"] <= 1e-3:
         return
     raise InfeasibilityException(f"Solve failed with status {_STATUS_NAME.get(status, status)}")
 

@@ -27,6 +27,8 @@ extern "C" void acb_default_options(acb_options* o) {
     o->check_every = 25;
     o->equality = 0;
     o->adapt_rho = 1;
+    o->restart = 1;
+    o->avg_every = 5;
 }
 
 // cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major), double.

@@ -3,7 +3,7 @@
 // Replaces AdaptiveChargingOptimization.build_problem + solve (reference
 // adacharge/adaptive_charging_optimization.py:220-321, i.e. cvxpy canonicalisation and
 // the ECOS interior-point solve) and the objective library (:363-408) by an
-// over-relaxed ADMM with residual-balanced penalty on the split
+// over-relaxed, restarted ADMM on the split
 //     minimise  c'r + qd|r|^2 + g(Khat r_t)   s.t.  r in B,
 // B = charging-rate box (aco.py:61-79) intersected with the per-session energy rows
 // (aco.py:105-123), Khat = scaled [A cos(phi); A sin(phi)] / |A| rows (aco.py:156-172),
@@ -19,17 +19,27 @@
 //                  Newton on the multiplier (warp reductions);
 //                  per coupling row: v update; disc / half-line projections; peak
 //                  epigraph level by Newton.
+//   every check_every iterations: a rigorous duality gap.  P = objective of a candidate
+//   schedule that satisfies box and energy rows exactly; D = Lagrangian lower bound that
+//   dualises only the coupling and energy rows (the box keeps the inner minimum finite, so
+//   ANY multipliers give a valid bound).  Candidates: the current z and the projection of
+//   the running average of v; when the averaged candidate's gap has halved the iteration
+//   restarts from the average (restarted averaging gives linear convergence on the
+//   LP-like instances).  Stop when P - D <= eps_abs + eps_rel max(|P|,|D|) and the
+//   candidate's relative coupling violation <= viol_tol.
 // State: v (N x Tp) in registers, coupling v (R x Tp), bounds and partial sums in
-// shared memory; HBM is touched at load and store only.
+// shared memory; HBM is touched at load/store and for the running average only.
 #include <algorithm>
 #include <cfloat>
+#include <type_traits>
 #include "acb_common.cuh"
 
-struct BatchDev {
-    acb_batch b;
-};
-
 __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -49,10 +59,10 @@ __device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za
     zb = b * f;
 }
 
-// shared-memory layout (floats), computed identically on host and device
+// shared-memory layout (in floats), computed identically on host and device
 struct SmemLayout {
-    int LB, UB, PART, VC, VOUT, HG, ALPHA, BETA, PLIM, EBAR, MFT, CS, SINV, XS, SESS_A, SESS_B, SESS_E, SESS_MU,
-        SLOT, PGOFF, NGRP, KG, LIM, SCALE, RED, SCAL, total;
+    int LB, UB, PART, VC, VOUT, HG, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
+        SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
     int OP;  // padded output count of MFT
 };
 __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps) {
@@ -62,7 +72,9 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
     L.OP = ((NG + R + ACB_OPP - 1) / ACB_OPP) * ACB_OPP;
     L.LB = take(N * Tp);
     L.UB = take(N * Tp);
-    L.PART = take(NP * Tp);
+    // PART doubles as scratch for Sinv (R*R) and X (R*NG) while the column matrix is rebuilt
+    const int scratch = R * R + R * NG + 8;
+    L.PART = take(NP * Tp > scratch ? NP * Tp : scratch);
     L.VC = take(R * Tp);
     L.VOUT = take(R * Tp);
     L.HG = take(NG * Tp);
@@ -72,20 +84,21 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
     L.EBAR = take(Tp);
     L.MFT = take((NG + R) * L.OP);
     L.CS = take(R * NG);
-    L.SINV = take(R * R);
-    L.XS = take(R * NG);
     L.SESS_A = take(S_max);
     L.SESS_B = take(S_max);
     L.SESS_E = take(S_max);
     L.SESS_MU = take(S_max);
+    L.SESS_MU2 = take(S_max);
     L.SLOT = take(nSlots * 6);  // row, grp, prow, first, sess_first, sess_cnt
     L.PGOFF = take(NG + 1);
     L.NGRP = take(NG);
     L.KG = take(NG);
     L.LIM = take(R);
     L.SCALE = take(R);
-    L.RED = take(nwarps * ACB_NRED);
+    L.REDF = take(nwarps * ACB_NRED);
+    L.REDD = take(nwarps * ACB_NRED * 2);  // doubles
     L.SCAL = take(32);
+    L.SCALD = take(32);  // 16 doubles
     L.total = o;
     return L;
 }
@@ -93,27 +106,33 @@ size_t acb_solve_smem_bytes(const SiteDev& s, int Tp, int S_max, int nwarps) {
     return (size_t)make_layout(s.N, s.R, s.NG, s.NP, s.nSlots, Tp, S_max, nwarps).total * sizeof(float);
 }
 
-// indices into the SCAL scratch
-enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_EVALS };
-// reduction slots per warp
-enum { RD_E1 = 0, RD_E2, RD_XMAX, RD_ZMAX, RD_YMAX, RD_CX, RD_XX, RD_YZ, RD_RPC, RD_VIOL, RD_HD, RD_NAN, RD_EV };
+// float scalars
+enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG };
+// double scalars
+enum { SD_DBEST = 0, SD_GAPRESTART };
+// per-warp float reduction slots (max-type)
+enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA };
+// per-warp double reduction slots (sum-type)
+enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA };
 
 template <int Q, int TPW>
 __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch B, acb_options opt) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    const int Tp = B.Tp, N = S.N, R = S.R, NG = S.NG, NP = S.NP;
+    constexpr int Tp = 32 * Q;  // the host pads every batch to an instantiated horizon
+    const int N = S.N, R = S.R, NG = S.NG, NP = S.NP;
     const SmemLayout L = make_layout(N, R, NG, NP, S.nSlots, Tp, B.S_max, nwarps);
     float* LB = sm + L.LB; float* UB = sm + L.UB; float* PART = sm + L.PART; float* VC = sm + L.VC;
     float* VOUT = sm + L.VOUT; float* HG = sm + L.HG; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
     float* PLIM = sm + L.PLIM; float* EBAR = sm + L.EBAR; float* MFT = sm + L.MFT; float* CS = sm + L.CS;
-    float* SINV = sm + L.SINV; float* XS = sm + L.XS;
+    float* SINV = PART; float* XS = PART + R * R;
     int* SESS_A = (int*)(sm + L.SESS_A); int* SESS_B = (int*)(sm + L.SESS_B);
-    float* SESS_E = sm + L.SESS_E; float* SESS_MU = sm + L.SESS_MU;
+    float* SESS_E = sm + L.SESS_E; float* SESS_MU = sm + L.SESS_MU; float* SESS_MU2 = sm + L.SESS_MU2;
     int* SLOT = (int*)(sm + L.SLOT); int* PGOFF = (int*)(sm + L.PGOFF);
     float* NGRP = sm + L.NGRP; float* KG = sm + L.KG; float* LIM = sm + L.LIM; float* SCALE = sm + L.SCALE;
-    float* RED = sm + L.RED; float* SCAL = sm + L.SCAL;
+    float* REDF = sm + L.REDF; double* REDD = (double*)(sm + L.REDD); float* SCAL = sm + L.SCAL;
+    double* SCALD = (double*)(sm + L.SCALD);
     const int OP = L.OP, NIN = NG + R;
 
     const int b = blockIdx.x;
@@ -122,6 +141,16 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
     const int nDisc = S.nDisc, nLin = S.nLin;
     const int rPL = 2 * nDisc + nLin, rU = rPL + S.has_pl;
     const int nCT = nDisc + nLin + S.has_pl + S.has_u;  // coupling tasks
+    // coupling tasks run on the warps that own no EVSE rows (if any); the aggregate-power task,
+    // which carries the peak-level root find, gets a warp of its own when two or more are free
+    const int nFree = nwarps - S.nRowWarps;
+    auto task_warp = [&](int c) -> int {
+        if (nFree <= 0) return nwarps - 1 - (c % nwarps);
+        if (S.has_u && nFree >= 2) return (c == nCT - 1) ? nwarps - 1 : S.nRowWarps + (c % (nFree - 1));
+        return S.nRowWarps + (c % nFree);
+    };
+    float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
+    const bool useAvg = opt.restart && VSUM != nullptr;
 
     // ------------------------------------------------------------------ prologue
     for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
@@ -145,6 +174,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
         SESS_B[i] = ok ? B.sess_start[k] + B.sess_len[k] : 0;
         SESS_E[i] = ok ? B.sess_energy[k] : 0.f;
         SESS_MU[i] = (ok && B.warm_mu) ? B.warm_mu[k] : 0.f;
+        SESS_MU2[i] = 0.f;
     }
     for (int t = tid; t < Tp; t += nthreads) {
         bool ok = t < Tb;
@@ -202,17 +232,22 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
             m = fmaxf(m, fabsf(ALPHA[t] + KG[g] * BETA[t]));
         }
         m = warp_max(m);
-        if (lane == 0) RED[warp * ACB_NRED] = m;
+        if (lane == 0) REDF[warp * ACB_NRED] = m;
     }
     __syncthreads();
     if (tid == 0) {
         float m = 0.f;
-        for (int w = 0; w < nwarps; ++w) m = fmaxf(m, RED[w * ACB_NRED]);
+        for (int w = 0; w < nwarps; ++w) m = fmaxf(m, REDF[w * ACB_NRED]);
         SCAL[SC_CS] = (m > 1e-20f) ? 1.0f / m : 1.0f;
         SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : opt.rho0;
         SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
         SCAL[SC_FLAG] = 0.f;
-        SCAL[SC_EVALS] = 0.f;
+        SCAL[SC_NSUM] = 0.f;
+        SCAL[SC_NREST] = 0.f;
+        SCAL[SC_USEDAVG] = 0.f;
+        SCAL[SC_RP] = SCAL[SC_RD] = SCAL[SC_GAP] = SCAL[SC_VIOL] = 0.f;
+        SCALD[SD_DBEST] = -1.0e300;
+        SCALD[SD_GAPRESTART] = 1.0e300;
     }
     __syncthreads();
     const float cs = SCAL[SC_CS];
@@ -233,7 +268,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
         for (int q = 0; q < Q; ++q) {
             int t = lane + 32 * q;
             float v = 0.f;
-            if (row >= 0 && t < Tp) {
+            if (row >= 0) {
                 if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
                 else v = clampf(0.f, LB[row * Tp + t], UB[row * Tp + t]);
             }
@@ -242,18 +277,70 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
     }
 
     // ---- helpers --------------------------------------------------------------
-    // element multiplier of row slot `sl` at period t
-    // (rows with a single session use its multiplier everywhere: outside the window lb = ub = 0)
-    auto mu_at = [&](int sfirst, int scnt, int t) -> float {
+    // multiplier of the session covering period t of a row (rows with a single session use
+    // its multiplier everywhere: outside the window lb = ub = 0)
+    auto mu_at = [&](const float* MU, int sfirst, int scnt, int t) -> float {
         float m = 0.f;
         for (int s = sfirst; s < sfirst + scnt; ++s)
-            if (t >= SESS_A[s] && t < SESS_B[s]) m = SESS_MU[s];
+            if (t >= SESS_A[s] && t < SESS_B[s]) m = MU[s];
         return m;
     };
-#define MU_ELEM(sf, scn, mu0, t) ((scn) <= 1 ? (mu0) : mu_at(sf, scn, t))
+#define MU_ELEM(MU, sf, scn, mu0, t) ((scn) <= 1 ? (mu0) : mu_at(MU, sf, scn, t))
+    // multiplier mu with sum_{t in [a,e)} clip(vv_t - mu, lb_t, ub_t) = Eb (or <= Eb with mu >= 0):
+    // safeguarded Newton on a piecewise-linear monotone function, warm-started at mu
+    // `single`: the row has one session, so outside its window lb = ub = 0 and no mask is needed.
+    // `max_evals` = 1 gives one Newton step from the warm start without re-evaluation (used on
+    // non-check iterations: the projection is then inexact by an active-set change at most).
+    auto newton_mu = [&](const float (&vv)[Q], const float (&lb)[Q], const float (&ub)[Q], int a, int e, float Eb, float mu,
+                         bool single, int max_evals) -> float {
+        const float tol = 2e-6f * (Eb + 1.f);
+        // inequality rows: lo = -1 marks "mu = 0 not evaluated yet" (mu itself stays >= 0)
+        float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
+        if (!opt.equality) mu = fmaxf(mu, 0.f);
+        for (int step = 0; step < 16; ++step) {
+            float E = 0.f;
+            int nf = 0;
+            if (single) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    float w = vv[q] - mu;
+                    E += clampf(w, lb[q], ub[q]);
+                    nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    int t = lane + 32 * q;
+                    if (t >= a && t < e) {
+                        float w = vv[q] - mu;
+                        E += clampf(w, lb[q], ub[q]);
+                        nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
+                    }
+                }
+            }
+            E = warp_sum(E);
+            nf = __reduce_add_sync(0xffffffffu, nf);
+            float rr = E - Eb;
+            if (fabsf(rr) <= tol) break;
+            if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
+            if (rr > 0.f) lo = mu; else hi = mu;
+            float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
+            if (!opt.equality) mun = fmaxf(mun, 0.f);
+            if (!(mun > lo && mun < hi)) {
+                if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
+                else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
+                else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
+                if (!opt.equality) mun = fmaxf(mun, 0.f);
+            }
+            mu = mun;
+            if (step + 1 >= max_evals && nf > 0) break;
+        }
+        return mu;
+    };
     // (NG+R)^2 matrix of the column pass for the current rho:
     //   Sinv = U diag(1/(d/rho + lam)) U',  X = Sinv C,
     //   hg = -C'X sa + (d/rho) X' g,   v = X sa + (I - (d/rho) Sinv) g
+    // (PART is scratch here: callers rewrite it afterwards)
     auto build_matrix = [&]() {
         const float dr = dd / rho;
         for (int i = tid; i < R * R; i += nthreads) {
@@ -289,13 +376,55 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
         }
         __syncthreads();
     };
-    // coupling-row projection inputs for column t: z of row r given stored v
-    auto agg_a = [&](float v, int t) -> float {  // unconstrained minimiser of the aggregate-power prox (kW)
+    // unconstrained minimiser of the aggregate-power prox (kW) given the stored v of that row
+    auto agg_a = [&](float v, int t) -> float {
         float rp = rho / (su * su);
         return (rp * (v * su) - 2.f * Gamma * EBAR[t]) / (rp + 2.f * Gamma);
     };
-    // write partial sums of (mode 0) q = 2z - v or (mode 1) z for this warp's rows
-    auto write_part = [&](int mode) {
+    // peak-epigraph level for the aggregate-power row stored in VC (called by one warp):
+    // minimise pk_w*max(p,p0) + cur/2 sum (a_t - p)_+^2 over p
+    auto peak_level = [&](float guess) -> float {
+        const int r = rU;
+        const float rp = rho / (su * su), cur = rp + 2.f * Gamma;
+        float av[Q];
+        float amax = -3.0e38f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            int t = lane + 32 * q;
+            av[q] = (t < Tb) ? agg_a(VC[r * Tp + t], t) : -3.0e38f;
+            amax = fmaxf(amax, av[q]);
+        }
+        amax = warp_max(amax);
+        float pl = fmaxf(amax, pk_p0);
+        if (pk_w > 0.f && amax > pk_p0) {
+            float F0 = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) F0 += fmaxf(av[q] - pk_p0, 0.f);
+            F0 = warp_sum(F0) * cur;
+            if (F0 <= pk_w) pl = pk_p0;
+            else {
+                float p = fminf(fmaxf(guess, pk_p0), amax), lo = pk_p0, hi = amax;
+                for (int step = 0; step < 24; ++step) {
+                    float F = 0.f;
+                    int na = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        if (av[q] > p) { F += av[q] - p; ++na; }
+                    F = warp_sum(F) * cur - pk_w;
+                    na = __reduce_add_sync(0xffffffffu, na);
+                    if (fabsf(F) <= 1e-6f * pk_w) break;
+                    if (F > 0.f) lo = p; else hi = p;
+                    float pn = (na > 0) ? p + F / (cur * (float)na) : 0.5f * (lo + hi);
+                    if (!(pn > lo && pn < hi)) pn = 0.5f * (lo + hi);
+                    p = pn;
+                }
+                pl = p;
+            }
+        }
+        return pl;
+    };
+    // write partial sums of q = 2z - v for this warp's rows (z from the stored v and multipliers)
+    auto write_part_q = [&]() {
         if (!rowWarp) return;
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
@@ -308,20 +437,57 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
             for (int q = 0; q < Q; ++q) {
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(sf, scn, mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
-                float val = mode ? z : 2.f * z - v1[k][q];
+                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sf, scn, mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
+                float val = 2.f * z - v1[k][q];
                 if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
             }
         }
     };
+    // column evaluation of a candidate whose group partial sums are in PART: relative coupling
+    // violation, max and quadratic part of the aggregate power; optionally HG <- C' yc (yc in VOUT)
+    auto eval_columns = [&](bool with_hy, float& viol, float& umax, double& uq) {
+        viol = -1.f; umax = -3.0e38f; uq = 0.0;
+        for (int t = tid; t < Tp; t += nthreads) {
+            for (int g = 0; g < NG; ++g) {
+                float sz = 0.f;
+                for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) sz += PART[p * Tp + t];
+                HG[g * Tp + t] = sz;
+            }
+            int r = 0;
+            for (int j = 0; j < nDisc; ++j, r += 2) {
+                float ka = 0.f, kb = 0.f;
+                for (int g = 0; g < NG; ++g) { float sz = HG[g * Tp + t]; ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz; }
+                if (LIM[r] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / LIM[r] - 1.f);
+            }
+            for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
+                float ka = 0.f;
+                for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
+                float cap = (j == nLin) ? PLIM[t] : LIM[r];
+                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
+            }
+            if (S.has_u && t < Tb) {
+                float ka = 0.f;
+                for (int g = 0; g < NG; ++g) ka += CS[rU * NG + g] * HG[g * Tp + t];
+                float u = ka * su;
+                umax = fmaxf(umax, u);
+                uq += (double)(u + EBAR[t]) * (double)(u + EBAR[t]);
+            }
+            if (with_hy)
+                for (int g = 0; g < NG; ++g) {
+                    float acc = 0.f;
+                    for (int rr = 0; rr < R; ++rr) acc += CS[rr * NG + g] * VOUT[rr * Tp + t];
+                    HG[g * Tp + t] = acc;
+                }
+        }
+    };
 
     build_matrix();
-    write_part(0);
+    write_part_q();
     __syncthreads();
 
     int it = 0, status = ACB_MAX_ITER;
-    float last_rp = 0.f, last_rd = 0.f, last_gap = 0.f, last_viol = 0.f;
     const int nParts = (NIN + ACB_OPP - 1) / ACB_OPP;
+    const int avgEvery = max(1, opt.avg_every);
     for (it = 1; it <= opt.max_iter; ++it) {
         const float plevel = SCAL[SC_PLEVEL];
         // ------------------------------------------------------------ column pass
@@ -375,103 +541,73 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
         }
         __syncthreads();
         const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter);
-        float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rCx = 0.f, rXx = 0.f, rYz = 0.f, rRpc = 0.f, rNan = 0.f;
-        float nEv = 0.f;
+        const bool doAvg = useAvg && (it % avgEvery == 0);
+        const bool avgFirst = SCAL[SC_NSUM] == 0.f;
+        float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f;
+        double dPc = 0.0, dD = 0.0;  // primal (linear + diagonal part) of the current candidate; dual pieces
         // --------------------------------------------------------------- row pass
-        if (rowWarp) {
+        // (two instantiations: the hot non-check version keeps fewer values live)
+        auto row_pass = [&](auto chk_tag) {
+            constexpr bool CHK = decltype(chk_tag)::value;
 #pragma unroll
             for (int k = 0; k < TPW; ++k) {
                 const int* sl = SLOT + (warp * TPW + k) * 6;
                 const int row = sl[0];
                 if (row < 0) continue;
                 const int g = sl[1], prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
-                const float kgc = KG[g];
                 const float mu0 = scn ? SESS_MU[sf] : 0.f;
-                float lb[Q], ub[Q], zo[Q];
+                const float* lbp = LB + row * Tp + lane;
+                const float* ubp = UB + row * Tp + lane;
+                const float* hgp = HG + g * Tp + lane;
+                float lb[Q], ub[Q], zo[CHK ? Q : 1];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    int t = lane + 32 * q;
-                    bool in = t < Tp;
-                    lb[q] = in ? LB[row * Tp + t] : 0.f;
-                    ub[q] = in ? UB[row * Tp + t] : 0.f;
+                    lb[q] = lbp[32 * q];
+                    ub[q] = ubp[32 * q];
                     float vo = v1[k][q];
-                    float z = clampf(vo - MU_ELEM(sf, scn, mu0, t), lb[q], ub[q]);
-                    float hg = in ? HG[g * Tp + t] : 0.f;
-                    float x = (rho1 * (2.f * z - vo) + hg) * inv_d;
+                    float z = clampf(vo - MU_ELEM(SESS_MU, sf, scn, mu0, lane + 32 * q), lb[q], ub[q]);
+                    float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
                     v1[k][q] = vo + alpha * (x - z);
-                    zo[q] = z;
-                    if (chk) {
-                        float c = in ? (ALPHA[t] + kgc * BETA[t]) : 0.f;
-                        rE1 = fmaxf(rE1, fabsf(x - z));
-                        rXm = fmaxf(rXm, fabsf(x));
-                        rCx += c * x;
-                        rXx += x * x;
-                    }
+                    if (CHK) { zo[q] = z; rE1 = fmaxf(rE1, fabsf(x - z)); rXm = fmaxf(rXm, fabsf(x)); }
                 }
                 // projection onto box ∩ energy rows: one multiplier per session
                 for (int s = sf; s < sf + scn; ++s) {
-                    const int a = SESS_A[s], e = SESS_B[s];
-                    const float Eb = SESS_E[s];
-                    const float tol = 2e-6f * (Eb + 1.f);
-                    float mu = SESS_MU[s];
-                    // inequality rows: lo = -1 marks "mu = 0 not evaluated yet" (mu itself stays >= 0)
-                    float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
-                    if (!opt.equality) mu = fmaxf(mu, 0.f);
-                    for (int step = 0; step < 16; ++step) {
-                        float E = 0.f;
-                        int nf = 0;
-#pragma unroll
-                        for (int q = 0; q < Q; ++q) {
-                            int t = lane + 32 * q;
-                            if (t >= a && t < e) {
-                                float w = v1[k][q] - mu;
-                                E += clampf(w, lb[q], ub[q]);
-                                nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
-                            }
-                        }
-                        E = warp_sum(E);
-                        nf = __reduce_add_sync(0xffffffffu, nf);
-                        nEv += 1.f;
-                        float rr = E - Eb;
-                        if (fabsf(rr) <= tol) break;
-                        if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
-                        if (rr > 0.f) lo = mu; else hi = mu;
-                        float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
-                        if (!opt.equality) mun = fmaxf(mun, 0.f);
-                        if (!(mun > lo && mun < hi)) {
-                            if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
-                            else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
-                            else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
-                            if (!opt.equality) mun = fmaxf(mun, 0.f);
-                        }
-                        mu = mun;
-                    }
+                    float mu = newton_mu(v1[k], lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], scn == 1, 16);
                     if (lane == 0) SESS_MU[s] = mu;
                     __syncwarp();
                 }
                 const float mu1 = scn ? SESS_MU[sf] : 0.f;
+                float* pp = PART + prow * Tp + lane;
+                const float kgc = KG[g];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    int t = lane + 32 * q;
-                    if (t >= Tp) continue;
+                    const int t = lane + 32 * q;
                     float vn = v1[k][q];
-                    float zn = clampf(vn - MU_ELEM(sf, scn, mu1, t), lb[q], ub[q]);
-                    float val = chk ? zn : 2.f * zn - vn;
-                    if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
-                    if (chk) {
+                    float zn = clampf(vn - MU_ELEM(SESS_MU, sf, scn, mu1, t), lb[q], ub[q]);
+                    float val = CHK ? zn : 2.f * zn - vn;
+                    if (first) pp[32 * q] = val; else pp[32 * q] += val;
+                    if (doAvg) {
+                        float* vs = VSUM + (size_t)row * Tp + t;
+                        *vs = avgFirst ? vn : *vs + vn;
+                    }
+                    if (CHK) {
+                        float c = ALPHA[t] + kgc * BETA[t];
+                        dPc += (double)(c * zn + qd * zn * zn);
                         rE2 = fmaxf(rE2, fabsf(zn - zo[q]));
                         rZm = fmaxf(rZm, fabsf(zn));
-                        float y = rho1 * (vn - zn);
-                        rYm = fmaxf(rYm, fabsf(y));
-                        rYz += y * zn;
+                        rYm = fmaxf(rYm, fabsf(rho1 * (vn - zn)));
                         if (!(fabsf(vn) < 1.0e30f)) rNan = 1.f;
                     }
                 }
             }
+        };
+        if (rowWarp) {
+            if (chk) row_pass(std::true_type{}); else row_pass(std::false_type{});
         }
         // ---------------------------------------------------------- coupling rows
+        // v update; on check iterations VOUT <- y = rho (v - z) and the conjugate terms of D
         for (int c = 0; c < nCT; ++c) {
-            if (warp != nwarps - 1 - (c % nwarps)) continue;
+            if (warp != task_warp(c)) continue;
             if (c < nDisc) {
                 const int r = 2 * c;
                 const float lim = LIM[r];
@@ -481,14 +617,16 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
                     float ka = VOUT[r * Tp + t], kb = VOUT[(r + 1) * Tp + t];
                     float an = a + alpha * (ka - za), bn = bb + alpha * (kb - zb);
                     VC[r * Tp + t] = an; VC[(r + 1) * Tp + t] = bn;
+                    if (doAvg) {
+                        float* vs = VSUM + (size_t)(N + r) * Tp + t;
+                        vs[0] = avgFirst ? an : vs[0] + an; vs[Tp] = avgFirst ? bn : vs[Tp] + bn;
+                    }
                     if (chk) {
                         float zan, zbn;
                         proj_disc(an, bn, lim, zan, zbn);
-                        rRpc = fmaxf(rRpc, fmaxf(fabsf(ka - zan), fabsf(kb - zbn)));
-                        rXm = fmaxf(rXm, fmaxf(fabsf(ka), fabsf(kb)));
-                        VOUT[r * Tp + t] = rho * ((alpha - 1.f) * (ka - za) + (za - zan));
-                        VOUT[(r + 1) * Tp + t] = rho * ((alpha - 1.f) * (kb - zb) + (zb - zbn));
-                        rYz += rho * ((an - zan) * zan + (bn - zbn) * zbn);
+                        float ya = rho * (an - zan), yb = rho * (bn - zbn);
+                        VOUT[r * Tp + t] = ya; VOUT[(r + 1) * Tp + t] = yb;
+                        dD -= (double)(lim * sqrtf(ya * ya + yb * yb));  // support function of the disc
                     }
                 }
             } else if (c < nDisc + nLin + S.has_pl) {
@@ -499,170 +637,181 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
                     float v = VC[r * Tp + t], z = fminf(v, cap), kx = VOUT[r * Tp + t];
                     float vn = v + alpha * (kx - z);
                     VC[r * Tp + t] = vn;
+                    if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
                     if (chk) {
-                        float zn = fminf(vn, cap);
-                        rRpc = fmaxf(rRpc, fabsf(kx - zn));
-                        rXm = fmaxf(rXm, fabsf(kx));
-                        VOUT[r * Tp + t] = rho * ((alpha - 1.f) * (kx - z) + (z - zn));
-                        rYz += rho * (vn - zn) * zn;
+                        float zn = fminf(vn, cap), y = rho * (vn - zn);
+                        VOUT[r * Tp + t] = y;
+                        if (y > 0.f) dD -= (double)(cap * y);  // support function of the half line
                     }
                 }
             } else {
                 // aggregate-power row: quadratic (load flattening) + peak epigraph
                 const int r = rU;
-                const float rp = rho / (su * su), cur = rp + 2.f * Gamma;
-                float amax = -3.0e38f;
-                float pre[Q];
+                for (int t = lane; t < Tp; t += 32) {
+                    float v = VC[r * Tp + t], a = agg_a(v, t);
+                    float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+                    float vn = v + alpha * (VOUT[r * Tp + t] - z);
+                    VC[r * Tp + t] = vn;
+                    if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
+                }
+                __syncwarp();
+                const float pl = peak_level(plevel);
+                if (lane == 0) SCAL[SC_PLEVEL] = pl;
+                if (chk) {
+                    // Fenchel equality for y in dg(z): -g*(y) = g(z) - <y, z>
+                    float zmax = -3.0e38f;
+                    double acc = 0.0;
+                    for (int t = lane; t < Tp; t += 32) {
+                        float vn = VC[r * Tp + t], an = agg_a(vn, t);
+                        float zk = (pk_w > 0.f) ? fminf(an, pl) : an;  // kW
+                        float zn = zk / su, y = rho * (vn - zn);
+                        VOUT[r * Tp + t] = y;
+                        if (t < Tb) { zmax = fmaxf(zmax, zk); acc += (double)Gamma * (double)(zk + EBAR[t]) * (double)(zk + EBAR[t]); }
+                        acc -= (double)y * (double)zn;
+                    }
+                    zmax = warp_max(zmax);
+                    dD += acc;
+                    if (lane == 0) dD += (double)pk_w * (double)fmaxf(zmax, pk_p0);
+                }
+            }
+        }
+        if (!chk) {
+            __syncthreads();
+            if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;  // next read is after the next barrier
+            continue;
+        }
+
+        // ============================================================= check path
+        __syncthreads();  // PART = group sums of z, VOUT = y
+        if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;
+        float violC, umaxC; double uqC;
+        eval_columns(true, violC, umaxC, uqC);  // HG <- C'y afterwards
+        __syncthreads();
+        // Lagrangian inner minimum over the box and energy-row terms; averaged candidate
+        const float nsum = SCAL[SC_NSUM];
+        const bool haveAvg = useAvg && nsum >= 2.f;
+        double dPa = 0.0;
+        if (rowWarp) {
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                const int* sl = SLOT + (warp * TPW + k) * 6;
+                const int row = sl[0];
+                if (row < 0) continue;
+                const int g = sl[1], prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
+                const float kgc = KG[g];
+                const float mu0 = scn ? SESS_MU[sf] : 0.f;
+                float lb[Q], ub[Q], va[Q];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     int t = lane + 32 * q;
-                    pre[q] = 0.f;
-                    if (t >= Tp) continue;
-                    float v = VC[r * Tp + t], a = agg_a(v, t);
-                    float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
-                    float kx = VOUT[r * Tp + t];
-                    float vn = v + alpha * (kx - z);
-                    VC[r * Tp + t] = vn;
-                    pre[q] = (alpha - 1.f) * (kx - z) + z;
-                    if (t < Tb) amax = fmaxf(amax, agg_a(vn, t));
-                }
-                amax = warp_max(amax);
-                float pl = fmaxf(amax, pk_p0);
-                if (pk_w > 0.f && amax > pk_p0) {
-                    // minimise pk_w*max(p,p0) + cur/2 sum (a_t - p)_+^2 over p
-                    float F0 = 0.f;
-                    for (int t = lane; t < Tb; t += 32) F0 += fmaxf(agg_a(VC[r * Tp + t], t) - pk_p0, 0.f);
-                    F0 = warp_sum(F0) * cur;
-                    if (F0 <= pk_w) pl = pk_p0;
-                    else {
-                        float p = fminf(fmaxf(plevel, pk_p0), amax), lo = pk_p0, hi = amax;
-                        for (int step = 0; step < 24; ++step) {
-                            float F = 0.f;
-                            int na = 0;
-                            for (int t = lane; t < Tb; t += 32) {
-                                float a = agg_a(VC[r * Tp + t], t);
-                                if (a > p) { F += a - p; ++na; }
-                            }
-                            F = warp_sum(F) * cur - pk_w;
-                            na = __reduce_add_sync(0xffffffffu, na);
-                            if (fabsf(F) <= 1e-6f * pk_w) break;
-                            if (F > 0.f) lo = p; else hi = p;
-                            float pn = (na > 0) ? p + F / (cur * (float)na) : 0.5f * (lo + hi);
-                            if (!(pn > lo && pn < hi)) pn = 0.5f * (lo + hi);
-                            p = pn;
-                        }
-                        pl = p;
+                    bool in = t < Tp;
+                    lb[q] = in ? LB[row * Tp + t] : 0.f;
+                    ub[q] = in ? UB[row * Tp + t] : 0.f;
+                    va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] / nsum : 0.f;
+                    if (in) {
+                        // reduced cost: c + (Khat' y) + lambda_s, lambda_s = rho1 * mu_s on the session window
+                        float lam = rho1 * MU_ELEM(SESS_MU, sf, scn, mu0, t);
+                        float rt = ALPHA[t] + kgc * BETA[t] + HG[g * Tp + t] + lam;
+                        float phi;
+                        if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lb[q], ub[q]); phi = qd * xs * xs + rt * xs; }
+                        else phi = fminf(lb[q] * rt, ub[q] * rt);
+                        dD += (double)phi;
                     }
                 }
-                if (lane == 0) SCAL[SC_PLEVEL] = pl;
-                if (chk) {
+                if (lane == 0)
+                    for (int s = sf; s < sf + scn; ++s) dD -= (double)(rho1 * SESS_MU[s]) * (double)SESS_E[s];
+                if (haveAvg) {
+                    for (int s = sf; s < sf + scn; ++s) {
+                        float mu = newton_mu(va, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], scn == 1, 16);
+                        if (lane == 0) SESS_MU2[s] = mu;
+                        __syncwarp();
+                    }
+                    const float mu2 = scn ? SESS_MU2[sf] : 0.f;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
                         if (t >= Tp) continue;
-                        float vn = VC[r * Tp + t], an = agg_a(vn, t);
-                        float zn = ((pk_w > 0.f) ? fminf(an, pl) : an) / su;
-                        float kx = VOUT[r * Tp + t];
-                        rRpc = fmaxf(rRpc, fabsf(kx - zn));
-                        rXm = fmaxf(rXm, fabsf(kx));
-                        VOUT[r * Tp + t] = rho * (pre[q] - zn);
-                        rYz += rho * (vn - zn) * zn;
+                        float zn = clampf(va[q] - MU_ELEM(SESS_MU2, sf, scn, mu2, t), lb[q], ub[q]);
+                        if (first) PART[prow * Tp + t] = zn; else PART[prow * Tp + t] += zn;
+                        float c = ALPHA[t] + kgc * BETA[t];
+                        dPa += (double)(c * zn + qd * zn * zn);
                     }
                 }
             }
         }
-        if (!chk) { __syncthreads(); continue; }
-        // ------------------------------------------------------------- check path
-        rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm);
-        rRpc = warp_max(rRpc); rNan = warp_max(rNan);
-        rCx = warp_sum(rCx); rXx = warp_sum(rXx); rYz = warp_sum(rYz);
+        __syncthreads();  // PART = group sums of the averaged candidate
+        float violA = 3.0e38f, umaxA = -3.0e38f; double uqA = 0.0;
+        if (haveAvg) eval_columns(false, violA, umaxA, uqA);
+        // block reductions
+        rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm); rNan = warp_max(rNan);
+        violC = warp_max(violC); umaxC = warp_max(umaxC);
+        violA = warp_max(violA); umaxA = warp_max(umaxA);
+        dPc = warp_sum(dPc); dPa = warp_sum(dPa); dD = warp_sum(dD); uqC = warp_sum(uqC); uqA = warp_sum(uqA);
         if (lane == 0) {
-            float* r = RED + warp * ACB_NRED;
-            r[RD_E1] = rE1; r[RD_E2] = rE2; r[RD_XMAX] = rXm; r[RD_ZMAX] = rZm; r[RD_YMAX] = rYm; r[RD_CX] = rCx;
-            r[RD_XX] = rXx; r[RD_YZ] = rYz; r[RD_RPC] = rRpc; r[RD_NAN] = rNan; r[RD_VIOL] = -1.f; r[RD_HD] = 0.f;
-            r[RD_EV] = nEv;
+            float* rf = REDF + warp * ACB_NRED;
+            rf[RF_E1] = rE1; rf[RF_E2] = rE2; rf[RF_XMAX] = rXm; rf[RF_ZMAX] = rZm; rf[RF_YMAX] = rYm; rf[RF_NAN] = rNan;
+            rf[RF_VIOLC] = violC; rf[RF_VIOLA] = violA; rf[RF_UMAXC] = umaxC; rf[RF_UMAXA] = umaxA;
+            double* rd = REDD + warp * ACB_NRED;
+            rd[RD_PC] = dPc; rd[RD_PA] = dPa; rd[RD_D] = dD; rd[RD_UQC] = uqC; rd[RD_UQA] = uqA;
         }
         __syncthreads();
-        // violation of the candidate schedule z and |C' delta_c| (columns)
-        {
-            float viol = -1.f, hd = 0.f;
-            for (int t = tid; t < Tp; t += nthreads) {
-                // group sums of z (HG is free here and serves as scratch)
-                for (int g = 0; g < NG; ++g) {
-                    float sz = 0.f;
-                    for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) sz += PART[p * Tp + t];
-                    HG[g * Tp + t] = sz;
-                }
-                int r = 0;
-                for (int j = 0; j < nDisc; ++j, r += 2) {
-                    float ka = 0.f, kb = 0.f;
-                    for (int g = 0; g < NG; ++g) {
-                        float sz = HG[g * Tp + t];
-                        ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz;
-                    }
-                    if (LIM[r] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / LIM[r] - 1.f);
-                }
-                for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
-                    float ka = 0.f;
-                    for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
-                    float cap = (j == nLin) ? PLIM[t] : LIM[r];
-                    if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
-                }
-                for (int g = 0; g < NG; ++g) {
-                    float acc = 0.f;
-                    for (int rr = 0; rr < R; ++rr) acc += CS[rr * NG + g] * VOUT[rr * Tp + t];
-                    hd = fmaxf(hd, fabsf(acc));
-                }
+        if (tid == 0) {
+            float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, nn = 0, vC = -1.f, vA = -1.f, uC = -3.0e38f, uA = -3.0e38f;
+            double Pc = 0, Pa = 0, D = 0, qC = 0, qA = 0;
+            for (int w = 0; w < nwarps; ++w) {
+                const float* rf = REDF + w * ACB_NRED;
+                e1 = fmaxf(e1, rf[RF_E1]); e2 = fmaxf(e2, rf[RF_E2]); xm = fmaxf(xm, rf[RF_XMAX]); zm = fmaxf(zm, rf[RF_ZMAX]);
+                ym = fmaxf(ym, rf[RF_YMAX]); nn = fmaxf(nn, rf[RF_NAN]); vC = fmaxf(vC, rf[RF_VIOLC]);
+                if (haveAvg) vA = fmaxf(vA, rf[RF_VIOLA]);
+                uC = fmaxf(uC, rf[RF_UMAXC]); uA = fmaxf(uA, rf[RF_UMAXA]);
+                const double* rd = REDD + w * ACB_NRED;
+                Pc += rd[RD_PC]; Pa += rd[RD_PA]; D += rd[RD_D]; qC += rd[RD_UQC]; qA += rd[RD_UQA];
             }
-            viol = warp_max(viol); hd = warp_max(hd);
-            if (lane == 0) { RED[warp * ACB_NRED + RD_VIOL] = viol; RED[warp * ACB_NRED + RD_HD] = hd; }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, cx = 0, xx = 0, yz = 0, rpc = 0, vi = -1.f, hd = 0, nn = 0, ev = 0;
-            for (int w = lane; w < nwarps; w += 32) {
-                const float* r = RED + w * ACB_NRED;
-                e1 = fmaxf(e1, r[RD_E1]); e2 = fmaxf(e2, r[RD_E2]); xm = fmaxf(xm, r[RD_XMAX]); zm = fmaxf(zm, r[RD_ZMAX]);
-                ym = fmaxf(ym, r[RD_YMAX]); cx += r[RD_CX]; xx += r[RD_XX]; yz += r[RD_YZ]; rpc = fmaxf(rpc, r[RD_RPC]);
-                vi = fmaxf(vi, r[RD_VIOL]); hd = fmaxf(hd, r[RD_HD]); nn = fmaxf(nn, r[RD_NAN]); ev += r[RD_EV];
+            if (S.has_u) {
+                Pc += (double)Gamma * qC + (double)pk_w * (double)fmaxf(uC, pk_p0);
+                Pa += (double)Gamma * qA + (double)pk_w * (double)fmaxf(uA, pk_p0);
             }
-            e1 = warp_max(e1); e2 = warp_max(e2); xm = warp_max(xm); zm = warp_max(zm); ym = warp_max(ym);
-            rpc = warp_max(rpc); vi = warp_max(vi); hd = warp_max(hd); nn = warp_max(nn);
-            cx = warp_sum(cx); xx = warp_sum(xx); yz = warp_sum(yz); ev = warp_sum(ev);
-            if (lane == 0) {
-                float rp = fmaxf(e1 + e2, rpc);
-                float rd = rho1 * (fabsf(alpha - 1.f) * e1 + e2) + hd;
-                float pn = fmaxf(fmaxf(xm, zm), 1e-6f);
-                float dn = fmaxf(fmaxf(1.0f, ym), 1e-6f);  // |c|_inf = 1 after cost scaling
-                float gap = 2.f * qd * xx + cx + yz;
-                float gsc = fmaxf(fabsf(qd * xx + cx), fabsf(qd * xx + yz));
-                float rp_rel = rp / (opt.eps_abs / opt.eps_rel + pn);
-                float rd_rel = rd / (opt.eps_abs / opt.eps_rel + dn);
-                float gap_rel = fabsf(gap) / (opt.eps_abs / opt.eps_rel + gsc);
-                SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel; SCAL[SC_GAP] = gap_rel; SCAL[SC_VIOL] = vi;
-                SCAL[SC_EVALS] += ev;
-                float flag = 0.f;
-                if (nn > 0.f || !(rp == rp) || !(rd == rd)) flag = 3.f;
-                else if (rp_rel <= opt.eps_rel && rd_rel <= opt.eps_rel && gap_rel <= opt.eps_rel && vi <= opt.viol_tol) flag = 1.f;
-                else if (opt.adapt_rho) {
+            double Dbest = SCALD[SD_DBEST];
+            if (D == D && D > Dbest) Dbest = D;
+            SCALD[SD_DBEST] = Dbest;
+            const double gapC = Pc - Dbest, gapA = Pa - Dbest;
+            const double tolC = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pc), fabs(Dbest));
+            const double tolA = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pa), fabs(Dbest));
+            // residual estimates (only used to balance rho)
+            float rp = e1 + e2, rd_ = rho1 * (fabsf(alpha - 1.f) * e1 + e2);
+            float rp_rel = rp / fmaxf(fmaxf(xm, zm), 1e-6f), rd_rel = rd_ / fmaxf(1.0f, ym);
+            float flag = 0.f;
+            const bool okC = gapC <= tolC && vC <= opt.viol_tol;
+            const bool okA = haveAvg && gapA <= tolA && vA <= opt.viol_tol;
+            if (nn > 0.f || !(Pc == Pc)) flag = 3.f;
+            else if (okC && (!okA || gapC <= gapA)) flag = 1.f;
+            else if (okA) flag = 4.f;
+            else {
+                if (haveAvg && gapA <= 0.5 * SCALD[SD_GAPRESTART] && vA <= fmaxf(vC, opt.viol_tol) + 1e-3f) {
+                    SCALD[SD_GAPRESTART] = gapA;
+                    flag = 5.f;
+                }
+                if (opt.adapt_rho) {
                     float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
                     if (ratio > 5.f || ratio < 0.2f) {
                         SCAL[SC_NEWRHO] = fminf(fmaxf(rho * ratio, 1e-4f), 1e4f);
-                        flag = 2.f;
+                        flag += 10.f;  // combined with a restart: 15
                     }
                 }
-                SCAL[SC_FLAG] = flag;
             }
+            SCAL[SC_FLAG] = flag;
+            SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel;
+            const bool useA = (flag == 4.f);
+            SCAL[SC_GAP] = (float)((useA ? gapA : gapC) / fmax(fmax(fabs(useA ? Pa : Pc), fabs(Dbest)), 1e-30));
+            SCAL[SC_VIOL] = useA ? vA : vC;
         }
         __syncthreads();
         const float flag = SCAL[SC_FLAG];
-        last_rp = SCAL[SC_RP]; last_rd = SCAL[SC_RD]; last_gap = SCAL[SC_GAP]; last_viol = SCAL[SC_VIOL];
         if (flag == 1.f) { status = ACB_SOLVED; break; }
         if (flag == 3.f) { status = ACB_NUMERICAL; break; }
-        if (it == opt.max_iter) break;
-        if (flag == 2.f) {
-            // keep y: v <- z + (rho/rho_new)(v - z), then rebuild the column matrix
-            const float rn = SCAL[SC_NEWRHO], f = rho / rn;
+        const bool toAvg = (flag == 4.f) || (flag == 5.f) || (flag == 15.f);
+        if (toAvg) {
+            // adopt the averaged state: v <- mean v, multipliers of its projection, mean coupling v
             if (rowWarp) {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k) {
@@ -672,8 +821,37 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
+                        if (t < Tp) v1[k][q] = VSUM[(size_t)row * Tp + t] / nsum;
+                    }
+                }
+            }
+            for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = SESS_MU2[i];
+            for (int i = tid; i < R * Tp; i += nthreads) VC[i] = VSUM[(size_t)N * Tp + i] / nsum;
+            __syncthreads();
+            if (S.has_u && warp == nwarps - 1) {
+                float pl = peak_level(SCAL[SC_PLEVEL]);
+                if (lane == 0) SCAL[SC_PLEVEL] = pl;
+            }
+            if (tid == 0) { SCAL[SC_NSUM] = 0.f; SCAL[SC_NREST] += 1.f; }
+            __syncthreads();
+            if (flag == 4.f) { status = ACB_SOLVED; if (tid == 0) SCAL[SC_USEDAVG] = 1.f; break; }
+        }
+        if (it == opt.max_iter) break;
+        if (flag >= 10.f) {
+            // keep y: v <- z + (rho/rho_new)(v - z), then rebuild the column matrix
+            const float rn = SCAL[SC_NEWRHO], f = rho / rn;
+            if (rowWarp) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    const int* sl = SLOT + (warp * TPW + k) * 6;
+                    int row = sl[0];
+                    if (row < 0) continue;
+                    const float mu0 = sl[5] ? SESS_MU[sl[4]] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        int t = lane + 32 * q;
                         if (t >= Tp) continue;
-                        float z = clampf(v1[k][q] - mu_at(sl[4], sl[5], t), LB[row * Tp + t], UB[row * Tp + t]);
+                        float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
                         v1[k][q] = z + f * (v1[k][q] - z);
                     }
                 }
@@ -691,16 +869,15 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
                 if (S.has_u) {
                     float v = VC[r * Tp + t], a = agg_a(v, t);
                     float z = ((pk_w > 0.f) ? fminf(a, pl) : a) / su;
-                    // y = rho (v - z) must be preserved under the new rho
                     VC[r * Tp + t] = z + f * (v - z);
                 }
             }
             __syncthreads();
             rho = rn; rho1 = kappa * rho; dd = 2.f * qd + rho1; inv_d = 1.f / dd;
-            if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_FLAG] = 0.f; }
+            if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_NSUM] = 0.f; }  // the average restarts with the new metric
             build_matrix();
         }
-        write_part(0);
+        write_part_q();
         __syncthreads();
     }
     if (it > opt.max_iter) it = opt.max_iter;
@@ -712,11 +889,12 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
             const int* sl = SLOT + (warp * TPW + k) * 6;
             int row = sl[0];
             if (row < 0) continue;
+            const float mu0 = sl[5] ? SESS_MU[sl[4]] : 0.f;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - mu_at(sl[4], sl[5], t), LB[row * Tp + t], UB[row * Tp + t]);
+                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
                 B.rates[((size_t)b * N + row) * Tp + t] = z;
                 if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
             }
@@ -729,8 +907,8 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch
         B.status[b] = status;
         B.iters[b] = it;
         float* st = B.stats + (size_t)b * ACB_NSTATS;
-        st[0] = last_rp; st[1] = last_rd; st[2] = last_gap; st[3] = last_viol; st[4] = rho; st[5] = cs;
-        st[6] = SCAL[SC_EVALS]; st[7] = 0.f;
+        st[0] = SCAL[SC_RP]; st[1] = SCAL[SC_RD]; st[2] = SCAL[SC_GAP]; st[3] = SCAL[SC_VIOL]; st[4] = rho; st[5] = cs;
+        st[6] = SCAL[SC_NREST]; st[7] = SCAL[SC_USEDAVG];
     }
 }
 
@@ -776,8 +954,12 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     ACB_CUDA(cudaSetDevice(site->device));
     const SiteDev& d = site->d;
     const int Q = batch->Tp / 32;
+    if (Q != 1 && Q != 3 && Q != 5 && Q != 9) {
+        acb_set_error("acb_solve_batch: Tp must be one of 32, 96, 160, 288 (pad the horizon up)");
+        return ACB_E_INVALID;
+    }
     const int nParts = (d.NG + d.R + ACB_OPP - 1) / ACB_OPP;
-    // threads: enough warps for the EVSE rows, and for one column-pass sweep if possible
+    // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
     const int nCT = d.nDisc + d.nLin + d.has_pl + d.has_u;
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
     int nthreads = std::min(1024, ((want + 31) / 32) * 32);
@@ -788,9 +970,9 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
         return ACB_E_TOO_LARGE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-#define CASE(QQ, TT) if (Q <= QQ && d.TPW == TT) return launch_solve<QQ, TT>(site, batch, opt_ptr, nthreads, smem, st);
     const acb_options* opt_ptr = &opt;
-    CASE(1, 2) CASE(5, 2) CASE(9, 2)
+#define CASE(QQ, TT) if (Q == QQ && d.TPW == TT) return launch_solve<QQ, TT>(site, batch, opt_ptr, nthreads, smem, st);
+    CASE(1, 2) CASE(3, 2) CASE(5, 2) CASE(9, 2)
 #undef CASE
     acb_set_error("acb_solve_batch: no kernel instantiation for Tp=" + std::to_string(batch->Tp) + " TPW=" + std::to_string(d.TPW));
     return ACB_E_TOO_LARGE;

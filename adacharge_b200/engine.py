@@ -182,6 +182,9 @@ def pack_sessions(sessions, infra, period) -> dict:
     return out
 
 
+SUPPORTED_HORIZONS = (32, 96, 160, 288)  # padded horizons the solve kernel is instantiated for
+
+
 class PackedBatch:
     """Pinned host staging + device tensors of a batch; owns the acb_batch struct."""
 
@@ -190,7 +193,12 @@ class PackedBatch:
         self.site = site
         B = len(instances)
         Tmax = max(i.T for i in instances)
-        self.Tp = Tp or ((Tmax + 31) // 32) * 32
+        if Tp is None:
+            fits = [t for t in SUPPORTED_HORIZONS if t >= Tmax]
+            if not fits:
+                raise ValueError(f"horizon {Tmax} exceeds the largest on-chip horizon {SUPPORTED_HORIZONS[-1]}")
+            Tp = fits[0]
+        self.Tp = Tp
         self.S_max = S_max or max(4, max(len(i.sess_row) for i in instances))
         self.B = B
         Tp_, S_ = self.Tp, self.S_max
@@ -247,6 +255,7 @@ class PackedBatch:
         self.status = torch.empty((B,), dtype=torch.int32, device=dev)
         self.iters = torch.empty((B,), dtype=torch.int32, device=dev)
         self.stats = torch.empty((B, _cabi.ACB_NSTATS), dtype=torch.float32, device=dev)
+        self.work = torch.empty((B, N + max(R, 1), Tp_), dtype=torch.float32, device=dev)
         self.warm = None
         self.warm_out = None
         if want_warm_out:
@@ -277,6 +286,7 @@ class PackedBatch:
         s.warm_v1, s.warm_vc, s.warm_mu, s.warm_scal = (_ptr(w.get(k)) for k in ("v1", "vc", "mu", "scal"))
         o = self.warm_out or {}
         s.out_v1, s.out_vc, s.out_mu, s.out_scal = (_ptr(o.get(k)) for k in ("v1", "vc", "mu", "scal"))
+        s.work = _ptr(self.work)
         s.rates, s.status, s.iters, s.stats = _ptr(self.rates), _ptr(self.status), _ptr(self.iters), _ptr(self.stats)
         return s
 

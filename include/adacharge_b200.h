@@ -50,7 +50,7 @@ extern "C" {
 #define ACB_INFEASIBLE 2 /* primal infeasibility detected */
 #define ACB_NUMERICAL 3  /* non-finite iterate */
 
-#define ACB_NSTATS 8 /* stats row: r_prim, r_dual, gap, violation, rho, cost_scale, newton_evals, reserved */
+#define ACB_NSTATS 8 /* stats row: r_prim, r_dual, rel. gap, violation, rho, cost_scale, restarts, 1 if the averaged candidate was returned */
 
 typedef struct acb_site acb_site;
 
@@ -70,8 +70,9 @@ int acb_site_dims(const acb_site* site, int* N, int* M, int* R, int* NG, int* NP
 int acb_site_max_horizon(const acb_site* site);
 
 typedef struct acb_options {
-    float eps_abs;      /* absolute residual tolerance (scaled units), e.g. 1e-5 */
-    float eps_rel;      /* relative residual / gap tolerance, e.g. 1e-4 */
+    float eps_abs;      /* absolute gap tolerance in cost-scaled units (largest |cost coefficient| = 1) */
+    float eps_rel;      /* relative duality-gap tolerance: P - D <= eps_abs + eps_rel * max(|P|, |D|), where P is the
+                           objective of the returned schedule and D a Lagrangian lower bound */
     float viol_tol;     /* max relative infrastructure / peak violation of the returned schedule */
     float rho0;         /* initial penalty */
     float kappa;        /* identity-block penalty = kappa * rho */
@@ -80,6 +81,8 @@ typedef struct acb_options {
     int32_t check_every; /* residual check period (iterations) */
     int32_t equality;    /* enforce_energy_equality */
     int32_t adapt_rho;   /* 1 = residual balancing */
+    int32_t restart;     /* 1 = average the state and restart from the average when its gap halves */
+    int32_t avg_every;   /* state is added to the average every avg_every iterations */
 } acb_options;
 
 void acb_default_options(acb_options* o);
@@ -111,6 +114,7 @@ typedef struct acb_batch {
     const float* peak_limit;     /* [B*Tp] or NULL (required iff use_peak_row) */
     /* warm start (all optional, NULL = cold).  Layout: v1 [B][N][Tp], vc [B][R][Tp],
      * mu [B][S_max], scal [B][2] = {rho, peak level}. */
+    float* work;                 /* scratch [B][N+R][Tp] for the averaged state; NULL disables restarts */
     const float* warm_v1; const float* warm_vc; const float* warm_mu; const float* warm_scal;
     float* out_v1; float* out_vc; float* out_mu; float* out_scal;
     /* results */

@@ -36,7 +36,7 @@ run("c2-cap40", config_c2(2, infra=caltech_acn_infrastructure(transformer_cap=40
 for cfg, obj, B in (("c1", [OC(ab.quick_charge), OC(ab.equal_share, 1e-3)], 592), ("c2", obj2, 296)):
     insts = []
     for seed in range(B):
-        d = config_c1(seed) if cfg == "c1" else config_c2(seed)
+        d = config_c1(seed) if cfg == "c1" else config_c2(seed, price_noise=0.2)
         iface = ab.TestingInterface(d); S = iface.active_sessions(); I = iface.infrastructure_info()
         aco = ab.AdaptiveChargingOptimization(obj, iface)
         insts.append(aco.build_instance(S, I, None, iface.get_prev_peak()))
@@ -47,4 +47,4 @@ for cfg, obj, B in (("c1", [OC(ab.quick_charge), OC(ab.equal_share, 1e-3)], 592)
     e0.record(); pb.solve(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
-    print(f"batch {cfg} B={B}: {ms:.2f} ms -> {B/ms*1e3:.0f} solves/s; iters mean {it.mean():.0f} max {it.max()} status counts {np.bincount(st, minlength=4)}; evals/row/iter {pb.stats[:,6].sum().item()/ (it.sum()*pb.host['n_sessions'].float().mean().item()):.2f}")
+    print(f"batch {cfg} B={B}: {ms:.2f} ms -> {B/ms*1e3:.0f} solves/s; iters mean {it.mean():.0f} max {it.max()} status counts {np.bincount(st, minlength=4)}; restarts mean {pb.stats[:,6].mean().item():.1f} averaged {pb.stats[:,7].mean().item():.2f}")
