@@ -38,7 +38,7 @@ _P = C.c_void_p
 
 class Batch(C.Structure):
     _fields_ = [
-        ("B", C.c_int32), ("Tp", C.c_int32), ("S_max", C.c_int32),
+        ("B", C.c_int32), ("Tp", C.c_int32), ("S_max", C.c_int32), ("multi_session", C.c_int32),
         ("T", _P), ("n_sessions", _P), ("sess_row", _P), ("sess_start", _P), ("sess_len", _P),
         ("sess_energy", _P), ("sess_rate_off", _P), ("min_rates", _P), ("max_rates", _P),
         ("alpha", _P), ("beta", _P), ("qd", _P), ("gamma", _P), ("ext", _P), ("peak_w", _P), ("peak_p0", _P),

@@ -1,915 +1,11 @@
-// Batched MPC solve: one thread block per instance, all solver state on chip.
-//
-// Replaces AdaptiveChargingOptimization.build_problem + solve (reference
-// adacharge/adaptive_charging_optimization.py:220-321, i.e. cvxpy canonicalisation and
-// the ECOS interior-point solve) and the objective library (:363-408) by an
-// over-relaxed, restarted ADMM on the split
-//     minimise  c'r + qd|r|^2 + g(Khat r_t)   s.t.  r in B,
-// B = charging-rate box (aco.py:61-79) intersected with the per-session energy rows
-// (aco.py:105-123), Khat = scaled [A cos(phi); A sin(phi)] / |A| rows (aco.py:156-172),
-// the peak-limit row (aco.py:196-197) and the aggregate-power row used by
-// peak / demand_charge / load_flattening (aco.py:387-408).
-//
-// Per iteration (DESIGN.md "solve kernel"):
-//   column pass  : per period t, group sums of q = 2 z - v over electrically identical
-//                  EVSEs, then ONE (NG+R) x (NG+R) matrix apply that yields both
-//                  Khat'h (per group) and Khat x (per coupling row).
-//   row pass     : per EVSE row (one warp, lanes over t): x, over-relaxed v update,
-//                  projection onto box ∩ energy row by a warm-started safeguarded
-//                  Newton on the multiplier (warp reductions);
-//                  per coupling row: v update; disc / half-line projections; peak
-//                  epigraph level by Newton.
-//   every check_every iterations: a rigorous duality gap.  P = objective of a candidate
-//   schedule that satisfies box and energy rows exactly; D = Lagrangian lower bound that
-//   dualises only the coupling and energy rows (the box keeps the inner minimum finite, so
-//   ANY multipliers give a valid bound).  Candidates: the current z and the projection of
-//   the running average of v; when the averaged candidate's gap has halved the iteration
-//   restarts from the average (restarted averaging gives linear convergence on the
-//   LP-like instances).  Stop when P - D <= eps_abs + eps_rel max(|P|,|D|) and the
-//   candidate's relative coupling violation <= viol_tol.
-// State: v (N x Tp) in registers, coupling v (R x Tp), bounds and partial sums in
-// shared memory; HBM is touched at load/store and for the running average only.
+// Host side of the batched solve: argument checks, launch configuration, dispatch to the
+// per-horizon kernel instantiations (acb_solve_q5.cu, acb_solve_q9.cu), and the standalone
+// charging_rate_bounds kernel.
 #include <algorithm>
-#include <cfloat>
-#include <type_traits>
-#include "acb_common.cuh"
+#include "acb_solve_kernel.cuh"
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-
-// projection of (a, b) onto the disc of radius lim
-__device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za, float& zb) {
-    float n2 = a * a + b * b;
-    float f = (n2 > lim * lim) ? lim * rsqrtf(n2) : 1.0f;
-    za = a * f;
-    zb = b * f;
-}
-
-// shared-memory layout (in floats), computed identically on host and device
-struct SmemLayout {
-    int LB, UB, PART, VC, VOUT, HG, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
-        SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
-    int OP;  // padded output count of MFT
-};
-__host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps) {
-    SmemLayout L;
-    int o = 0;
-    auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
-    L.OP = ((NG + R + ACB_OPP - 1) / ACB_OPP) * ACB_OPP;
-    L.LB = take(N * Tp);
-    L.UB = take(N * Tp);
-    // PART doubles as scratch for Sinv (R*R) and X (R*NG) while the column matrix is rebuilt
-    const int scratch = R * R + R * NG + 8;
-    L.PART = take(NP * Tp > scratch ? NP * Tp : scratch);
-    L.VC = take(R * Tp);
-    L.VOUT = take(R * Tp);
-    L.HG = take(NG * Tp);
-    L.ALPHA = take(Tp);
-    L.BETA = take(Tp);
-    L.PLIM = take(Tp);
-    L.EBAR = take(Tp);
-    L.MFT = take((NG + R) * L.OP);
-    L.CS = take(R * NG);
-    L.SESS_A = take(S_max);
-    L.SESS_B = take(S_max);
-    L.SESS_E = take(S_max);
-    L.SESS_MU = take(S_max);
-    L.SESS_MU2 = take(S_max);
-    L.SLOT = take(nSlots * 6);  // row, grp, prow, first, sess_first, sess_cnt
-    L.PGOFF = take(NG + 1);
-    L.NGRP = take(NG);
-    L.KG = take(NG);
-    L.LIM = take(R);
-    L.SCALE = take(R);
-    L.REDF = take(nwarps * ACB_NRED);
-    L.REDD = take(nwarps * ACB_NRED * 2);  // doubles
-    L.SCAL = take(32);
-    L.SCALD = take(32);  // 16 doubles
-    L.total = o;
-    return L;
-}
 size_t acb_solve_smem_bytes(const SiteDev& s, int Tp, int S_max, int nwarps) {
     return (size_t)make_layout(s.N, s.R, s.NG, s.NP, s.nSlots, Tp, S_max, nwarps).total * sizeof(float);
-}
-
-// float scalars
-enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG };
-// double scalars
-enum { SD_DBEST = 0, SD_GAPRESTART };
-// per-warp float reduction slots (max-type)
-enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA };
-// per-warp double reduction slots (sum-type)
-enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA };
-
-template <int Q, int TPW>
-__global__ void __launch_bounds__(1024, 1) acb_solve_kernel(SiteDev S, acb_batch B, acb_options opt) {
-    extern __shared__ __align__(16) float sm[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    constexpr int Tp = 32 * Q;  // the host pads every batch to an instantiated horizon
-    const int N = S.N, R = S.R, NG = S.NG, NP = S.NP;
-    const SmemLayout L = make_layout(N, R, NG, NP, S.nSlots, Tp, B.S_max, nwarps);
-    float* LB = sm + L.LB; float* UB = sm + L.UB; float* PART = sm + L.PART; float* VC = sm + L.VC;
-    float* VOUT = sm + L.VOUT; float* HG = sm + L.HG; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
-    float* PLIM = sm + L.PLIM; float* EBAR = sm + L.EBAR; float* MFT = sm + L.MFT; float* CS = sm + L.CS;
-    float* SINV = PART; float* XS = PART + R * R;
-    int* SESS_A = (int*)(sm + L.SESS_A); int* SESS_B = (int*)(sm + L.SESS_B);
-    float* SESS_E = sm + L.SESS_E; float* SESS_MU = sm + L.SESS_MU; float* SESS_MU2 = sm + L.SESS_MU2;
-    int* SLOT = (int*)(sm + L.SLOT); int* PGOFF = (int*)(sm + L.PGOFF);
-    float* NGRP = sm + L.NGRP; float* KG = sm + L.KG; float* LIM = sm + L.LIM; float* SCALE = sm + L.SCALE;
-    float* REDF = sm + L.REDF; double* REDD = (double*)(sm + L.REDD); float* SCAL = sm + L.SCAL;
-    double* SCALD = (double*)(sm + L.SCALD);
-    const int OP = L.OP, NIN = NG + R;
-
-    const int b = blockIdx.x;
-    const int Tb = B.T[b];
-    const int nS = B.n_sessions[b];
-    const int nDisc = S.nDisc, nLin = S.nLin;
-    const int rPL = 2 * nDisc + nLin, rU = rPL + S.has_pl;
-    const int nCT = nDisc + nLin + S.has_pl + S.has_u;  // coupling tasks
-    // coupling tasks run on the warps that own no EVSE rows (if any); the aggregate-power task,
-    // which carries the peak-level root find, gets a warp of its own when two or more are free
-    const int nFree = nwarps - S.nRowWarps;
-    auto task_warp = [&](int c) -> int {
-        if (nFree <= 0) return nwarps - 1 - (c % nwarps);
-        if (S.has_u && nFree >= 2) return (c == nCT - 1) ? nwarps - 1 : S.nRowWarps + (c % (nFree - 1));
-        return S.nRowWarps + (c % nFree);
-    };
-    float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
-    const bool useAvg = opt.restart && VSUM != nullptr;
-
-    // ------------------------------------------------------------------ prologue
-    for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
-    for (int i = tid; i < R * Tp; i += nthreads) {
-        VC[i] = B.warm_vc ? B.warm_vc[(size_t)b * R * Tp + i] : 0.f;
-        VOUT[i] = 0.f;
-    }
-    for (int i = tid; i < R * NG; i += nthreads) CS[i] = S.C[i];
-    for (int i = tid; i < R; i += nthreads) { LIM[i] = S.lim[i]; SCALE[i] = S.row_scale[i]; }
-    for (int i = tid; i <= NG; i += nthreads) PGOFF[i] = S.pg_off[i];
-    for (int i = tid; i < NG; i += nthreads) { NGRP[i] = S.ngrp[i]; KG[i] = S.kg[i]; }
-    for (int i = tid; i < S.nSlots; i += nthreads) {
-        SLOT[i * 6 + 0] = S.slot_row[i]; SLOT[i * 6 + 1] = S.slot_grp[i];
-        SLOT[i * 6 + 2] = S.slot_prow[i]; SLOT[i * 6 + 3] = S.slot_first[i];
-        SLOT[i * 6 + 4] = 0; SLOT[i * 6 + 5] = 0;
-    }
-    for (int i = tid; i < B.S_max; i += nthreads) {
-        bool ok = i < nS;
-        size_t k = (size_t)b * B.S_max + i;
-        SESS_A[i] = ok ? B.sess_start[k] : 0;
-        SESS_B[i] = ok ? B.sess_start[k] + B.sess_len[k] : 0;
-        SESS_E[i] = ok ? B.sess_energy[k] : 0.f;
-        SESS_MU[i] = (ok && B.warm_mu) ? B.warm_mu[k] : 0.f;
-        SESS_MU2[i] = 0.f;
-    }
-    for (int t = tid; t < Tp; t += nthreads) {
-        bool ok = t < Tb;
-        ALPHA[t] = ok ? B.alpha[(size_t)b * Tp + t] : 0.f;
-        BETA[t] = ok ? B.beta[(size_t)b * Tp + t] : 0.f;
-        EBAR[t] = (ok && B.ext) ? B.ext[(size_t)b * Tp + t] : 0.f;
-        PLIM[t] = (ok && B.peak_limit && S.has_pl) ? B.peak_limit[(size_t)b * Tp + t] / S.row_scale[rPL] : 3.0e38f;
-    }
-    __syncthreads();
-    // sessions -> bounds (charging_rate_bounds incl. the ub<lb patch) and per-slot session lists.
-    // Sessions arrive sorted by EVSE row (host packer), so each row's sessions are contiguous.
-    for (int s = warp; s < nS; s += nwarps) {
-        size_t k = (size_t)b * B.S_max + s;
-        int row = B.sess_row[k], a = SESS_A[s], len = SESS_B[s] - a, off = B.sess_rate_off[k];
-        for (int j = lane; j < len; j += 32) {
-            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
-            if (a + j < Tp) { LB[row * Tp + a + j] = lo; UB[row * Tp + a + j] = fmaxf(hi, lo); }
-        }
-    }
-    if (tid < S.nSlots) {
-        int row = SLOT[tid * 6 + 0], first = -1, cnt = 0;
-        if (row >= 0)
-            for (int s = 0; s < nS; ++s)
-                if (B.sess_row[(size_t)b * B.S_max + s] == row) { if (first < 0) first = s; ++cnt; }
-        SLOT[tid * 6 + 4] = first < 0 ? 0 : first;
-        SLOT[tid * 6 + 5] = cnt;
-    }
-    if (tid == 0) SCAL[SC_FLAG] = 0.f;
-    __syncthreads();
-    // row-level infeasibility: a session whose window cannot hold its energy equality, or whose
-    // minimum rates already exceed its energy cap (the reference would get INFEASIBLE from ECOS)
-    for (int s = warp; s < nS; s += nwarps) {
-        int row = B.sess_row[(size_t)b * B.S_max + s];
-        float slo = 0.f, shi = 0.f;
-        for (int t = SESS_A[s] + lane; t < min(SESS_B[s], Tp); t += 32) { slo += LB[row * Tp + t]; shi += UB[row * Tp + t]; }
-        slo = warp_sum(slo); shi = warp_sum(shi);
-        const float Eb = SESS_E[s], tol = 1e-5f * (fabsf(Eb) + 1.f);
-        if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) SCAL[SC_FLAG] = 1.f;
-    }
-    __syncthreads();
-    if (SCAL[SC_FLAG] != 0.f) {
-        for (int i = tid; i < N * Tp; i += nthreads) B.rates[(size_t)b * N * Tp + i] = 0.f;
-        if (tid == 0) {
-            B.status[b] = ACB_INFEASIBLE;
-            B.iters[b] = 0;
-            for (int k = 0; k < ACB_NSTATS; ++k) B.stats[(size_t)b * ACB_NSTATS + k] = 0.f;
-        }
-        return;
-    }
-    // cost scale = 1 / max |alpha_t + k_g beta_t|
-    {
-        float m = 0.f;
-        for (int i = tid; i < NG * Tp; i += nthreads) {
-            int g = i / Tp, t = i - g * Tp;
-            m = fmaxf(m, fabsf(ALPHA[t] + KG[g] * BETA[t]));
-        }
-        m = warp_max(m);
-        if (lane == 0) REDF[warp * ACB_NRED] = m;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        float m = 0.f;
-        for (int w = 0; w < nwarps; ++w) m = fmaxf(m, REDF[w * ACB_NRED]);
-        SCAL[SC_CS] = (m > 1e-20f) ? 1.0f / m : 1.0f;
-        SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : opt.rho0;
-        SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
-        SCAL[SC_FLAG] = 0.f;
-        SCAL[SC_NSUM] = 0.f;
-        SCAL[SC_NREST] = 0.f;
-        SCAL[SC_USEDAVG] = 0.f;
-        SCAL[SC_RP] = SCAL[SC_RD] = SCAL[SC_GAP] = SCAL[SC_VIOL] = 0.f;
-        SCALD[SD_DBEST] = -1.0e300;
-        SCALD[SD_GAPRESTART] = 1.0e300;
-    }
-    __syncthreads();
-    const float cs = SCAL[SC_CS];
-    for (int t = tid; t < Tp; t += nthreads) { ALPHA[t] *= cs; BETA[t] *= cs; }
-    const float qd = B.qd[b] * cs, Gamma = B.gamma[b] * cs, pk_w = B.peak_w[b] * cs, pk_p0 = B.peak_p0[b];
-    const float alpha = opt.alpha, kappa = opt.kappa;
-    float rho = SCAL[SC_RHO];
-    float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
-    const float su = S.has_u ? S.row_scale[rU] : 1.f;
-
-    // per-lane state: v for this warp's EVSE rows
-    float v1[TPW][Q];
-    const bool rowWarp = warp < S.nRowWarps;
-#pragma unroll
-    for (int k = 0; k < TPW; ++k) {
-        int row = rowWarp ? SLOT[(warp * TPW + k) * 6] : -1;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            int t = lane + 32 * q;
-            float v = 0.f;
-            if (row >= 0) {
-                if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
-                else v = clampf(0.f, LB[row * Tp + t], UB[row * Tp + t]);
-            }
-            v1[k][q] = v;
-        }
-    }
-
-    // ---- helpers --------------------------------------------------------------
-    // multiplier of the session covering period t of a row (rows with a single session use
-    // its multiplier everywhere: outside the window lb = ub = 0)
-    auto mu_at = [&](const float* MU, int sfirst, int scnt, int t) -> float {
-        float m = 0.f;
-        for (int s = sfirst; s < sfirst + scnt; ++s)
-            if (t >= SESS_A[s] && t < SESS_B[s]) m = MU[s];
-        return m;
-    };
-#define MU_ELEM(MU, sf, scn, mu0, t) ((scn) <= 1 ? (mu0) : mu_at(MU, sf, scn, t))
-    // multiplier mu with sum_{t in [a,e)} clip(vv_t - mu, lb_t, ub_t) = Eb (or <= Eb with mu >= 0):
-    // safeguarded Newton on a piecewise-linear monotone function, warm-started at mu
-    // `single`: the row has one session, so outside its window lb = ub = 0 and no mask is needed.
-    // `max_evals` = 1 gives one Newton step from the warm start without re-evaluation (used on
-    // non-check iterations: the projection is then inexact by an active-set change at most).
-    auto newton_mu = [&](const float (&vv)[Q], const float (&lb)[Q], const float (&ub)[Q], int a, int e, float Eb, float mu,
-                         bool single, int max_evals) -> float {
-        const float tol = 2e-6f * (Eb + 1.f);
-        // inequality rows: lo = -1 marks "mu = 0 not evaluated yet" (mu itself stays >= 0)
-        float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
-        if (!opt.equality) mu = fmaxf(mu, 0.f);
-        for (int step = 0; step < 16; ++step) {
-            float E = 0.f;
-            int nf = 0;
-            if (single) {
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    float w = vv[q] - mu;
-                    E += clampf(w, lb[q], ub[q]);
-                    nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    int t = lane + 32 * q;
-                    if (t >= a && t < e) {
-                        float w = vv[q] - mu;
-                        E += clampf(w, lb[q], ub[q]);
-                        nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
-                    }
-                }
-            }
-            E = warp_sum(E);
-            nf = __reduce_add_sync(0xffffffffu, nf);
-            float rr = E - Eb;
-            if (fabsf(rr) <= tol) break;
-            if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
-            if (rr > 0.f) lo = mu; else hi = mu;
-            float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
-            if (!opt.equality) mun = fmaxf(mun, 0.f);
-            if (!(mun > lo && mun < hi)) {
-                if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
-                else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
-                else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
-                if (!opt.equality) mun = fmaxf(mun, 0.f);
-            }
-            mu = mun;
-            if (step + 1 >= max_evals && nf > 0) break;
-        }
-        return mu;
-    };
-    // (NG+R)^2 matrix of the column pass for the current rho:
-    //   Sinv = U diag(1/(d/rho + lam)) U',  X = Sinv C,
-    //   hg = -C'X sa + (d/rho) X' g,   v = X sa + (I - (d/rho) Sinv) g
-    // (PART is scratch here: callers rewrite it afterwards)
-    auto build_matrix = [&]() {
-        const float dr = dd / rho;
-        for (int i = tid; i < R * R; i += nthreads) {
-            int r = i / R, c = i - r * R;
-            float acc = 0.f;
-            for (int e = 0; e < R; ++e) acc += __ldg(S.U + r * R + e) * __ldg(S.U + c * R + e) / (dr + __ldg(S.lam + e));
-            SINV[i] = acc;
-        }
-        __syncthreads();
-        for (int i = tid; i < R * NG; i += nthreads) {
-            int r = i / NG, g = i - r * NG;
-            float acc = 0.f;
-            for (int c = 0; c < R; ++c) acc += SINV[r * R + c] * CS[c * NG + g];
-            XS[i] = acc;
-        }
-        __syncthreads();
-        for (int i = tid; i < NIN * OP; i += nthreads) {
-            int c = i / OP, o = i - c * OP;
-            float m = 0.f;
-            if (o < NIN) {
-                if (o < NG && c < NG) {
-                    for (int r = 0; r < R; ++r) m -= CS[r * NG + o] * XS[r * NG + c];
-                } else if (o < NG) {
-                    m = dr * XS[(c - NG) * NG + o];
-                } else if (c < NG) {
-                    m = XS[(o - NG) * NG + c];
-                } else {
-                    int r = o - NG, j = c - NG;
-                    m = (r == j ? 1.f : 0.f) - dr * SINV[r * R + j];
-                }
-            }
-            MFT[i] = m;
-        }
-        __syncthreads();
-    };
-    // unconstrained minimiser of the aggregate-power prox (kW) given the stored v of that row
-    auto agg_a = [&](float v, int t) -> float {
-        float rp = rho / (su * su);
-        return (rp * (v * su) - 2.f * Gamma * EBAR[t]) / (rp + 2.f * Gamma);
-    };
-    // peak-epigraph level for the aggregate-power row stored in VC (called by one warp):
-    // minimise pk_w*max(p,p0) + cur/2 sum (a_t - p)_+^2 over p
-    auto peak_level = [&](float guess) -> float {
-        const int r = rU;
-        const float rp = rho / (su * su), cur = rp + 2.f * Gamma;
-        float av[Q];
-        float amax = -3.0e38f;
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            int t = lane + 32 * q;
-            av[q] = (t < Tb) ? agg_a(VC[r * Tp + t], t) : -3.0e38f;
-            amax = fmaxf(amax, av[q]);
-        }
-        amax = warp_max(amax);
-        float pl = fmaxf(amax, pk_p0);
-        if (pk_w > 0.f && amax > pk_p0) {
-            float F0 = 0.f;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) F0 += fmaxf(av[q] - pk_p0, 0.f);
-            F0 = warp_sum(F0) * cur;
-            if (F0 <= pk_w) pl = pk_p0;
-            else {
-                float p = fminf(fmaxf(guess, pk_p0), amax), lo = pk_p0, hi = amax;
-                for (int step = 0; step < 24; ++step) {
-                    float F = 0.f;
-                    int na = 0;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q)
-                        if (av[q] > p) { F += av[q] - p; ++na; }
-                    F = warp_sum(F) * cur - pk_w;
-                    na = __reduce_add_sync(0xffffffffu, na);
-                    if (fabsf(F) <= 1e-6f * pk_w) break;
-                    if (F > 0.f) lo = p; else hi = p;
-                    float pn = (na > 0) ? p + F / (cur * (float)na) : 0.5f * (lo + hi);
-                    if (!(pn > lo && pn < hi)) pn = 0.5f * (lo + hi);
-                    p = pn;
-                }
-                pl = p;
-            }
-        }
-        return pl;
-    };
-    // write partial sums of q = 2z - v for this warp's rows (z from the stored v and multipliers)
-    auto write_part_q = [&]() {
-        if (!rowWarp) return;
-#pragma unroll
-        for (int k = 0; k < TPW; ++k) {
-            const int* sl = SLOT + (warp * TPW + k) * 6;
-            int row = sl[0];
-            if (row < 0) continue;
-            int prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
-            const float mu0 = scn ? SESS_MU[sf] : 0.f;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                int t = lane + 32 * q;
-                if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sf, scn, mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
-                float val = 2.f * z - v1[k][q];
-                if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
-            }
-        }
-    };
-    // column evaluation of a candidate whose group partial sums are in PART: relative coupling
-    // violation, max and quadratic part of the aggregate power; optionally HG <- C' yc (yc in VOUT)
-    auto eval_columns = [&](bool with_hy, float& viol, float& umax, double& uq) {
-        viol = -1.f; umax = -3.0e38f; uq = 0.0;
-        for (int t = tid; t < Tp; t += nthreads) {
-            for (int g = 0; g < NG; ++g) {
-                float sz = 0.f;
-                for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) sz += PART[p * Tp + t];
-                HG[g * Tp + t] = sz;
-            }
-            int r = 0;
-            for (int j = 0; j < nDisc; ++j, r += 2) {
-                float ka = 0.f, kb = 0.f;
-                for (int g = 0; g < NG; ++g) { float sz = HG[g * Tp + t]; ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz; }
-                if (LIM[r] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / LIM[r] - 1.f);
-            }
-            for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
-                float ka = 0.f;
-                for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
-                float cap = (j == nLin) ? PLIM[t] : LIM[r];
-                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
-            }
-            if (S.has_u && t < Tb) {
-                float ka = 0.f;
-                for (int g = 0; g < NG; ++g) ka += CS[rU * NG + g] * HG[g * Tp + t];
-                float u = ka * su;
-                umax = fmaxf(umax, u);
-                uq += (double)(u + EBAR[t]) * (double)(u + EBAR[t]);
-            }
-            if (with_hy)
-                for (int g = 0; g < NG; ++g) {
-                    float acc = 0.f;
-                    for (int rr = 0; rr < R; ++rr) acc += CS[rr * NG + g] * VOUT[rr * Tp + t];
-                    HG[g * Tp + t] = acc;
-                }
-        }
-    };
-
-    build_matrix();
-    write_part_q();
-    __syncthreads();
-
-    int it = 0, status = ACB_MAX_ITER;
-    const int nParts = (NIN + ACB_OPP - 1) / ACB_OPP;
-    const int avgEvery = max(1, opt.avg_every);
-    for (it = 1; it <= opt.max_iter; ++it) {
-        const float plevel = SCAL[SC_PLEVEL];
-        // ------------------------------------------------------------ column pass
-        for (int wk = tid; wk < nParts * Tp; wk += nthreads) {
-            const int part = wk / Tp, t = wk - part * Tp;
-            const int obase = part * ACB_OPP;
-            float out[ACB_OPP];
-#pragma unroll
-            for (int k = 0; k < ACB_OPP; ++k) out[k] = 0.f;
-            const float al = ALPHA[t], be = BETA[t];
-            auto accum = [&](int c, float in) {
-                const float4 m0 = *reinterpret_cast<const float4*>(MFT + c * OP + obase);
-                const float4 m1 = *reinterpret_cast<const float4*>(MFT + c * OP + obase + 4);
-                out[0] += m0.x * in; out[1] += m0.y * in; out[2] += m0.z * in; out[3] += m0.w * in;
-                out[4] += m1.x * in; out[5] += m1.y * in; out[6] += m1.z * in; out[7] += m1.w * in;
-            };
-            for (int g = 0; g < NG; ++g) {
-                float acc = 0.f;
-                for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) acc += PART[p * Tp + t];
-                accum(g, rho1 * acc - NGRP[g] * (al + KG[g] * be));
-            }
-            int r = 0;
-            for (int j = 0; j < nDisc; ++j, r += 2) {
-                float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
-                proj_disc(a, bb, LIM[r], za, zb);
-                accum(NG + r, rho * (2.f * za - a));
-                accum(NG + r + 1, rho * (2.f * zb - bb));
-            }
-            for (int j = 0; j < nLin; ++j, ++r) {
-                float v = VC[r * Tp + t], z = fminf(v, LIM[r]);
-                accum(NG + r, rho * (2.f * z - v));
-            }
-            if (S.has_pl) {
-                float v = VC[r * Tp + t], z = fminf(v, PLIM[t]);
-                accum(NG + r, rho * (2.f * z - v));
-                ++r;
-            }
-            if (S.has_u) {
-                float v = VC[r * Tp + t], a = agg_a(v, t);
-                float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
-                accum(NG + r, rho * (2.f * z - v));
-                ++r;
-            }
-            const float inv_rho = 1.f / rho;
-#pragma unroll
-            for (int k = 0; k < ACB_OPP; ++k) {
-                int o = obase + k;
-                if (o < NG) HG[o * Tp + t] = out[k] - (al + KG[o] * be);
-                else if (o < NIN) VOUT[(o - NG) * Tp + t] = out[k] * inv_rho;
-            }
-        }
-        __syncthreads();
-        const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter);
-        const bool doAvg = useAvg && (it % avgEvery == 0);
-        const bool avgFirst = SCAL[SC_NSUM] == 0.f;
-        float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f;
-        double dPc = 0.0, dD = 0.0;  // primal (linear + diagonal part) of the current candidate; dual pieces
-        // --------------------------------------------------------------- row pass
-        // (two instantiations: the hot non-check version keeps fewer values live)
-        auto row_pass = [&](auto chk_tag) {
-            constexpr bool CHK = decltype(chk_tag)::value;
-#pragma unroll
-            for (int k = 0; k < TPW; ++k) {
-                const int* sl = SLOT + (warp * TPW + k) * 6;
-                const int row = sl[0];
-                if (row < 0) continue;
-                const int g = sl[1], prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
-                const float mu0 = scn ? SESS_MU[sf] : 0.f;
-                const float* lbp = LB + row * Tp + lane;
-                const float* ubp = UB + row * Tp + lane;
-                const float* hgp = HG + g * Tp + lane;
-                float lb[Q], ub[Q], zo[CHK ? Q : 1];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    lb[q] = lbp[32 * q];
-                    ub[q] = ubp[32 * q];
-                    float vo = v1[k][q];
-                    float z = clampf(vo - MU_ELEM(SESS_MU, sf, scn, mu0, lane + 32 * q), lb[q], ub[q]);
-                    float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
-                    v1[k][q] = vo + alpha * (x - z);
-                    if (CHK) { zo[q] = z; rE1 = fmaxf(rE1, fabsf(x - z)); rXm = fmaxf(rXm, fabsf(x)); }
-                }
-                // projection onto box ∩ energy rows: one multiplier per session
-                for (int s = sf; s < sf + scn; ++s) {
-                    float mu = newton_mu(v1[k], lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], scn == 1, 16);
-                    if (lane == 0) SESS_MU[s] = mu;
-                    __syncwarp();
-                }
-                const float mu1 = scn ? SESS_MU[sf] : 0.f;
-                float* pp = PART + prow * Tp + lane;
-                const float kgc = KG[g];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const int t = lane + 32 * q;
-                    float vn = v1[k][q];
-                    float zn = clampf(vn - MU_ELEM(SESS_MU, sf, scn, mu1, t), lb[q], ub[q]);
-                    float val = CHK ? zn : 2.f * zn - vn;
-                    if (first) pp[32 * q] = val; else pp[32 * q] += val;
-                    if (doAvg) {
-                        float* vs = VSUM + (size_t)row * Tp + t;
-                        *vs = avgFirst ? vn : *vs + vn;
-                    }
-                    if (CHK) {
-                        float c = ALPHA[t] + kgc * BETA[t];
-                        dPc += (double)(c * zn + qd * zn * zn);
-                        rE2 = fmaxf(rE2, fabsf(zn - zo[q]));
-                        rZm = fmaxf(rZm, fabsf(zn));
-                        rYm = fmaxf(rYm, fabsf(rho1 * (vn - zn)));
-                        if (!(fabsf(vn) < 1.0e30f)) rNan = 1.f;
-                    }
-                }
-            }
-        };
-        if (rowWarp) {
-            if (chk) row_pass(std::true_type{}); else row_pass(std::false_type{});
-        }
-        // ---------------------------------------------------------- coupling rows
-        // v update; on check iterations VOUT <- y = rho (v - z) and the conjugate terms of D
-        for (int c = 0; c < nCT; ++c) {
-            if (warp != task_warp(c)) continue;
-            if (c < nDisc) {
-                const int r = 2 * c;
-                const float lim = LIM[r];
-                for (int t = lane; t < Tp; t += 32) {
-                    float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
-                    proj_disc(a, bb, lim, za, zb);
-                    float ka = VOUT[r * Tp + t], kb = VOUT[(r + 1) * Tp + t];
-                    float an = a + alpha * (ka - za), bn = bb + alpha * (kb - zb);
-                    VC[r * Tp + t] = an; VC[(r + 1) * Tp + t] = bn;
-                    if (doAvg) {
-                        float* vs = VSUM + (size_t)(N + r) * Tp + t;
-                        vs[0] = avgFirst ? an : vs[0] + an; vs[Tp] = avgFirst ? bn : vs[Tp] + bn;
-                    }
-                    if (chk) {
-                        float zan, zbn;
-                        proj_disc(an, bn, lim, zan, zbn);
-                        float ya = rho * (an - zan), yb = rho * (bn - zbn);
-                        VOUT[r * Tp + t] = ya; VOUT[(r + 1) * Tp + t] = yb;
-                        dD -= (double)(lim * sqrtf(ya * ya + yb * yb));  // support function of the disc
-                    }
-                }
-            } else if (c < nDisc + nLin + S.has_pl) {
-                const int r = 2 * nDisc + (c - nDisc);
-                const bool isPL = (c == nDisc + nLin);
-                for (int t = lane; t < Tp; t += 32) {
-                    float cap = isPL ? PLIM[t] : LIM[r];
-                    float v = VC[r * Tp + t], z = fminf(v, cap), kx = VOUT[r * Tp + t];
-                    float vn = v + alpha * (kx - z);
-                    VC[r * Tp + t] = vn;
-                    if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
-                    if (chk) {
-                        float zn = fminf(vn, cap), y = rho * (vn - zn);
-                        VOUT[r * Tp + t] = y;
-                        if (y > 0.f) dD -= (double)(cap * y);  // support function of the half line
-                    }
-                }
-            } else {
-                // aggregate-power row: quadratic (load flattening) + peak epigraph
-                const int r = rU;
-                for (int t = lane; t < Tp; t += 32) {
-                    float v = VC[r * Tp + t], a = agg_a(v, t);
-                    float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
-                    float vn = v + alpha * (VOUT[r * Tp + t] - z);
-                    VC[r * Tp + t] = vn;
-                    if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
-                }
-                __syncwarp();
-                const float pl = peak_level(plevel);
-                if (lane == 0) SCAL[SC_PLEVEL] = pl;
-                if (chk) {
-                    // Fenchel equality for y in dg(z): -g*(y) = g(z) - <y, z>
-                    float zmax = -3.0e38f;
-                    double acc = 0.0;
-                    for (int t = lane; t < Tp; t += 32) {
-                        float vn = VC[r * Tp + t], an = agg_a(vn, t);
-                        float zk = (pk_w > 0.f) ? fminf(an, pl) : an;  // kW
-                        float zn = zk / su, y = rho * (vn - zn);
-                        VOUT[r * Tp + t] = y;
-                        if (t < Tb) { zmax = fmaxf(zmax, zk); acc += (double)Gamma * (double)(zk + EBAR[t]) * (double)(zk + EBAR[t]); }
-                        acc -= (double)y * (double)zn;
-                    }
-                    zmax = warp_max(zmax);
-                    dD += acc;
-                    if (lane == 0) dD += (double)pk_w * (double)fmaxf(zmax, pk_p0);
-                }
-            }
-        }
-        if (!chk) {
-            __syncthreads();
-            if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;  // next read is after the next barrier
-            continue;
-        }
-
-        // ============================================================= check path
-        __syncthreads();  // PART = group sums of z, VOUT = y
-        if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;
-        float violC, umaxC; double uqC;
-        eval_columns(true, violC, umaxC, uqC);  // HG <- C'y afterwards
-        __syncthreads();
-        // Lagrangian inner minimum over the box and energy-row terms; averaged candidate
-        const float nsum = SCAL[SC_NSUM];
-        const bool haveAvg = useAvg && nsum >= 2.f;
-        double dPa = 0.0;
-        if (rowWarp) {
-#pragma unroll
-            for (int k = 0; k < TPW; ++k) {
-                const int* sl = SLOT + (warp * TPW + k) * 6;
-                const int row = sl[0];
-                if (row < 0) continue;
-                const int g = sl[1], prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
-                const float kgc = KG[g];
-                const float mu0 = scn ? SESS_MU[sf] : 0.f;
-                float lb[Q], ub[Q], va[Q];
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    int t = lane + 32 * q;
-                    bool in = t < Tp;
-                    lb[q] = in ? LB[row * Tp + t] : 0.f;
-                    ub[q] = in ? UB[row * Tp + t] : 0.f;
-                    va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] / nsum : 0.f;
-                    if (in) {
-                        // reduced cost: c + (Khat' y) + lambda_s, lambda_s = rho1 * mu_s on the session window
-                        float lam = rho1 * MU_ELEM(SESS_MU, sf, scn, mu0, t);
-                        float rt = ALPHA[t] + kgc * BETA[t] + HG[g * Tp + t] + lam;
-                        float phi;
-                        if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lb[q], ub[q]); phi = qd * xs * xs + rt * xs; }
-                        else phi = fminf(lb[q] * rt, ub[q] * rt);
-                        dD += (double)phi;
-                    }
-                }
-                if (lane == 0)
-                    for (int s = sf; s < sf + scn; ++s) dD -= (double)(rho1 * SESS_MU[s]) * (double)SESS_E[s];
-                if (haveAvg) {
-                    for (int s = sf; s < sf + scn; ++s) {
-                        float mu = newton_mu(va, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], scn == 1, 16);
-                        if (lane == 0) SESS_MU2[s] = mu;
-                        __syncwarp();
-                    }
-                    const float mu2 = scn ? SESS_MU2[sf] : 0.f;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        int t = lane + 32 * q;
-                        if (t >= Tp) continue;
-                        float zn = clampf(va[q] - MU_ELEM(SESS_MU2, sf, scn, mu2, t), lb[q], ub[q]);
-                        if (first) PART[prow * Tp + t] = zn; else PART[prow * Tp + t] += zn;
-                        float c = ALPHA[t] + kgc * BETA[t];
-                        dPa += (double)(c * zn + qd * zn * zn);
-                    }
-                }
-            }
-        }
-        __syncthreads();  // PART = group sums of the averaged candidate
-        float violA = 3.0e38f, umaxA = -3.0e38f; double uqA = 0.0;
-        if (haveAvg) eval_columns(false, violA, umaxA, uqA);
-        // block reductions
-        rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm); rNan = warp_max(rNan);
-        violC = warp_max(violC); umaxC = warp_max(umaxC);
-        violA = warp_max(violA); umaxA = warp_max(umaxA);
-        dPc = warp_sum(dPc); dPa = warp_sum(dPa); dD = warp_sum(dD); uqC = warp_sum(uqC); uqA = warp_sum(uqA);
-        if (lane == 0) {
-            float* rf = REDF + warp * ACB_NRED;
-            rf[RF_E1] = rE1; rf[RF_E2] = rE2; rf[RF_XMAX] = rXm; rf[RF_ZMAX] = rZm; rf[RF_YMAX] = rYm; rf[RF_NAN] = rNan;
-            rf[RF_VIOLC] = violC; rf[RF_VIOLA] = violA; rf[RF_UMAXC] = umaxC; rf[RF_UMAXA] = umaxA;
-            double* rd = REDD + warp * ACB_NRED;
-            rd[RD_PC] = dPc; rd[RD_PA] = dPa; rd[RD_D] = dD; rd[RD_UQC] = uqC; rd[RD_UQA] = uqA;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, nn = 0, vC = -1.f, vA = -1.f, uC = -3.0e38f, uA = -3.0e38f;
-            double Pc = 0, Pa = 0, D = 0, qC = 0, qA = 0;
-            for (int w = 0; w < nwarps; ++w) {
-                const float* rf = REDF + w * ACB_NRED;
-                e1 = fmaxf(e1, rf[RF_E1]); e2 = fmaxf(e2, rf[RF_E2]); xm = fmaxf(xm, rf[RF_XMAX]); zm = fmaxf(zm, rf[RF_ZMAX]);
-                ym = fmaxf(ym, rf[RF_YMAX]); nn = fmaxf(nn, rf[RF_NAN]); vC = fmaxf(vC, rf[RF_VIOLC]);
-                if (haveAvg) vA = fmaxf(vA, rf[RF_VIOLA]);
-                uC = fmaxf(uC, rf[RF_UMAXC]); uA = fmaxf(uA, rf[RF_UMAXA]);
-                const double* rd = REDD + w * ACB_NRED;
-                Pc += rd[RD_PC]; Pa += rd[RD_PA]; D += rd[RD_D]; qC += rd[RD_UQC]; qA += rd[RD_UQA];
-            }
-            if (S.has_u) {
-                Pc += (double)Gamma * qC + (double)pk_w * (double)fmaxf(uC, pk_p0);
-                Pa += (double)Gamma * qA + (double)pk_w * (double)fmaxf(uA, pk_p0);
-            }
-            double Dbest = SCALD[SD_DBEST];
-            if (D == D && D > Dbest) Dbest = D;
-            SCALD[SD_DBEST] = Dbest;
-            const double gapC = Pc - Dbest, gapA = Pa - Dbest;
-            const double tolC = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pc), fabs(Dbest));
-            const double tolA = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pa), fabs(Dbest));
-            // residual estimates (only used to balance rho)
-            float rp = e1 + e2, rd_ = rho1 * (fabsf(alpha - 1.f) * e1 + e2);
-            float rp_rel = rp / fmaxf(fmaxf(xm, zm), 1e-6f), rd_rel = rd_ / fmaxf(1.0f, ym);
-            float flag = 0.f;
-            const bool okC = gapC <= tolC && vC <= opt.viol_tol;
-            const bool okA = haveAvg && gapA <= tolA && vA <= opt.viol_tol;
-            if (nn > 0.f || !(Pc == Pc)) flag = 3.f;
-            else if (okC && (!okA || gapC <= gapA)) flag = 1.f;
-            else if (okA) flag = 4.f;
-            else {
-                if (haveAvg && gapA <= 0.5 * SCALD[SD_GAPRESTART] && vA <= fmaxf(vC, opt.viol_tol) + 1e-3f) {
-                    SCALD[SD_GAPRESTART] = gapA;
-                    flag = 5.f;
-                }
-                if (opt.adapt_rho) {
-                    float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
-                    if (ratio > 5.f || ratio < 0.2f) {
-                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * ratio, 1e-4f), 1e4f);
-                        flag += 10.f;  // combined with a restart: 15
-                    }
-                }
-            }
-            SCAL[SC_FLAG] = flag;
-            SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel;
-            const bool useA = (flag == 4.f);
-            SCAL[SC_GAP] = (float)((useA ? gapA : gapC) / fmax(fmax(fabs(useA ? Pa : Pc), fabs(Dbest)), 1e-30));
-            SCAL[SC_VIOL] = useA ? vA : vC;
-        }
-        __syncthreads();
-        const float flag = SCAL[SC_FLAG];
-        if (flag == 1.f) { status = ACB_SOLVED; break; }
-        if (flag == 3.f) { status = ACB_NUMERICAL; break; }
-        const bool toAvg = (flag == 4.f) || (flag == 5.f) || (flag == 15.f);
-        if (toAvg) {
-            // adopt the averaged state: v <- mean v, multipliers of its projection, mean coupling v
-            if (rowWarp) {
-#pragma unroll
-                for (int k = 0; k < TPW; ++k) {
-                    const int* sl = SLOT + (warp * TPW + k) * 6;
-                    int row = sl[0];
-                    if (row < 0) continue;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        int t = lane + 32 * q;
-                        if (t < Tp) v1[k][q] = VSUM[(size_t)row * Tp + t] / nsum;
-                    }
-                }
-            }
-            for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = SESS_MU2[i];
-            for (int i = tid; i < R * Tp; i += nthreads) VC[i] = VSUM[(size_t)N * Tp + i] / nsum;
-            __syncthreads();
-            if (S.has_u && warp == nwarps - 1) {
-                float pl = peak_level(SCAL[SC_PLEVEL]);
-                if (lane == 0) SCAL[SC_PLEVEL] = pl;
-            }
-            if (tid == 0) { SCAL[SC_NSUM] = 0.f; SCAL[SC_NREST] += 1.f; }
-            __syncthreads();
-            if (flag == 4.f) { status = ACB_SOLVED; if (tid == 0) SCAL[SC_USEDAVG] = 1.f; break; }
-        }
-        if (it == opt.max_iter) break;
-        if (flag >= 10.f) {
-            // keep y: v <- z + (rho/rho_new)(v - z), then rebuild the column matrix
-            const float rn = SCAL[SC_NEWRHO], f = rho / rn;
-            if (rowWarp) {
-#pragma unroll
-                for (int k = 0; k < TPW; ++k) {
-                    const int* sl = SLOT + (warp * TPW + k) * 6;
-                    int row = sl[0];
-                    if (row < 0) continue;
-                    const float mu0 = sl[5] ? SESS_MU[sl[4]] : 0.f;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        int t = lane + 32 * q;
-                        if (t >= Tp) continue;
-                        float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
-                        v1[k][q] = z + f * (v1[k][q] - z);
-                    }
-                }
-            }
-            const float pl = SCAL[SC_PLEVEL];
-            for (int t = tid; t < Tp; t += nthreads) {
-                int r = 0;
-                for (int j = 0; j < nDisc; ++j, r += 2) {
-                    float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
-                    proj_disc(a, bb, LIM[r], za, zb);
-                    VC[r * Tp + t] = za + f * (a - za); VC[(r + 1) * Tp + t] = zb + f * (bb - zb);
-                }
-                for (int j = 0; j < nLin; ++j, ++r) { float v = VC[r * Tp + t], z = fminf(v, LIM[r]); VC[r * Tp + t] = z + f * (v - z); }
-                if (S.has_pl) { float v = VC[r * Tp + t], z = fminf(v, PLIM[t]); VC[r * Tp + t] = z + f * (v - z); ++r; }
-                if (S.has_u) {
-                    float v = VC[r * Tp + t], a = agg_a(v, t);
-                    float z = ((pk_w > 0.f) ? fminf(a, pl) : a) / su;
-                    VC[r * Tp + t] = z + f * (v - z);
-                }
-            }
-            __syncthreads();
-            rho = rn; rho1 = kappa * rho; dd = 2.f * qd + rho1; inv_d = 1.f / dd;
-            if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_NSUM] = 0.f; }  // the average restarts with the new metric
-            build_matrix();
-        }
-        write_part_q();
-        __syncthreads();
-    }
-    if (it > opt.max_iter) it = opt.max_iter;
-
-    // ------------------------------------------------------------------ epilogue
-    if (rowWarp) {
-#pragma unroll
-        for (int k = 0; k < TPW; ++k) {
-            const int* sl = SLOT + (warp * TPW + k) * 6;
-            int row = sl[0];
-            if (row < 0) continue;
-            const float mu0 = sl[5] ? SESS_MU[sl[4]] : 0.f;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                int t = lane + 32 * q;
-                if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
-                B.rates[((size_t)b * N + row) * Tp + t] = z;
-                if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
-            }
-        }
-    }
-    if (B.out_vc) for (int i = tid; i < R * Tp; i += nthreads) B.out_vc[(size_t)b * R * Tp + i] = VC[i];
-    if (B.out_mu) for (int i = tid; i < B.S_max; i += nthreads) B.out_mu[(size_t)b * B.S_max + i] = SESS_MU[i];
-    if (tid == 0) {
-        if (B.out_scal) { B.out_scal[b * 2] = rho; B.out_scal[b * 2 + 1] = SCAL[SC_PLEVEL]; }
-        B.status[b] = status;
-        B.iters[b] = it;
-        float* st = B.stats + (size_t)b * ACB_NSTATS;
-        st[0] = SCAL[SC_RP]; st[1] = SCAL[SC_RD]; st[2] = SCAL[SC_GAP]; st[3] = SCAL[SC_VIOL]; st[4] = rho; st[5] = cs;
-        st[6] = SCAL[SC_NREST]; st[7] = SCAL[SC_USEDAVG];
-    }
 }
 
 // charging_rate_bounds as a standalone kernel (parity tests; the solve kernel fuses it)
@@ -931,14 +27,8 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
     }
 }
 
-template <int Q, int TPW>
-static int launch_solve(acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads, size_t smem, cudaStream_t st) {
-    auto kern = acb_solve_kernel<Q, TPW>;
-    ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<batch->B, nthreads, smem, st>>>(site->d, *batch, *opt);
-    ACB_CUDA(cudaGetLastError());
-    return ACB_OK;
-}
+int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 
 extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* opt_in, void* stream) {
     if (!site || !batch || batch->B <= 0 || batch->Tp <= 0 || batch->Tp % 32 != 0) {
@@ -953,14 +43,19 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     if (opt_in) opt = *opt_in; else acb_default_options(&opt);
     ACB_CUDA(cudaSetDevice(site->device));
     const SiteDev& d = site->d;
+    const int nCT_ = d.nDisc + d.nLin + d.has_pl + d.has_u;
+    const int nCT = nCT_;
     const int Q = batch->Tp / 32;
-    if (Q != 1 && Q != 3 && Q != 5 && Q != 9) {
-        acb_set_error("acb_solve_batch: Tp must be one of 32, 96, 160, 288 (pad the horizon up)");
+    if (Q != 5 && Q != 9) {
+        acb_set_error("acb_solve_batch: Tp must be 160 or 288 (pad the horizon up)");
         return ACB_E_INVALID;
     }
-    const int nParts = (d.NG + d.R + ACB_OPP - 1) / ACB_OPP;
+    if (d.TPW != 2) { acb_set_error("acb_solve_batch: only 2 EVSE rows per warp are instantiated (N <= 64)"); return ACB_E_TOO_LARGE; }
+    const int NIN = d.NG + d.R;
+    const int nch = (NIN <= ACB_OPP) ? 1 : 3;
+    const int nParts = (NIN + ACB_OPP * nch - 1) / (ACB_OPP * nch);
+    if (nCT_ > 32) { acb_set_error("acb_solve_batch: more than 32 coupling tasks"); return ACB_E_TOO_LARGE; }
     // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
-    const int nCT = d.nDisc + d.nLin + d.has_pl + d.has_u;
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
     int nthreads = std::min(1024, ((want + 31) / 32) * 32);
     if (d.nRowWarps * 32 > 1024) { acb_set_error("acb_solve_batch: too many EVSE rows for the on-chip path"); return ACB_E_TOO_LARGE; }
@@ -970,12 +65,9 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
         return ACB_E_TOO_LARGE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const acb_options* opt_ptr = &opt;
-#define CASE(QQ, TT) if (Q == QQ && d.TPW == TT) return launch_solve<QQ, TT>(site, batch, opt_ptr, nthreads, smem, st);
-    CASE(1, 2) CASE(3, 2) CASE(5, 2) CASE(9, 2)
-#undef CASE
-    acb_set_error("acb_solve_batch: no kernel instantiation for Tp=" + std::to_string(batch->Tp) + " TPW=" + std::to_string(d.TPW));
-    return ACB_E_TOO_LARGE;
+    const bool multi = batch->multi_session != 0;
+    if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, nthreads, smem, st, multi, nch);
+    return acb_launch_solve_q9(site, batch, &opt, nthreads, smem, st, multi, nch);
 }
 
 extern "C" int acb_charging_rate_bounds(acb_site* site, const acb_batch* batch, float* lb, float* ub, void* stream) {

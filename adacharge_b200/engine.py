@@ -182,7 +182,7 @@ def pack_sessions(sessions, infra, period) -> dict:
     return out
 
 
-SUPPORTED_HORIZONS = (32, 96, 160, 288)  # padded horizons the solve kernel is instantiated for
+SUPPORTED_HORIZONS = (160, 288)  # padded horizons the solve kernel is instantiated for
 
 
 class PackedBatch:
@@ -204,6 +204,7 @@ class PackedBatch:
         Tp_, S_ = self.Tp, self.S_max
         f32, i32 = np.float32, np.int32
         h = {}
+        self.multi_session = any(len(set(i.sess_row.tolist())) < len(i.sess_row) for i in instances)
         h["T"] = np.array([i.T for i in instances], dtype=i32)
         h["n_sessions"] = np.array([len(i.sess_row) for i in instances], dtype=i32)
         for name in ("sess_row", "sess_start", "sess_len"):
@@ -279,6 +280,7 @@ class PackedBatch:
     def _fill_struct(self):
         s = self.struct
         s.B, s.Tp, s.S_max = self.B, self.Tp, self.S_max
+        s.multi_session = int(self.multi_session)
         for name in ("T", "n_sessions", "sess_row", "sess_start", "sess_len", "sess_energy", "sess_rate_off",
                      "min_rates", "max_rates", "alpha", "beta", "qd", "gamma", "ext", "peak_w", "peak_p0", "peak_limit"):
             setattr(s, name, _ptr(self.dev.get(name)))
