@@ -116,6 +116,9 @@ def cpu_oracle_throughput(n_instances, cores, seed0=0):
     """Solves `n_instances` instances of the workload with the CPU oracle, one per worker."""
     import multiprocessing as mp
 
+    # one single-threaded solver per core: set before the workers import numpy/scipy
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = "1"
     ctx = mp.get_context("spawn")
     t = time.perf_counter()
     with ctx.Pool(cores) as pool:
