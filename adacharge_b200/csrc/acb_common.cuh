@@ -12,10 +12,12 @@
 #define ACB_MAX_WARPS 32
 
 // Device view of a site (all pointers device).  Row layout of the scaled coupling
-// matrix Khat (R x N): 2*nDisc SOC rows (cos, sin pairs), nLin linear rows, then the
+// matrix Khat (R x N): 2*nDisc SOC rows (cos, sin pairs) for rows that mix phases, nLin
+// linear rows (LINEAR mode: |A| rows; SOC mode: single-phase rows, two-sided), then the
 // optional peak-limit row (1/sqrt(N)) and the optional aggregate-power row (k/|k|).
 struct SiteDev {
     int N, M, R, NG, NP, nDisc, nLin, has_pl, has_u;
+    int lin_two_sided;  // linear rows are |.| <= limit (single-phase SOC rows) instead of . <= limit (LINEAR mode)
     int TPW;        // EVSE rows per warp
     int nRowWarps;  // warps that own EVSE rows
     int nSlots;     // nRowWarps * TPW

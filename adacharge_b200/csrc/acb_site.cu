@@ -104,12 +104,8 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
     memset(&d, 0, sizeof(d));
     d.N = N;
     d.M = M;
-    d.nDisc = (constraint_type == ACB_SOC) ? M : 0;
-    d.nLin = (constraint_type == ACB_LINEAR) ? M : 0;
     d.has_pl = use_peak_row ? 1 : 0;
     d.has_u = use_agg_row ? 1 : 0;
-    const int R = 2 * d.nDisc + d.nLin + d.has_pl + d.has_u;
-    d.R = R;
 
     // float64 rows exactly as the reference forms them (utils.py:6-8)
     std::vector<double> acos_((size_t)M * N, 0.0), asin_((size_t)M * N, 0.0);
@@ -121,11 +117,33 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
                 asin_[(size_t)j * N + i] = cm[(size_t)j * N + i] * std::sin(rad);
             }
     }
+    // SOC rows whose EVSEs all share one phase angle have colinear components:
+    // ||(c s, s' s)|| = |s| with s = sum_i A_ji r_i, i.e. an exact two-sided linear row.  They are
+    // kept as single rows (half the coupling rows on the Caltech site).
+    std::vector<int> discRows, absRows;
+    if (constraint_type == ACB_SOC) {
+        for (int j = 0; j < M; ++j) {
+            bool same = true, any = false;
+            double ph0 = 0;
+            for (int i = 0; i < N; ++i)
+                if (cm[(size_t)j * N + i] != 0.0) {
+                    if (!any) { ph0 = phases_deg[i]; any = true; }
+                    else if (phases_deg[i] != ph0) same = false;
+                }
+            if (same) absRows.push_back(j); else discRows.push_back(j);
+        }
+    }
+    d.nDisc = (int)discRows.size();
+    d.nLin = (constraint_type == ACB_LINEAR) ? M : (int)absRows.size();
+    d.lin_two_sided = (constraint_type == ACB_SOC) ? 1 : 0;
+    const int R = 2 * d.nDisc + d.nLin + d.has_pl + d.has_u;
+    d.R = R;
     // scaled coupling matrix
     std::vector<double> K((size_t)R * N, 0.0), scale(R, 1.0), lim(R, 0.0), kv(N);
     for (int i = 0; i < N; ++i) kv[i] = voltages[i] / 1e3;
     int r = 0;
-    for (int j = 0; j < d.nDisc; ++j, r += 2) {
+    for (int jj = 0; jj < d.nDisc; ++jj, r += 2) {
+        const int j = discRows[jj];
         double ss = 0;
         for (int i = 0; i < N; ++i)
             ss += acos_[(size_t)j * N + i] * acos_[(size_t)j * N + i] + asin_[(size_t)j * N + i] * asin_[(size_t)j * N + i];
@@ -138,12 +156,14 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
         scale[r] = scale[r + 1] = sc;
         lim[r] = lim[r + 1] = limits[j] / sc;
     }
-    for (int j = 0; j < d.nLin; ++j, ++r) {
+    for (int jj = 0; jj < d.nLin; ++jj, ++r) {
+        const int j = (constraint_type == ACB_LINEAR) ? jj : absRows[jj];
         double ss = 0;
         for (int i = 0; i < N; ++i) ss += cm[(size_t)j * N + i] * cm[(size_t)j * N + i];
         double sc = std::sqrt(ss);
         if (!(sc > 0)) sc = 1;
-        for (int i = 0; i < N; ++i) K[(size_t)r * N + i] = std::fabs(cm[(size_t)j * N + i]) / sc;
+        for (int i = 0; i < N; ++i)
+            K[(size_t)r * N + i] = ((constraint_type == ACB_LINEAR) ? std::fabs(cm[(size_t)j * N + i]) : cm[(size_t)j * N + i]) / sc;
         scale[r] = sc;
         lim[r] = limits[j] / sc;
     }

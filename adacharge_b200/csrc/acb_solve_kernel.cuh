@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
     const int nDisc = S.nDisc, nLin = S.nLin;
     const int rPL = 2 * nDisc + nLin, rU = rPL + S.has_pl;
     const int nCT = nDisc + nLin + S.has_pl + S.has_u;  // coupling tasks
+    const float linLo = S.lin_two_sided ? -1.f : -3.0e38f;  // lower end of a linear row as a multiple of its limit
     // coupling tasks run on the warps that own no EVSE rows (if any); the aggregate-power task,
     // which carries the peak-level root find, gets a warp of its own when two or more are free
     unsigned myTasks = 0;  // bit c set <=> this warp runs coupling task c (nCT <= 32 on this path)
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
                 float ka = 0.f;
                 for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
                 float cap = (j == nLin) ? PLIM[t] : LIM[r];
+                if (j < nLin && S.lin_two_sided) ka = fabsf(ka);
                 if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
             }
             if (S.has_u && t < Tb) {
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
                 accum(NG + r + 1, rho * (2.f * zb - bb));
             }
             for (int j = 0; j < nLin; ++j, ++r) {
-                float v = VC[r * Tp + t], z = fminf(v, LIM[r]);
+                float v = VC[r * Tp + t], z = clampf(v, (linLo < -1.0e30f) ? linLo : linLo * LIM[r], LIM[r]);
                 accum(NG + r, rho * (2.f * z - v));
             }
             if (S.has_pl) {
@@ -638,16 +640,18 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
             } else if (c < nDisc + nLin + S.has_pl) {
                 const int r = 2 * nDisc + (c - nDisc);
                 const bool isPL = (c == nDisc + nLin);
+                const float lo = isPL ? -3.0e38f : linLo;
                 for (int t = lane; t < Tp; t += 32) {
                     float cap = isPL ? PLIM[t] : LIM[r];
-                    float v = VC[r * Tp + t], z = fminf(v, cap), kx = VOUT[r * Tp + t];
+                    float capLo = (lo < -1.0e30f) ? lo : lo * cap;
+                    float v = VC[r * Tp + t], z = clampf(v, capLo, cap), kx = VOUT[r * Tp + t];
                     float vn = v + alpha * (kx - z);
                     VC[r * Tp + t] = vn;
                     if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
                     if (chk) {
-                        float zn = fminf(vn, cap), y = rho * (vn - zn);
+                        float zn = clampf(vn, capLo, cap), y = rho * (vn - zn);
                         VOUT[r * Tp + t] = y;
-                        if (y > 0.f) dD -= (double)(cap * y);  // support function of the half line
+                        if (y != 0.f) dD -= (double)(cap * fabsf(y));  // support function of the half line / interval
                     }
                 }
             } else {
@@ -870,7 +874,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
                     proj_disc(a, bb, LIM[r], za, zb);
                     VC[r * Tp + t] = za + f * (a - za); VC[(r + 1) * Tp + t] = zb + f * (bb - zb);
                 }
-                for (int j = 0; j < nLin; ++j, ++r) { float v = VC[r * Tp + t], z = fminf(v, LIM[r]); VC[r * Tp + t] = z + f * (v - z); }
+                for (int j = 0; j < nLin; ++j, ++r) { float v = VC[r * Tp + t], z = clampf(v, (linLo < -1.0e30f) ? linLo : linLo * LIM[r], LIM[r]); VC[r * Tp + t] = z + f * (v - z); }
                 if (S.has_pl) { float v = VC[r * Tp + t], z = fminf(v, PLIM[t]); VC[r * Tp + t] = z + f * (v - z); ++r; }
                 if (S.has_u) {
                     float v = VC[r * Tp + t], a = agg_a(v, t);
