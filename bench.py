@@ -253,7 +253,8 @@ def main():
     achieved = alg_bytes_rank / (launch_ms / 1e3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_dram.json"))).get("dram_bytes_per_launch")
+        # measured DRAM bytes per instance (ncu, profiles/) x instances per launch on this rank
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_dram.json")))["dram_bytes_per_instance"] * args.batch
     except Exception:
         pass
     if rank == 0:
