@@ -132,13 +132,15 @@ def run_reference(args):
     if rank != 0:
         return
     cores = max(1, min(os.cpu_count() or 1, 16))
-    per_step = cores
-    for _ in range(min(args.warmup, 1)):  # one warm-up pass is enough to page the interpreter in
-        cpu_oracle_throughput(per_step, cores)
+    # bounded sample: one instance per worker, fewer workers per step when many steps are asked
+    # for, so that the whole run stays within a few minutes (an oracle solve takes 10-40 s)
+    per_step = int(min(cores, max(2, (cores * 3) // max(args.steps, 1))))
+    if args.warmup > 0:  # one small warm-up pass is enough to page the interpreter in
+        cpu_oracle_throughput(2, 2, seed0=10_000)
     t = time.perf_counter()
     n = 0
     for k in range(args.steps):
-        cpu_oracle_throughput(per_step, cores, seed0=k * per_step)
+        cpu_oracle_throughput(per_step, per_step, seed0=k * per_step)
         n += per_step
     wall = time.perf_counter() - t
     value = n / wall
@@ -146,7 +148,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": make_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": per_step, "kind": "port",
                          "sample": f"{per_step} instances of the workload per step (one per core), oracle/mpc.py interior-point restatement; "
                                    "the reference's cvxpy/ECOS path cannot run here (cvxpy, ecos, acnportal not installed)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
