@@ -48,6 +48,7 @@ struct acb_site {
     SiteDev d;
     std::vector<void*> allocs;
     int constraint_type;
+    const int* grp_off_dev;  // [NG+1] offsets of each group's rows in the (group-sorted) slot list
     size_t smem_fixed;   // bytes of shared memory independent of Tp
     size_t smem_per_col; // bytes per padded column
 };
@@ -63,3 +64,4 @@ void acb_set_error(const std::string& s);
     } while (0)
 
 size_t acb_solve_smem_bytes(const SiteDev& s, int Tp, int S_max, int nwarps);
+int acb_solve_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st);

@@ -29,6 +29,7 @@ extern "C" void acb_default_options(acb_options* o) {
     o->adapt_rho = 1;
     o->restart = 1;
     o->avg_every = 5;
+    o->path = 0;
 }
 
 // cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major), double.
@@ -260,6 +261,11 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
 #define UP(vec, field) if ((rc = upload(s, vec, &d.field)) != ACB_OK) { acb_site_destroy(s); return rc; }
     UP(slot_row, slot_row) UP(slot_grp, slot_grp) UP(slot_prow, slot_prow) UP(slot_first, slot_first)
     UP(pg_off, pg_off) UP(ngrp, ngrp) UP(kg, kg) UP(Cf, C) UP(Uf, U) UP(lamf, lam) UP(scf, row_scale) UP(limf, lim)
+    {
+        std::vector<int> goff(NG + 1, 0);
+        for (int g = 0; g < NG; ++g) goff[g + 1] = goff[g] + (int)ngrp[g];
+        if ((rc = upload(s, goff, &s->grp_off_dev)) != ACB_OK) { acb_site_destroy(s); return rc; }
+    }
     UP(acos_, a_cos) UP(asin_, a_sin) UP(lim64, limits) UP(mp, max_pilot) UP(aoff, allow_off) UP(avals, allow_vals)
 #undef UP
     *out = s;

@@ -50,21 +50,21 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
         acb_set_error("acb_solve_batch: Tp must be 160 or 288 (pad the horizon up)");
         return ACB_E_INVALID;
     }
-    if (d.TPW != 2) { acb_set_error("acb_solve_batch: only 2 EVSE rows per warp are instantiated (N <= 64)"); return ACB_E_TOO_LARGE; }
+    cudaStream_t st = (cudaStream_t)stream;
     const int NIN = d.NG + d.R;
     const int nch = (NIN <= ACB_OPP) ? 1 : 3;
     const int nParts = (NIN + ACB_OPP * nch - 1) / (ACB_OPP * nch);
-    if (nCT_ > 32) { acb_set_error("acb_solve_batch: more than 32 coupling tasks"); return ACB_E_TOO_LARGE; }
     // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
     int nthreads = std::min(1024, ((want + 31) / 32) * 32);
-    if (d.nRowWarps * 32 > 1024) { acb_set_error("acb_solve_batch: too many EVSE rows for the on-chip path"); return ACB_E_TOO_LARGE; }
     size_t smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
-    if (smem > 232448) {
-        acb_set_error("acb_solve_batch: instance needs " + std::to_string(smem) + " B of shared memory (> 232448); not supported by the on-chip path");
+    const bool fits = d.TPW == 2 && nCT_ <= 32 && d.nRowWarps * 32 <= 1024 && smem <= 232448;
+    if (opt.path == 2 || (!fits && opt.path == 0)) return acb_solve_general(site, batch, opt, st);
+    if (!fits) {
+        acb_set_error("acb_solve_batch: instance does not fit the on-chip path (N <= 64, <= 32 coupling tasks, " +
+                      std::to_string(smem) + " B of shared memory needed, 232448 available)");
         return ACB_E_TOO_LARGE;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     const bool multi = batch->multi_session != 0;
     if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, nthreads, smem, st, multi, nch);
     return acb_launch_solve_q9(site, batch, &opt, nthreads, smem, st, multi, nch);

@@ -1,0 +1,680 @@
+// General ("streaming") solve path for instances that do not fit on one SM (e.g. the
+// 1000-EVSE site of BASELINE config 5): the same ADMM split and the same rigorous
+// duality-gap stopping rule as acb_solve_kernel.cuh, with the state in HBM/L2 and one
+// kernel per phase over the whole batch:
+//   k_rows  block per (group of electrically identical EVSEs, instance): x, over-relaxed v,
+//           box ∩ energy projection (warp per row, Newton on the multiplier), group sums
+//   k_cols  block per (32-period tile, instance): the Woodbury solve in factored form
+//           b = C sa - (d/rho) g,  h = -U diag(1/(d/rho+lam)) U' b,  Kx = (g - h)/rho,
+//           hg = C'h - c, then the coupling-row v update for the tile
+//   k_level one warp per instance: peak-epigraph level of the aggregate-power row
+// and, every check_every iterations, k_chk_* / k_decide for P (candidate objective), D
+// (Lagrangian bound), violation, stopping flags and the rho balance.
+// Replaces the same reference code as the on-chip kernel (aco.py:220-321, 363-408).
+// Differences from the on-chip path: no running average / restarts; scalar reductions use
+// float64 atomics (summation order, hence the exact stopping iteration, may vary run to run).
+#include <algorithm>
+#include "acb_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double wsumd(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float wmax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+__device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za, float& zb) {
+    float n2 = a * a + b * b;
+    float f = (n2 > lim * lim) ? lim * rsqrtf(n2) : 1.0f;
+    za = a * f;
+    zb = b * f;
+}
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) {  // v >= 0
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+// per-instance scalars
+enum { GS_RHO = 0, GS_PLEVEL, GS_CS, GS_QD, GS_GAMMA, GS_PKW, GS_PKP0, GS_E1, GS_E2, GS_XMAX, GS_YMAX, GS_VIOL, GS_UMAX, GS_ZUMAX, GS_GAP, GS_RP, GS_RD, GS_N };
+enum { GD_P = 0, GD_D, GD_UQ, GD_DBEST, GD_N };
+
+struct GenWork {
+    float *V, *LB, *UB, *VC, *KX, *SG, *SGZ, *HG, *MU, *AL, *BE;  // AL/BE: cost-scaled alpha, beta [B][Tp]
+    float* scal;     // [B][GS_N]
+    double* dacc;    // [B][GD_N]
+    int* status;     // [B] -1 = running
+    int* row_first;  // [B][N] first session of the row
+    int* row_cnt;    // [B][N]
+    int* ndone;      // [1]
+    int* iters;      // [B]
+};
+
+struct GenDims {
+    int N, R, NG, Tp, Tt /*tiles*/, S_max, nDisc, nLin, has_pl, has_u, rPL, rU, lin_two_sided;
+};
+
+// ---------------------------------------------------------------------------- setup
+__global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int nS = B.n_sessions[b], Tb = B.T[b], Tp = D.Tp;
+    __shared__ float red[32];
+    __shared__ int infeas;
+    if (tid == 0) infeas = 0;
+    for (int i = tid; i < D.N; i += blockDim.x) { W.row_first[(size_t)b * D.N + i] = 0; W.row_cnt[(size_t)b * D.N + i] = 0; }
+    __syncthreads();
+    // per-row session runs (sessions are sorted by row)
+    for (int s = tid; s < nS; s += blockDim.x) {
+        const int* rows = B.sess_row + (size_t)b * B.S_max;
+        int row = rows[s];
+        if (s == 0 || rows[s - 1] != row) {
+            int c = 1;
+            while (s + c < nS && rows[s + c] == row) ++c;
+            W.row_first[(size_t)b * D.N + row] = s;
+            W.row_cnt[(size_t)b * D.N + row] = c;
+        }
+        W.MU[(size_t)b * B.S_max + s] = B.warm_mu ? B.warm_mu[(size_t)b * B.S_max + s] : 0.f;
+    }
+    // cost scale and scaled cost vectors
+    float m = 0.f;
+    for (int i = tid; i < D.NG * Tp; i += blockDim.x) {
+        int g = i / Tp, t = i - g * Tp;
+        if (t < Tb) m = fmaxf(m, fabsf(B.alpha[(size_t)b * Tp + t] + S.kg[g] * B.beta[(size_t)b * Tp + t]));
+    }
+    m = wmax(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float mm = 0.f;
+        for (int w = 0; w < nw; ++w) mm = fmaxf(mm, red[w]);
+        red[0] = (mm > 1e-20f) ? 1.f / mm : 1.f;
+    }
+    __syncthreads();
+    const float cs = red[0];
+    for (int t = tid; t < Tp; t += blockDim.x) {
+        bool ok = t < Tb;
+        W.AL[(size_t)b * Tp + t] = ok ? B.alpha[(size_t)b * Tp + t] * cs : 0.f;
+        W.BE[(size_t)b * Tp + t] = ok ? B.beta[(size_t)b * Tp + t] * cs : 0.f;
+    }
+    // row-level infeasibility (same rule as the on-chip kernel)
+    for (int s = warp; s < nS; s += nw) {
+        size_t k = (size_t)b * B.S_max + s;
+        int row = B.sess_row[k], a = B.sess_start[k], e = min(a + B.sess_len[k], Tp);
+        float slo = 0.f, shi = 0.f;
+        for (int t = a + lane; t < e; t += 32) { slo += W.LB[((size_t)b * D.N + row) * Tp + t]; shi += W.UB[((size_t)b * D.N + row) * Tp + t]; }
+        slo = wsum(slo); shi = wsum(shi);
+        float Eb = B.sess_energy[k], tol = 1e-5f * (fabsf(Eb) + 1.f);
+        if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) infeas = 1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float* sc = W.scal + (size_t)b * GS_N;
+        sc[GS_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : opt.rho0;
+        sc[GS_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
+        sc[GS_CS] = cs;
+        sc[GS_QD] = B.qd[b] * cs; sc[GS_GAMMA] = B.gamma[b] * cs; sc[GS_PKW] = B.peak_w[b] * cs; sc[GS_PKP0] = B.peak_p0[b];
+        sc[GS_E1] = sc[GS_E2] = sc[GS_XMAX] = sc[GS_YMAX] = sc[GS_VIOL] = sc[GS_UMAX] = sc[GS_ZUMAX] = sc[GS_GAP] = sc[GS_RP] = sc[GS_RD] = 0.f;
+        double* da = W.dacc + (size_t)b * GD_N;
+        da[GD_P] = da[GD_D] = da[GD_UQ] = 0.0;
+        da[GD_DBEST] = -1.0e300;
+        W.status[b] = infeas ? ACB_INFEASIBLE : -1;
+        W.iters[b] = 0;
+        if (infeas) atomicAdd(W.ndone, 1);
+    }
+    // state
+    for (int i = tid; i < D.N * Tp; i += blockDim.x) {
+        size_t k = (size_t)b * D.N * Tp + i;
+        W.V[k] = B.warm_v1 ? B.warm_v1[k] : clampf(0.f, W.LB[k], W.UB[k]);
+    }
+    for (int i = tid; i < D.R * Tp; i += blockDim.x) {
+        size_t k = (size_t)b * D.R * Tp + i;
+        W.VC[k] = B.warm_vc ? B.warm_vc[k] : 0.f;
+        W.KX[k] = 0.f;
+    }
+}
+
+// multiplier of the session covering period t
+__device__ __forceinline__ float mu_at(const float* MU, const int* SA, const int* SL, int sf, int sc, int t) {
+    float m = 0.f;
+    for (int s = sf; s < sf + sc; ++s)
+        if (t >= SA[s] && t < SA[s] + SL[s]) m = MU[s];
+    return m;
+}
+
+// MODE 0: iteration (x, v update, projection, SG <- sums of q);  MODE 1: init (SG <- sums of q from V);
+// MODE 2: check (SGZ <- sums of z, P_lin);  MODE 3: check (Lagrangian inner terms with HG = C'y);
+// MODE 4: write the schedule;  MODE 5: rescale V for a new rho (scal[GS_E1] holds rho_old/rho_new)
+template <int Q, int MODE>
+__global__ void __launch_bounds__(256) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
+    const int g = blockIdx.x, b = blockIdx.y;
+    if (W.status[b] >= 0 && MODE != 4) return;
+    constexpr int Tp = 32 * Q;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    __shared__ float part[8][Tp];
+    const float* sc = W.scal + (size_t)b * GS_N;
+    const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, inv_d = 1.f / dd, alpha = opt.alpha;
+    const float kgc = S.kg[g];
+    const float* AL = W.AL + (size_t)b * Tp;
+    const float* BE = W.BE + (size_t)b * Tp;
+    const int* SA = B.sess_start + (size_t)b * B.S_max;
+    const int* SL = B.sess_len + (size_t)b * B.S_max;
+    float* MU = W.MU + (size_t)b * B.S_max;
+    float acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = 0.f;
+    float e1 = 0.f, e2 = 0.f, xm = 0.f, ym = 0.f;
+    double dsum = 0.0;
+    const float rescale = (MODE == 5) ? sc[GS_E1] : 1.f;
+    if (MODE == 5 && rescale == 1.f) return;
+    for (int k = grp_off[g] + warp; k < grp_off[g + 1]; k += nw) {
+        const int row = S.slot_row[k];
+        const size_t base = ((size_t)b * D.N + row) * Tp + lane;
+        const int sf = W.row_first[(size_t)b * D.N + row], scn = W.row_cnt[(size_t)b * D.N + row];
+        float v[Q], lb[Q], ub[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) { v[q] = W.V[base + 32 * q]; lb[q] = W.LB[base + 32 * q]; ub[q] = W.UB[base + 32 * q]; }
+        if (MODE == 0) {
+            float zo[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int t = lane + 32 * q;
+                float z = clampf(v[q] - mu_at(MU, SA, SL, sf, scn, t), lb[q], ub[q]);
+                float x = (rho1 * (2.f * z - v[q]) + W.HG[((size_t)b * D.NG + g) * Tp + t]) * inv_d;
+                v[q] += alpha * (x - z);
+                zo[q] = z;
+                e1 = fmaxf(e1, fabsf(x - z));
+                xm = fmaxf(xm, fabsf(x));
+            }
+            for (int s = sf; s < sf + scn; ++s) {
+                const int a = SA[s], e = a + SL[s];
+                const float Eb = B.sess_energy[(size_t)b * B.S_max + s];
+                const float tol = 2e-6f * (Eb + 1.f);
+                float mu = MU[s];
+                float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
+                if (!opt.equality) mu = fmaxf(mu, 0.f);
+                for (int step = 0; step < 16; ++step) {
+                    float E = 0.f;
+                    int nf = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const int t = lane + 32 * q;
+                        if (t >= a && t < e) {
+                            float w = v[q] - mu;
+                            E += clampf(w, lb[q], ub[q]);
+                            nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
+                        }
+                    }
+                    E = wsum(E);
+                    nf = __reduce_add_sync(0xffffffffu, nf);
+                    float rr = E - Eb;
+                    if (fabsf(rr) <= tol) break;
+                    if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
+                    if (rr > 0.f) lo = mu; else hi = mu;
+                    float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
+                    if (!opt.equality) mun = fmaxf(mun, 0.f);
+                    if (!(mun > lo && mun < hi)) {
+                        if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
+                        else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
+                        else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
+                        if (!opt.equality) mun = fmaxf(mun, 0.f);
+                    }
+                    mu = mun;
+                }
+                if (lane == 0) MU[s] = mu;
+                __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int t = lane + 32 * q;
+                float zn = clampf(v[q] - mu_at(MU, SA, SL, sf, scn, t), lb[q], ub[q]);
+                acc[q] += 2.f * zn - v[q];
+                W.V[base + 32 * q] = v[q];
+                e2 = fmaxf(e2, fabsf(zn - zo[q]));
+                ym = fmaxf(ym, fabsf(rho1 * (v[q] - zn)));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int t = lane + 32 * q;
+                const float mu = mu_at(MU, SA, SL, sf, scn, t);
+                const float z = clampf(v[q] - mu, lb[q], ub[q]);
+                if (MODE == 1) acc[q] += 2.f * z - v[q];
+                if (MODE == 2) {
+                    acc[q] += z;
+                    float c = AL[t] + kgc * BE[t];
+                    dsum += (double)(c * z + qd * z * z);
+                }
+                if (MODE == 3) {
+                    float rt = AL[t] + kgc * BE[t] + W.HG[((size_t)b * D.NG + g) * Tp + t] + rho1 * mu;
+                    float phi;
+                    if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lb[q], ub[q]); phi = qd * xs * xs + rt * xs; }
+                    else phi = fminf(lb[q] * rt, ub[q] * rt);
+                    dsum += (double)phi;
+                }
+                if (MODE == 4) B.rates[base + 32 * q] = z;
+                if (MODE == 5) W.V[base + 32 * q] = z + rescale * (v[q] - z);
+            }
+            if (MODE == 3 && lane == 0)
+                for (int s = sf; s < sf + scn; ++s) dsum -= (double)(rho1 * MU[s]) * (double)B.sess_energy[(size_t)b * B.S_max + s];
+            if (MODE == 4 && B.out_v1) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) B.out_v1[base + 32 * q] = v[q];
+            }
+        }
+    }
+    if (MODE <= 2) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) part[warp][lane + 32 * q] = acc[q];
+        __syncthreads();
+        float* out = (MODE == 2 ? W.SGZ : W.SG) + ((size_t)b * D.NG + g) * Tp;
+        for (int t = tid; t < Tp; t += blockDim.x) {
+            float s = 0.f;
+            for (int w = 0; w < nw; ++w) s += part[w][t];
+            out[t] = s;
+        }
+    }
+    if (MODE == 0) {
+        e1 = wmax(e1); e2 = wmax(e2); xm = wmax(xm); ym = wmax(ym);
+        if (lane == 0) {
+            float* s = W.scal + (size_t)b * GS_N;
+            atomic_max_pos(s + GS_E1, e1); atomic_max_pos(s + GS_E2, e2); atomic_max_pos(s + GS_XMAX, xm); atomic_max_pos(s + GS_YMAX, ym);
+        }
+    }
+    if (MODE == 2 || MODE == 3) {
+        dsum = wsumd(dsum);
+        if (lane == 0) atomicAdd(W.dacc + (size_t)b * GD_N + (MODE == 2 ? GD_P : GD_D), dsum);
+    }
+}
+
+// block per (32-period tile, instance).  CHECK = 0: iteration;  CHECK = 1: evaluation of the
+// candidate (violation, aggregate-power part of P, conjugate terms of D, HG <- C'y).
+template <int CHECK>
+__global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
+    const int tile = blockIdx.x, b = blockIdx.y;
+    if (W.status[b] >= 0) return;
+    extern __shared__ float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int R = D.R, NG = D.NG, Tp = D.Tp, t = tile * 32 + lane, Tb = B.T[b];
+    float* sa = sm;                 // [NG][32]   group inputs / group sums of z
+    float* gg = sa + NG * 32;       // [R][32]    g (iteration) or y (check)
+    float* bv = gg + R * 32;        // [R][32]
+    float* y1 = bv + R * 32;        // [R][32]
+    const float* sc = W.scal + (size_t)b * GS_N;
+    const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, dr = dd / rho;
+    const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], pk_p0 = sc[GS_PKP0], plevel = sc[GS_PLEVEL];
+    const float su = D.has_u ? S.row_scale[D.rU] : 1.f;
+    const float linLo = D.lin_two_sided ? -1.f : -3.0e38f;
+    const float* AL = W.AL + (size_t)b * Tp;
+    const float* BE = W.BE + (size_t)b * Tp;
+    const float* ext = B.ext ? B.ext + (size_t)b * Tp : nullptr;
+    float* VC = W.VC + (size_t)b * R * Tp;
+    float* KX = W.KX + (size_t)b * R * Tp;
+    auto ebar = [&](int tt) -> float { return (ext && tt < Tb) ? ext[tt] : 0.f; };
+    auto plim = [&](int tt) -> float { return (B.peak_limit && tt < Tb) ? B.peak_limit[(size_t)b * Tp + tt] / S.row_scale[D.rPL] : 3.0e38f; };
+    auto agg_a = [&](float v, int tt) -> float { float rp = rho / (su * su); return (rp * (v * su) - 2.f * Gamma * ebar(tt)) / (rp + 2.f * Gamma); };
+    // z of coupling row r (disc rows are handled pairwise by the caller)
+    auto proj_row = [&](int r, float v, int tt) -> float {
+        if (r < 2 * D.nDisc + D.nLin) return clampf(v, (linLo < -1.0e30f) ? linLo : linLo * S.lim[r], S.lim[r]);
+        if (D.has_pl && r == D.rPL) return fminf(v, plim(tt));
+        float a = agg_a(v, tt);
+        return ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+    };
+    double dconj = 0.0, duq = 0.0;
+    float viol = -1.f, umax = 0.f, zumax = 0.f;
+    // ---- stage 1: inputs
+    for (int g = warp; g < NG; g += nw) {
+        float s = (CHECK ? W.SGZ : W.SG)[((size_t)b * NG + g) * Tp + t];
+        sa[g * 32 + lane] = CHECK ? s : rho1 * s - S.ngrp[g] * (AL[t] + S.kg[g] * BE[t]);
+    }
+    for (int r = warp; r < R; r += nw) {
+        float z;
+        if (r < 2 * D.nDisc) {
+            int r0 = r & ~1;
+            float a = VC[r0 * Tp + t], bb = VC[(r0 + 1) * Tp + t], za, zb;
+            proj_disc(a, bb, S.lim[r0], za, zb);
+            z = (r & 1) ? zb : za;
+        } else z = proj_row(r, VC[r * Tp + t], t);
+        float v = VC[r * Tp + t];
+        gg[r * 32 + lane] = CHECK ? rho * (v - z) : rho * (2.f * z - v);
+        if (CHECK) {
+            float y = rho * (v - z);
+            if (r < 2 * D.nDisc) {
+                // support function of the disc: after the barrier, from both components
+            } else if (r < 2 * D.nDisc + D.nLin + D.has_pl) {
+                float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
+                if (y != 0.f && cap < 1.0e30f) dconj -= (double)(cap * fabsf(y));
+            } else {
+                // aggregate-power row: Fenchel equality -g*(y) = g(z) - <y, z>; the max term is added in k_decide
+                float zk = z * su;
+                if (t < Tb) { dconj += (double)Gamma * (double)(zk + ebar(t)) * (double)(zk + ebar(t)); zumax = fmaxf(zumax, zk); }
+                dconj -= (double)y * (double)z;
+            }
+        }
+    }
+    __syncthreads();
+    if (CHECK) {
+        // disc support functions need both components
+        for (int j = warp; j < D.nDisc; j += nw) {
+            float ya = gg[(2 * j) * 32 + lane], yb = gg[(2 * j + 1) * 32 + lane];
+            dconj -= (double)(S.lim[2 * j] * sqrtf(ya * ya + yb * yb));
+        }
+        // Kz rows: violation and aggregate power of the candidate
+        for (int r = warp; r < R; r += nw) {
+            float ka = 0.f;
+            for (int g = 0; g < NG; ++g) ka += S.C[r * NG + g] * sa[g * 32 + lane];
+            bv[r * 32 + lane] = ka;
+        }
+        __syncthreads();
+        for (int j = warp; j < D.nDisc; j += nw) {
+            float ka = bv[(2 * j) * 32 + lane], kb = bv[(2 * j + 1) * 32 + lane];
+            if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f);
+        }
+        for (int r = 2 * D.nDisc + warp; r < 2 * D.nDisc + D.nLin + D.has_pl; r += nw) {
+            float ka = bv[r * 32 + lane];
+            float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
+            if (r < 2 * D.nDisc + D.nLin && D.lin_two_sided) ka = fabsf(ka);
+            if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
+        }
+        if (D.has_u && warp == 0 && t < Tb) {
+            float u = bv[D.rU * 32 + lane] * su;
+            umax = fmaxf(umax, u);
+            duq += (double)(u + ebar(t)) * (double)(u + ebar(t));
+        }
+        // HG <- C'y
+        for (int g = warp; g < NG; g += nw) {
+            float acc = 0.f;
+            for (int r = 0; r < R; ++r) acc += S.C[r * NG + g] * gg[r * 32 + lane];
+            W.HG[((size_t)b * NG + g) * Tp + t] = acc;
+        }
+        viol = wmax(viol); umax = wmax(umax); zumax = wmax(zumax);
+        dconj = wsumd(dconj); duq = wsumd(duq);
+        if (lane == 0) {
+            float* s = W.scal + (size_t)b * GS_N;
+            atomic_max_pos(s + GS_VIOL, viol + 4.f);
+            atomic_max_pos(s + GS_UMAX, fmaxf(umax, 0.f));
+            atomic_max_pos(s + GS_ZUMAX, fmaxf(zumax, 0.f));
+            atomicAdd(W.dacc + (size_t)b * GD_N + GD_D, dconj);
+            atomicAdd(W.dacc + (size_t)b * GD_N + GD_UQ, duq);
+        }
+        return;
+    }
+    // ---- stage 2: bv = C sa - (d/rho) g
+    for (int r = warp; r < R; r += nw) {
+        float acc = -dr * gg[r * 32 + lane];
+        for (int g = 0; g < NG; ++g) acc += S.C[r * NG + g] * sa[g * 32 + lane];
+        bv[r * 32 + lane] = acc;
+    }
+    __syncthreads();
+    // ---- stage 3: y1 = diag(1/(d/rho+lam)) U' bv
+    for (int e = warp; e < R; e += nw) {
+        float acc = 0.f;
+        for (int r = 0; r < R; ++r) acc += S.U[r * R + e] * bv[r * 32 + lane];
+        y1[e * 32 + lane] = acc / (dr + S.lam[e]);
+    }
+    __syncthreads();
+    // ---- stage 4: h = -U y1 (into bv), Kx = (g - h)/rho, coupling-row v update
+    for (int r = warp; r < R; r += nw) {
+        float acc = 0.f;
+        for (int e = 0; e < R; ++e) acc += S.U[r * R + e] * y1[e * 32 + lane];
+        bv[r * 32 + lane] = -acc;
+    }
+    __syncthreads();
+    for (int g = warp; g < NG; g += nw) {
+        float acc = 0.f;
+        for (int r = 0; r < R; ++r) acc += S.C[r * NG + g] * bv[r * 32 + lane];
+        W.HG[((size_t)b * NG + g) * Tp + t] = acc - (AL[t] + S.kg[g] * BE[t]);
+    }
+    for (int r = warp; r < R; r += nw) {
+        float g_ = gg[r * 32 + lane], v = VC[r * Tp + t];
+        float kx = (g_ - bv[r * 32 + lane]) / rho;
+        float z = 0.5f * (g_ / rho + v);  // g = rho (2z - v)
+        KX[r * Tp + t] = kx;
+        VC[r * Tp + t] = v + opt.alpha * (kx - z);
+    }
+}
+
+// one warp per instance: peak-epigraph level of the aggregate-power row
+__global__ void k_level(SiteDev S, acb_batch B, GenWork W, GenDims D) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    if (W.status[b] >= 0 || !D.has_u) return;
+    float* sc = W.scal + (size_t)b * GS_N;
+    const float rho = sc[GS_RHO], Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], pk_p0 = sc[GS_PKP0];
+    const float su = S.row_scale[D.rU], rp = rho / (su * su), cur = rp + 2.f * Gamma;
+    const int Tb = B.T[b], Tp = D.Tp;
+    const float* vu = W.VC + ((size_t)b * D.R + D.rU) * Tp;
+    const float* ext = B.ext ? B.ext + (size_t)b * Tp : nullptr;
+    auto a_of = [&](int t) -> float { return (rp * (vu[t] * su) - 2.f * Gamma * (ext ? ext[t] : 0.f)) / cur; };
+    float amax = -3.0e38f;
+    for (int t = lane; t < Tb; t += 32) amax = fmaxf(amax, a_of(t));
+    amax = wmax(amax);
+    float pl = fmaxf(amax, pk_p0);
+    if (pk_w > 0.f && amax > pk_p0) {
+        float F0 = 0.f;
+        for (int t = lane; t < Tb; t += 32) F0 += fmaxf(a_of(t) - pk_p0, 0.f);
+        F0 = wsum(F0) * cur;
+        if (F0 <= pk_w) pl = pk_p0;
+        else {
+            float p = fminf(fmaxf(sc[GS_PLEVEL], pk_p0), amax), lo = pk_p0, hi = amax;
+            for (int step = 0; step < 24; ++step) {
+                float F = 0.f;
+                int na = 0;
+                for (int t = lane; t < Tb; t += 32) { float a = a_of(t); if (a > p) { F += a - p; ++na; } }
+                F = wsum(F) * cur - pk_w;
+                na = __reduce_add_sync(0xffffffffu, na);
+                if (fabsf(F) <= 1e-6f * pk_w) break;
+                if (F > 0.f) lo = p; else hi = p;
+                float pn = (na > 0) ? p + F / (cur * (float)na) : 0.5f * (lo + hi);
+                if (!(pn > lo && pn < hi)) pn = 0.5f * (lo + hi);
+                p = pn;
+            }
+            pl = p;
+        }
+    }
+    if (lane == 0) sc[GS_PLEVEL] = pl;
+}
+
+// per instance: combine the check reductions, decide
+__global__ void k_decide(acb_batch B, acb_options opt, GenWork W, GenDims D, int it, int last) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B.B || W.status[b] >= 0) return;
+    float* sc = W.scal + (size_t)b * GS_N;
+    double* da = W.dacc + (size_t)b * GD_N;
+    const float rho = sc[GS_RHO], rho1 = opt.kappa * rho;
+    double P = da[GD_P], Dv = da[GD_D];
+    if (D.has_u) {
+        P += (double)sc[GS_GAMMA] * da[GD_UQ] + (double)sc[GS_PKW] * (double)fmaxf(sc[GS_UMAX], sc[GS_PKP0]);
+        Dv += (double)sc[GS_PKW] * (double)fmaxf(sc[GS_ZUMAX], sc[GS_PKP0]);
+    }
+    double Dbest = da[GD_DBEST];
+    if (Dv == Dv && Dv > Dbest) Dbest = Dv;
+    const double gap = P - Dbest, tol = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(P), fabs(Dbest));
+    const float viol = sc[GS_VIOL] - 4.f;
+    const float rp = sc[GS_E1] + sc[GS_E2], rd = rho1 * (fabsf(opt.alpha - 1.f) * sc[GS_E1] + sc[GS_E2]);
+    const float rp_rel = rp / fmaxf(sc[GS_XMAX], 1e-6f), rd_rel = rd / fmaxf(1.f, sc[GS_YMAX]);
+    sc[GS_GAP] = (float)(gap / fmax(fmax(fabs(P), fabs(Dbest)), 1e-30));
+    sc[GS_RP] = rp_rel; sc[GS_RD] = rd_rel;
+    const float viol_out = viol;
+    int st = -1;
+    float ratio_out = 1.f;
+    if (!(P == P)) st = ACB_NUMERICAL;
+    else if (gap <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;
+    else if (last) st = ACB_MAX_ITER;
+    else if (opt.adapt_rho) {
+        float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
+        if (ratio > 5.f || ratio < 0.2f) {
+            float rn = fminf(fmaxf(rho * ratio, 1e-4f), 1e4f);
+            ratio_out = rho / rn;
+            sc[GS_RHO] = rn;
+        }
+    }
+    W.iters[b] = it;
+    // reset the accumulators for the next check; GS_E1 carries the v rescale factor to k_rows<5>/k_rescale_vc
+    da[GD_P] = da[GD_D] = da[GD_UQ] = 0.0;
+    da[GD_DBEST] = Dbest;
+    sc[GS_E2] = sc[GS_XMAX] = sc[GS_YMAX] = sc[GS_UMAX] = sc[GS_ZUMAX] = 0.f;
+    sc[GS_VIOL] = viol_out;  // kept for the stats; k_clear_viol resets it before the next check
+    sc[GS_E1] = ratio_out;
+    if (st >= 0) { W.status[b] = st; atomicAdd(W.ndone, 1); }
+}
+
+// coupling rows: v <- z + f (v - z) after a rho change (f in GS_E1, rho already new: z uses the OLD rho = rho_new * f... see below)
+__global__ void k_rescale_vc(SiteDev S, acb_batch B, GenWork W, GenDims D) {
+    const int b = blockIdx.y;
+    if (W.status[b] >= 0) return;
+    float* sc = W.scal + (size_t)b * GS_N;
+    const float f = sc[GS_E1];
+    if (f == 1.f) return;
+    const int Tp = D.Tp, R = D.R, t = blockIdx.x * blockDim.x + threadIdx.x, Tb = B.T[b];
+    if (t >= Tp) return;
+    const float rho_old = sc[GS_RHO] * f;  // GS_RHO already holds the new value
+    const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], plevel = sc[GS_PLEVEL];
+    const float su = D.has_u ? S.row_scale[D.rU] : 1.f;
+    const float linLo = D.lin_two_sided ? -1.f : -3.0e38f;
+    float* VC = W.VC + (size_t)b * R * Tp;
+    int r = 0;
+    for (int j = 0; j < D.nDisc; ++j, r += 2) {
+        float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
+        proj_disc(a, bb, S.lim[r], za, zb);
+        VC[r * Tp + t] = za + f * (a - za); VC[(r + 1) * Tp + t] = zb + f * (bb - zb);
+    }
+    for (int j = 0; j < D.nLin; ++j, ++r) {
+        float v = VC[r * Tp + t], z = clampf(v, (linLo < -1.0e30f) ? linLo : linLo * S.lim[r], S.lim[r]);
+        VC[r * Tp + t] = z + f * (v - z);
+    }
+    if (D.has_pl) {
+        float cap = (B.peak_limit && t < Tb) ? B.peak_limit[(size_t)b * Tp + t] / S.row_scale[D.rPL] : 3.0e38f;
+        float v = VC[r * Tp + t], z = fminf(v, cap);
+        VC[r * Tp + t] = z + f * (v - z);
+        ++r;
+    }
+    if (D.has_u) {
+        float rp = rho_old / (su * su);
+        float e = (B.ext && t < Tb) ? B.ext[(size_t)b * Tp + t] : 0.f;
+        float v = VC[r * Tp + t], a = (rp * (v * su) - 2.f * Gamma * e) / (rp + 2.f * Gamma);
+        float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+        VC[r * Tp + t] = z + f * (v - z);
+    }
+}
+
+__global__ void k_clear_check(GenWork W, int B_) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B_) return;
+    float* sc = W.scal + (size_t)b * GS_N;
+    sc[GS_VIOL] = 0.f;  // encoded as viol + 4 by the atomic max
+    sc[GS_E1] = sc[GS_E2] = sc[GS_XMAX] = sc[GS_YMAX] = 0.f;
+}
+
+__global__ void k_finish(acb_batch B, GenWork W, GenDims D) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B.B) return;
+    const float* sc = W.scal + (size_t)b * GS_N;
+    int st = W.status[b];
+    B.status[b] = st < 0 ? ACB_MAX_ITER : st;
+    B.iters[b] = W.iters[b];
+    float* o = B.stats + (size_t)b * ACB_NSTATS;
+    o[0] = sc[GS_RP]; o[1] = sc[GS_RD]; o[2] = sc[GS_GAP]; o[3] = sc[GS_VIOL]; o[4] = sc[GS_RHO]; o[5] = sc[GS_CS]; o[6] = 0.f; o[7] = 0.f;
+    if (B.out_scal) { B.out_scal[b * 2] = sc[GS_RHO]; B.out_scal[b * 2 + 1] = sc[GS_PLEVEL]; }
+    if (B.out_mu) for (int s = 0; s < B.S_max; ++s) B.out_mu[(size_t)b * B.S_max + s] = W.MU[(size_t)b * B.S_max + s];
+}
+
+__global__ void k_bounds_general(SiteDev S, acb_batch B, float* lb, float* ub) {
+    const int b = blockIdx.x, N = S.N, Tp = B.Tp;
+    const int nS = B.n_sessions[b];
+    float* lbb = lb + (size_t)b * N * Tp;
+    float* ubb = ub + (size_t)b * N * Tp;
+    for (int i = threadIdx.x; i < N * Tp; i += blockDim.x) { lbb[i] = 0.f; ubb[i] = 0.f; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int s = warp; s < nS; s += nwarps) {
+        size_t k = (size_t)b * B.S_max + s;
+        int row = B.sess_row[k], a = B.sess_start[k], len = B.sess_len[k], off = B.sess_rate_off[k];
+        for (int j = lane; j < len; j += 32) {
+            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
+            if (a + j < Tp) { lbb[row * Tp + a + j] = lo; ubb[row * Tp + a + j] = fmaxf(hi, lo); }
+        }
+    }
+}
+
+template <int Q>
+int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st) {
+    const SiteDev& d = site->d;
+    const int B = batch->B, Tp = 32 * Q, N = d.N, R = d.R, NG = d.NG;
+    GenDims D{N, R, NG, Tp, Tp / 32, batch->S_max, d.nDisc, d.nLin, d.has_pl, d.has_u, 2 * d.nDisc + d.nLin, 2 * d.nDisc + d.nLin + d.has_pl, d.lin_two_sided};
+    // workspace
+    const size_t nNT = (size_t)B * N * Tp, nRT = (size_t)B * std::max(R, 1) * Tp, nGT = (size_t)B * NG * Tp;
+    const size_t floats = 3 * nNT + 2 * nRT + 3 * nGT + (size_t)B * batch->S_max + 2 * (size_t)B * Tp + (size_t)B * GS_N;
+    const size_t bytes = floats * sizeof(float) + (size_t)B * GD_N * sizeof(double) + ((size_t)B * (2 + 2 * N) + 4) * sizeof(int) + 256;
+    char* base = nullptr;
+    ACB_CUDA(cudaMallocAsync((void**)&base, bytes, st));
+    GenWork W;
+    char* p = base;
+    auto take = [&](size_t n, size_t sz) { void* r = p; p += ((n * sz + 15) / 16) * 16; return r; };
+    W.dacc = (double*)take((size_t)B * GD_N, 8);
+    W.V = (float*)take(nNT, 4); W.LB = (float*)take(nNT, 4); W.UB = (float*)take(nNT, 4);
+    W.VC = (float*)take(nRT, 4); W.KX = (float*)take(nRT, 4);
+    W.SG = (float*)take(nGT, 4); W.SGZ = (float*)take(nGT, 4); W.HG = (float*)take(nGT, 4);
+    W.MU = (float*)take((size_t)B * batch->S_max, 4);
+    W.AL = (float*)take((size_t)B * Tp, 4); W.BE = (float*)take((size_t)B * Tp, 4);
+    W.scal = (float*)take((size_t)B * GS_N, 4);
+    W.status = (int*)take(B, 4); W.iters = (int*)take(B, 4);
+    W.row_first = (int*)take((size_t)B * N, 4); W.row_cnt = (int*)take((size_t)B * N, 4);
+    W.ndone = (int*)take(1, 4);
+    ACB_CUDA(cudaMemsetAsync(W.ndone, 0, sizeof(int), st));
+    ACB_CUDA(cudaMemsetAsync(W.HG, 0, nGT * sizeof(float), st));
+    k_bounds_general<<<B, 256, 0, st>>>(d, *batch, W.LB, W.UB);
+    k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
+    const dim3 grow(NG, B), gcol(Tp / 32, B);
+    const size_t smem_cols = (size_t)(NG + 3 * std::max(R, 1)) * 32 * sizeof(float);
+    if (smem_cols > 48 * 1024) {
+        ACB_CUDA(cudaFuncSetAttribute(k_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    }
+    k_rows<Q, 1><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+    int h_done = 0, it = 0;
+    while (it < opt.max_iter) {
+        const int burst = std::min(opt.check_every, opt.max_iter - it);
+        for (int k = 0; k < burst; ++k) {
+            k_cols<0><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
+            k_level<<<B, 32, 0, st>>>(d, *batch, W, D);
+            if (k == burst - 1) k_clear_check<<<(B + 127) / 128, 128, 0, st>>>(W, B);
+            k_rows<Q, 0><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        }
+        it += burst;
+        // check
+        k_rows<Q, 2><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        k_cols<1><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
+        k_rows<Q, 3><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        k_decide<<<(B + 127) / 128, 128, 0, st>>>(*batch, opt, W, D, it, it >= opt.max_iter ? 1 : 0);
+        k_rows<Q, 5><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        k_rescale_vc<<<dim3((Tp + 127) / 128, B), 128, 0, st>>>(d, *batch, W, D);
+        k_rows<Q, 1><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);  // SG for the next column pass
+        ACB_CUDA(cudaMemcpyAsync(&h_done, W.ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ACB_CUDA(cudaStreamSynchronize(st));
+        if (h_done >= B) break;
+    }
+    k_rows<Q, 4><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+    k_finish<<<(B + 127) / 128, 128, 0, st>>>(*batch, W, D);
+    if (batch->out_vc) ACB_CUDA(cudaMemcpyAsync(batch->out_vc, W.VC, nRT * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    ACB_CUDA(cudaGetLastError());
+    ACB_CUDA(cudaFreeAsync(base, st));
+    return ACB_OK;
+}
+
+}  // namespace
+
+int acb_solve_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st) {
+    const int Q = batch->Tp / 32;
+    if (Q == 5) return run_general<5>(site, batch, opt, st);
+    if (Q == 9) return run_general<9>(site, batch, opt, st);
+    acb_set_error("acb_solve_batch (general path): Tp must be 160 or 288");
+    return ACB_E_INVALID;
+}

@@ -83,6 +83,7 @@ typedef struct acb_options {
     int32_t adapt_rho;   /* 1 = residual balancing */
     int32_t restart;     /* 1 = average the state and restart from the average when its gap halves */
     int32_t avg_every;   /* state is added to the average every avg_every iterations */
+    int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only */
 } acb_options;
 
 void acb_default_options(acb_options* o);

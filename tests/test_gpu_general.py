@@ -1,0 +1,98 @@
+"""General (streaming) solve path: same answers as the on-chip kernel / the oracle, and the
+1000-EVSE site of BASELINE config 5 at full size through size-independent properties plus
+the solver's own duality-gap certificate."""
+import numpy as np
+import pytest
+
+import adacharge_b200 as ab
+from adacharge_b200 import engine
+from adacharge_b200.generators import config_c2, config_c5, caltech_acn_infrastructure, hierarchical_three_phase_network, session_generator
+from oracle import mpc
+from tests.scenarios import SCENARIOS, make_interface, check_properties
+from tests.test_gpu_solver import _components, OBJ_TOL, VIOL_TOL
+
+pytestmark = pytest.mark.gpu
+GENERAL = dict(path=2)
+
+
+@pytest.mark.parametrize("name", ["tiny_feasible", "tiny_energy_equality", "tiny_same_evse", "tiny_min_charge", "tiny_peak_vector",
+                                  "large_three_soc", "large_three_linear", "tou_tiny_t4"])
+def test_reference_scenarios_general_path(require_gpu, name):
+    sc = SCENARIOS[name]
+    iface = make_interface(sc)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    aco = ab.AdaptiveChargingOptimization(_components(sc["objective"]), iface, sc.get("constraint_type", "SOC"), sc.get("equality", False),
+                                          solver_options=GENERAL)
+    R = aco.solve(S, I, peak_limit=sc.get("peak_limit"))
+    check_properties(R, sc, iface)
+    Ro = mpc.solve_mpc(sc["objective"], S, I, iface, sc.get("constraint_type", "SOC"), sc.get("equality", False), sc.get("peak_limit"), 0)
+    f, fo = (mpc.evaluate_objective(X, sc["objective"], I, iface) for X in (R, Ro))
+    assert abs(f - fo) <= OBJ_TOL * max(abs(fo), 1e-9), (f, fo, aco.last_info)
+
+
+def test_general_path_matches_oracle_golden(require_gpu, mpc_golden):
+    for g in [g for g in mpc_golden if g["config"] == "c2"]:
+        iface = ab.TestingInterface(config_c2(g["seed"], infra=caltech_acn_infrastructure(transformer_cap=g["transformer_cap"])))
+        S, I = iface.active_sessions(), iface.infrastructure_info()
+        obj = [tuple(o) for o in g["objective"]]
+        aco = ab.AdaptiveChargingOptimization(_components(obj), iface, solver_options=GENERAL)
+        R = aco.solve(S, I, prev_peak=iface.get_prev_peak())
+        f = mpc.evaluate_objective(R, obj, I, iface, S, iface.get_prev_peak())
+        assert abs(f - g["oracle_objective"]) <= OBJ_TOL * abs(g["oracle_objective"]), (g["seed"], f, g["oracle_objective"], aco.last_info)
+        v = mpc.violations(R, S, I, iface)
+        assert v["infrastructure_rel"] <= VIOL_TOL and v["energy"] <= 1e-4 and v["lb"] <= 0 and v["ub"] <= 0, v
+
+
+def _c5_like(n, T, seed, pods=10, panels=4):
+    infra = hierarchical_three_phase_network(n, evses_per_pod=pods, pods_per_panel=panels)
+    rng = np.random.default_rng(seed)
+    s = int(0.8 * n)
+    st = rng.permutation(n)[:s]
+    arr = rng.integers(0, T // 3, s)
+    dep = np.minimum(arr + rng.integers(T // 4, T, s), T)
+    dep[0] = T
+    dem = np.minimum(rng.uniform(2, 12, s), 0.9 * (dep - arr) * 32 * 208 / 1000 * 5 / 60)
+    sess = session_generator(s, arr.tolist(), dep.tolist(), dem.tolist(), dem.tolist(), [32] * s, station_ids=[infra["station_ids"][i] for i in st])
+    ext = 40 + 30 * np.sin(np.arange(T) / 7.0)
+    return {"active_sessions": sess, "infrastructure_info": infra, "current_time": 0, "period": 5, "prev_peak": 0.0,
+            "demand_charge": 15.51, "prices": np.full(T, 0.1)}, ext
+
+
+def test_mid_size_hierarchical_site_vs_oracle(require_gpu):
+    """N = 120 > 64 EVSE rows: only the general path can take it; compare with the oracle."""
+    d, ext = _c5_like(120, 48, seed=3)
+    iface = ab.TestingInterface(d)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    spec = [("load_flattening", 1.0, {"external_signal": ext}), ("non_completion_penalty", 50.0, {}), ("quick_charge", 1e-3, {})]
+    aco = ab.AdaptiveChargingOptimization(_components(spec), iface)
+    R = aco.solve(S, I)
+    Ro = mpc.solve_mpc(spec, S, I, iface)
+    f, fo = (mpc.evaluate_objective(X, spec, I, iface, S) for X in (R, Ro))
+    assert abs(f - fo) <= OBJ_TOL * abs(fo), (f, fo, aco.last_info)
+    v = mpc.violations(R, S, I, iface)
+    assert v["infrastructure_rel"] <= VIOL_TOL and v["energy"] <= 1e-4 and v["lb"] <= 0 and v["ub"] <= 0, v
+
+
+def test_config_c5_full_size_properties(require_gpu):
+    """1000 EVSEs x 288 periods, load_flattening + non_completion_penalty (BASELINE configs[4]),
+    a batch of 4: bounds, windows, energy caps and all 86 infrastructure rows hold, and the
+    solver certifies a 1e-4 duality gap for every instance."""
+    insts, ifaces = [], []
+    for seed in range(4):
+        d = config_c5(seed)
+        iface = ab.TestingInterface(d)
+        S, I = iface.active_sessions(), iface.infrastructure_info()
+        spec = [("load_flattening", 1.0, {"external_signal": d["external_signal"]}), ("non_completion_penalty", 100.0, {})]
+        aco = ab.AdaptiveChargingOptimization(_components(spec), iface)
+        insts.append(aco.build_instance(S, I))
+        ifaces.append((iface, S, I))
+    site = aco._site_for(I, insts[0])
+    pb = engine.PackedBatch(site, insts).upload().solve()
+    status = pb.status.cpu().numpy()
+    stats = pb.stats.cpu().numpy()
+    assert (status == 0).all(), (status, stats[:, :4], pb.iters.cpu().numpy())
+    assert (stats[:, 2] <= 1.05e-4).all() and (stats[:, 3] <= VIOL_TOL).all()
+    R = pb.rates.cpu().numpy().astype(np.float64)
+    for b, (iface, S, I) in enumerate(ifaces):
+        v = mpc.violations(R[b][:, : insts[b].T], S, I, iface)
+        assert v["lb"] <= 0 and v["ub"] <= 0 and v["energy"] <= 1e-4 and v["infrastructure_rel"] <= VIOL_TOL, v
