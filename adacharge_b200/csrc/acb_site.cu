@@ -20,8 +20,8 @@ extern "C" void acb_default_options(acb_options* o) {
     o->eps_abs = 1e-5f;
     o->eps_rel = 1e-4f;
     o->viol_tol = 1e-5f;
-    o->rho0 = 0.1f;
-    o->kappa = 1.0f;
+    o->rho0 = 0.07f;
+    o->kappa = 0.7f;
     o->alpha = 1.6f;
     o->max_iter = 20000;
     o->check_every = 25;

@@ -80,7 +80,7 @@ typedef struct acb_options {
     int32_t max_iter;
     int32_t check_every; /* residual check period (iterations) */
     int32_t equality;    /* enforce_energy_equality */
-    int32_t adapt_rho;   /* 1 = residual balancing */
+    int32_t adapt_rho;   /* 0 = off, 1 = residual balancing with threshold 5, n > 1 = threshold n/10 */
     int32_t restart;     /* 1 = average the state and restart from the average when its gap halves */
     int32_t avg_every;   /* state is added to the average every avg_every iterations */
     int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only */

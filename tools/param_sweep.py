@@ -1,0 +1,20 @@
+"""DEV: iterations / time to certificate on the bench workload for solver parameter variants."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, bench
+from adacharge_b200 import _cabi, engine
+B = 2368
+site, insts, _ = bench.build_instances(B, 0)
+pb = engine.PackedBatch(site, insts).upload()
+def run(**kw):
+    opt = _cabi.default_options(**kw)
+    pb.solve(opt); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); pb.solve(opt); e1.record(); torch.cuda.synchronize()
+    it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
+    print(f"{str(kw):70s} {e0.elapsed_time(e1):7.1f} ms  iters mean {it.mean():6.0f} p90 {np.percentile(it,90):6.0f} max {it.max():6d} unsolved {(st!=0).sum()}")
+run(rho0=0.07, kappa=0.7)
+for ar in (15, 20, 30):
+    run(rho0=0.07, kappa=0.7, adapt_rho=ar)
+run(rho0=0.07, kappa=0.7, adapt_rho=0)
+run(adapt_rho=20)
