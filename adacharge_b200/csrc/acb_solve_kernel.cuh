@@ -61,7 +61,7 @@ __device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za
 
 // shared-memory layout (in floats), computed identically on host and device
 struct SmemLayout {
-    int LB, UB, PART, VC, VOUT, HG, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
+    int LB, UB, PART, VC, VOUT, HG, THC, THA, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
         SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
     int OP;  // padded output count of MFT
 };
@@ -78,6 +78,8 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
     L.VC = take(R * Tp);
     L.VOUT = take(R * Tp);
     L.HG = take(NG * Tp);
+    L.THC = take(Tp);  // per-period restoration factors of the current / averaged candidate
+    L.THA = take(Tp);
     L.ALPHA = take(Tp);
     L.BETA = take(Tp);
     L.PLIM = take(Tp);
@@ -104,13 +106,13 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 }
 
 // float scalars
-enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG };
+enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS };
 // double scalars
 enum { SD_DBEST = 0, SD_GAPRESTART };
 // per-warp float reduction slots (max-type)
 enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA };
 // per-warp double reduction slots (sum-type)
-enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA };
+enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA, RD_PLC, RD_PLA };
 
 template <int Q, int TPW, bool MULTI, int NCH>
 __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L) {
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
     constexpr int Tp = 32 * Q;  // the host pads every batch to an instantiated horizon
     const int N = S.N, R = S.R, NG = S.NG, NP = S.NP;
     float* LB = sm + L.LB; float* UB = sm + L.UB; float* PART = sm + L.PART; float* VC = sm + L.VC;
-    float* VOUT = sm + L.VOUT; float* HG = sm + L.HG; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
+    float* VOUT = sm + L.VOUT; float* HG = sm + L.HG; float* THC = sm + L.THC; float* THA = sm + L.THA; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
     float* PLIM = sm + L.PLIM; float* EBAR = sm + L.EBAR; float* MFT = sm + L.MFT; float* CS = sm + L.CS;
     float* SINV = PART; float* XS = PART + R * R;
     int* SESS_A = (int*)(sm + L.SESS_A); int* SESS_B = (int*)(sm + L.SESS_B);
@@ -204,8 +206,14 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
         SLOT[tid * 6 + 4] = first < 0 ? 0 : first;
         SLOT[tid * 6 + 5] = cnt;
     }
-    if (tid == 0) SCAL[SC_FLAG] = 0.f;
+    if (tid == 0) { SCAL[SC_FLAG] = 0.f; SCAL[SC_LBPOS] = 0.f; }
+    for (int t = tid; t < Tp; t += nthreads) { THC[t] = 1.f; THA[t] = 1.f; }
     __syncthreads();
+    {
+        bool pos = false;
+        for (int i = tid; i < N * Tp; i += nthreads) pos |= (LB[i] != 0.f);
+        if (pos) SCAL[SC_LBPOS] = 1.f;  // benign race: every writer stores the same value
+    }
     // row-level infeasibility: a session whose window cannot hold its energy equality, or whose
     // minimum rates already exceed its energy cap (the reference would get INFEASIBLE from ECOS)
     for (int s = warp; s < nS; s += nwarps) {
@@ -256,6 +264,10 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
     for (int t = tid; t < Tp; t += nthreads) { ALPHA[t] *= cs; BETA[t] *= cs; }
     const float qd = B.qd[b] * cs, Gamma = B.gamma[b] * cs, pk_w = B.peak_w[b] * cs, pk_p0 = B.peak_p0[b];
     const float alpha = opt.alpha, kappa = opt.kappa;
+    // Feasibility restoration of a candidate: r_t <- theta_t r_t with theta_t = 1 / max(1, worst current/limit at t).
+    // With lb = 0, no quadratic term and inequality energy rows the scaled schedule satisfies box, energy caps and
+    // every coupling row exactly, and its objective follows from the per-group column sums.
+    const bool canRestore = (SCAL[SC_LBPOS] == 0.f) && (qd == 0.f) && !opt.equality;
     float rho = SCAL[SC_RHO];
     float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
     const float su = S.has_u ? S.row_scale[rU] : 1.f;
@@ -447,31 +459,38 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
     };
     // column evaluation of a candidate whose group partial sums are in PART: relative coupling
     // violation, max and quadratic part of the aggregate power; optionally HG <- C' yc (yc in VOUT)
-    auto eval_columns = [&](bool with_hy, float& viol, float& umax, double& uq) {
-        viol = -1.f; umax = -3.0e38f; uq = 0.0;
+    auto eval_columns = [&](bool with_hy, float* TH, float& viol, float& umax, double& uq, double& plin) {
+        viol = -1.f; umax = -3.0e38f; uq = 0.0; plin = 0.0;
         for (int t = tid; t < Tp; t += nthreads) {
+            float pcol = 0.f;
             for (int g = 0; g < NG; ++g) {
                 float sz = 0.f;
                 for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) sz += PART[p * Tp + t];
                 HG[g * Tp + t] = sz;
+                pcol += (ALPHA[t] + KG[g] * BETA[t]) * sz;  // linear cost of the period (same coefficient within a group)
             }
+            float worst = 0.f;  // worst current / limit of the period
             int r = 0;
             for (int j = 0; j < nDisc; ++j, r += 2) {
                 float ka = 0.f, kb = 0.f;
                 for (int g = 0; g < NG; ++g) { float sz = HG[g * Tp + t]; ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz; }
-                if (LIM[r] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / LIM[r] - 1.f);
+                if (LIM[r] > 0.f) worst = fmaxf(worst, sqrtf(ka * ka + kb * kb) / LIM[r]);
             }
             for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
                 float ka = 0.f;
                 for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
                 float cap = (j == nLin) ? PLIM[t] : LIM[r];
                 if (j < nLin && S.lin_two_sided) ka = fabsf(ka);
-                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
+                if (cap > 0.f && cap < 1.0e30f) worst = fmaxf(worst, ka / cap);
             }
+            const float th = (canRestore && worst > 1.f) ? 1.f / (worst * (1.f + 2e-7f)) : 1.f;
+            TH[t] = th;
+            viol = fmaxf(viol, worst * th - 1.f);
+            plin += (double)(th * pcol);
             if (S.has_u && t < Tb) {
                 float ka = 0.f;
                 for (int g = 0; g < NG; ++g) ka += CS[rU * NG + g] * HG[g * Tp + t];
-                float u = ka * su;
+                float u = ka * su * th;
                 umax = fmaxf(umax, u);
                 uq += (double)(u + EBAR[t]) * (double)(u + EBAR[t]);
             }
@@ -694,8 +713,8 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
         // ============================================================= check path
         __syncthreads();  // PART = group sums of z, VOUT = y
         if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;
-        float violC, umaxC; double uqC;
-        eval_columns(true, violC, umaxC, uqC);  // HG <- C'y afterwards
+        float violC, umaxC; double uqC, plC;
+        eval_columns(true, THC, violC, umaxC, uqC, plC);  // HG <- C'y afterwards
         __syncthreads();
         // Lagrangian inner minimum over the box and energy-row terms; averaged candidate
         const float nsum = SCAL[SC_NSUM];
@@ -750,24 +769,25 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
             }
         }
         __syncthreads();  // PART = group sums of the averaged candidate
-        float violA = 3.0e38f, umaxA = -3.0e38f; double uqA = 0.0;
-        if (haveAvg) eval_columns(false, violA, umaxA, uqA);
+        float violA = 3.0e38f, umaxA = -3.0e38f; double uqA = 0.0, plA = 0.0;
+        if (haveAvg) eval_columns(false, THA, violA, umaxA, uqA, plA);
         // block reductions
         rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm); rNan = warp_max(rNan);
         violC = warp_max(violC); umaxC = warp_max(umaxC);
         violA = warp_max(violA); umaxA = warp_max(umaxA);
         dPc = warp_sum(dPc); dPa = warp_sum(dPa); dD = warp_sum(dD); uqC = warp_sum(uqC); uqA = warp_sum(uqA);
+        plC = warp_sum(plC); plA = warp_sum(plA);
         if (lane == 0) {
             float* rf = REDF + warp * ACB_NRED;
             rf[RF_E1] = rE1; rf[RF_E2] = rE2; rf[RF_XMAX] = rXm; rf[RF_ZMAX] = rZm; rf[RF_YMAX] = rYm; rf[RF_NAN] = rNan;
             rf[RF_VIOLC] = violC; rf[RF_VIOLA] = violA; rf[RF_UMAXC] = umaxC; rf[RF_UMAXA] = umaxA;
             double* rd = REDD + warp * ACB_NRED;
-            rd[RD_PC] = dPc; rd[RD_PA] = dPa; rd[RD_D] = dD; rd[RD_UQC] = uqC; rd[RD_UQA] = uqA;
+            rd[RD_PC] = dPc; rd[RD_PA] = dPa; rd[RD_D] = dD; rd[RD_UQC] = uqC; rd[RD_UQA] = uqA; rd[RD_PLC] = plC; rd[RD_PLA] = plA;
         }
         __syncthreads();
         if (tid == 0) {
             float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, nn = 0, vC = -1.f, vA = -1.f, uC = -3.0e38f, uA = -3.0e38f;
-            double Pc = 0, Pa = 0, D = 0, qC = 0, qA = 0;
+            double Pc = 0, Pa = 0, D = 0, qC = 0, qA = 0, lC = 0, lA = 0;
             for (int w = 0; w < nwarps; ++w) {
                 const float* rf = REDF + w * ACB_NRED;
                 e1 = fmaxf(e1, rf[RF_E1]); e2 = fmaxf(e2, rf[RF_E2]); xm = fmaxf(xm, rf[RF_XMAX]); zm = fmaxf(zm, rf[RF_ZMAX]);
@@ -775,8 +795,9 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
                 if (haveAvg) vA = fmaxf(vA, rf[RF_VIOLA]);
                 uC = fmaxf(uC, rf[RF_UMAXC]); uA = fmaxf(uA, rf[RF_UMAXA]);
                 const double* rd = REDD + w * ACB_NRED;
-                Pc += rd[RD_PC]; Pa += rd[RD_PA]; D += rd[RD_D]; qC += rd[RD_UQC]; qA += rd[RD_UQA];
+                Pc += rd[RD_PC]; Pa += rd[RD_PA]; D += rd[RD_D]; qC += rd[RD_UQC]; qA += rd[RD_UQA]; lC += rd[RD_PLC]; lA += rd[RD_PLA];
             }
+            if (canRestore) { Pc = lC; Pa = lA; }  // objective of the restored (scaled) candidates, from the column sums
             if (S.has_u) {
                 Pc += (double)Gamma * qC + (double)pk_w * (double)fmaxf(uC, pk_p0);
                 Pa += (double)Gamma * qA + (double)pk_w * (double)fmaxf(uA, pk_p0);
@@ -894,6 +915,8 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
     if (it > opt.max_iter) it = opt.max_iter;
 
     // ------------------------------------------------------------------ epilogue
+    __syncthreads();  // SC_USEDAVG (written by thread 0 just before leaving the loop) must be visible
+    const float* THX = (SCAL[SC_USEDAVG] != 0.f) ? THA : THC;  // restoration factors of the returned candidate
     if (rowWarp) {
 #pragma unroll
         for (int k = 0; k < TPW; ++k) {
@@ -906,7 +929,7 @@ __global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, con
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
                 float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
-                B.rates[((size_t)b * N + row) * Tp + t] = z;
+                B.rates[((size_t)b * N + row) * Tp + t] = z * THX[t];
                 if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
             }
         }

@@ -112,6 +112,7 @@ class SiteReplay:
         pilots = engine.project_continuous(self.site, pb.rates.to(torch.float64))  # pp.py:77-94 on device
         first = pilots[:, :, 0].cpu().numpy()
         it, st = pb.iters.cpu().numpy(), pb.status.cpu().numpy()
+        self.last_stats = pb.stats.cpu().numpy()  # rows: r_prim, r_dual, gap, violation, rho, cost scale, restarts, averaged
         stats.iters.append(it)
         stats.status.append(st)
         # apply the first-period pilots (the simulator side)
