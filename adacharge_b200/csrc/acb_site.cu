@@ -201,7 +201,7 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
     const int NG = (int)gfirst.size();
     d.NG = NG;
     // slots: EVSEs ordered by group, TPW per warp
-    int TPW = 2;
+    int TPW = 3;  // EVSE rows per warp of the on-chip kernel (3 rows, 768-thread blocks, 80 registers: fastest of 2/3/4 measured)
     if (const char* e = getenv("ACB_TPW")) TPW = std::max(1, atoi(e));
     while ((N + TPW - 1) / TPW > ACB_MAX_WARPS) ++TPW;
     d.TPW = TPW;

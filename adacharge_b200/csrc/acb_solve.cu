@@ -56,12 +56,12 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     const int nParts = (NIN + ACB_OPP * nch - 1) / (ACB_OPP * nch);
     // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
-    int nthreads = std::min(1024, ((want + 31) / 32) * 32);
+    int nthreads = std::min(768, ((want + 31) / 32) * 32);
     size_t smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
-    const bool fits = d.TPW == 2 && nCT_ <= 32 && d.nRowWarps * 32 <= 1024 && smem <= 232448;
+    const bool fits = d.TPW == 3 && nCT_ <= 32 && nthreads <= 768 && d.nRowWarps * 32 <= nthreads && smem <= 232448;
     if (opt.path == 2 || (!fits && opt.path == 0)) return acb_solve_general(site, batch, opt, st);
     if (!fits) {
-        acb_set_error("acb_solve_batch: instance does not fit the on-chip path (N <= 64, <= 32 coupling tasks, " +
+        acb_set_error("acb_solve_batch: instance does not fit the on-chip path (N <= ~66 EVSEs, <= 32 coupling tasks, " +
                       std::to_string(smem) + " B of shared memory needed, 232448 available)");
         return ACB_E_TOO_LARGE;
     }

@@ -115,7 +115,7 @@ enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, 
 enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA, RD_PLC, RD_PLA };
 
 template <int Q, int TPW, bool MULTI, int NCH>
-__global__ void __launch_bounds__(1024, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L) {
+__global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -961,8 +961,8 @@ int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_o
 #define ACB_INSTANTIATE_Q(QQ)                                                                                              \
     int acb_launch_solve_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads,         \
                                size_t smem, cudaStream_t st, bool multi, int nch) {                                        \
-        if (!multi && nch == 1) return acb_launch_solve_t<QQ, 2, false, 1>(site, batch, opt, nthreads, smem, st);           \
-        if (!multi && nch == 3) return acb_launch_solve_t<QQ, 2, false, 3>(site, batch, opt, nthreads, smem, st);           \
-        if (multi && nch == 1) return acb_launch_solve_t<QQ, 2, true, 1>(site, batch, opt, nthreads, smem, st);             \
-        return acb_launch_solve_t<QQ, 2, true, 3>(site, batch, opt, nthreads, smem, st);                                    \
+        if (!multi && nch == 1) return acb_launch_solve_t<QQ, 3, false, 1>(site, batch, opt, nthreads, smem, st);           \
+        if (!multi && nch == 3) return acb_launch_solve_t<QQ, 3, false, 3>(site, batch, opt, nthreads, smem, st);           \
+        if (multi && nch == 1) return acb_launch_solve_t<QQ, 3, true, 1>(site, batch, opt, nthreads, smem, st);             \
+        return acb_launch_solve_t<QQ, 3, true, 3>(site, batch, opt, nthreads, smem, st);                                    \
     }
