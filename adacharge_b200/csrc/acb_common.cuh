@@ -31,6 +31,9 @@ struct SiteDev {
     const float* kg;        // [NG] kW per A
     const float* C;         // [R*NG] distinct scaled columns of Khat
     const float* U;         // [R*R] eigenvectors of Khat Khat' (U[r*R+e])
+    const float* Up;        // [R*Rp] U with rows padded to Rp = roundup(R, 4) (general path, float4 loads)
+    const float* Ut;        // [R*Rp] U' padded the same way
+    int Rp;
     const float* lam;       // [R] eigenvalues
     const float* row_scale; // [R]
     const float* lim;       // [R] limit / row_scale (disc rows: both entries; 0 for pl/u rows)

@@ -266,6 +266,15 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
         for (int g = 0; g < NG; ++g) goff[g + 1] = goff[g] + (int)ngrp[g];
         if ((rc = upload(s, goff, &s->grp_off_dev)) != ACB_OK) { acb_site_destroy(s); return rc; }
     }
+    {
+        const int Rp = (R + 3) & ~3;
+        d.Rp = Rp;
+        std::vector<float> up((size_t)std::max(R, 1) * std::max(Rp, 4), 0.f), ut((size_t)std::max(R, 1) * std::max(Rp, 4), 0.f);
+        for (int a = 0; a < R; ++a)
+            for (int b2 = 0; b2 < R; ++b2) { up[(size_t)a * Rp + b2] = Uf[(size_t)a * R + b2]; ut[(size_t)a * Rp + b2] = Uf[(size_t)b2 * R + a]; }
+        if ((rc = upload(s, up, &d.Up)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        if ((rc = upload(s, ut, &d.Ut)) != ACB_OK) { acb_site_destroy(s); return rc; }
+    }
     UP(acos_, a_cos) UP(asin_, a_sin) UP(lim64, limits) UP(mp, max_pilot) UP(aoff, allow_off) UP(avals, allow_vals)
 #undef UP
     *out = s;

@@ -154,7 +154,7 @@ __device__ __forceinline__ float mu_at(const float* MU, const int* SA, const int
 // MODE 2: check (SGZ <- sums of z, P_lin);  MODE 3: check (Lagrangian inner terms with HG = C'y);
 // MODE 4: write the schedule;  MODE 5: rescale V for a new rho (scal[GS_E1] holds rho_old/rho_new)
 template <int Q, int MODE>
-__global__ void __launch_bounds__(256) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
+__global__ void __launch_bounds__(256, 3) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
     const int g = blockIdx.x, b = blockIdx.y;
     if (W.status[b] >= 0 && MODE != 4) return;
     constexpr int Tp = 32 * Q;
@@ -306,8 +306,9 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
     const int R = D.R, NG = D.NG, Tp = D.Tp, t = tile * 32 + lane, Tb = B.T[b];
     float* sa = sm;                 // [NG][32]   group inputs / group sums of z
     float* gg = sa + NG * 32;       // [R][32]    g (iteration) or y (check)
-    float* bv = gg + R * 32;        // [R][32]
-    float* y1 = bv + R * 32;        // [R][32]
+    const int Rp = S.Rp;            // R rounded up to a multiple of 4; the padding rows of bv / y1 stay zero
+    float* bv = gg + R * 32;        // [Rp][32]
+    float* y1 = bv + Rp * 32;       // [Rp][32]
     const float* sc = W.scal + (size_t)b * GS_N;
     const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, dr = dd / rho;
     const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], pk_p0 = sc[GS_PKP0], plevel = sc[GS_PLEVEL];
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
     };
     double dconj = 0.0, duq = 0.0;
     float viol = -1.f, umax = 0.f, zumax = 0.f;
+    for (int i = tid; i < (Rp - R) * 32; i += blockDim.x) { bv[R * 32 + i] = 0.f; y1[R * 32 + i] = 0.f; }
     // ---- stage 1: inputs
     for (int g = warp; g < NG; g += nw) {
         float s = (CHECK ? W.SGZ : W.SG)[((size_t)b * NG + g) * Tp + t];
@@ -414,19 +416,34 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
         bv[r * 32 + lane] = acc;
     }
     __syncthreads();
-    // ---- stage 3: y1 = diag(1/(d/rho+lam)) U' bv
-    for (int e = warp; e < R; e += nw) {
-        float acc = 0.f;
-        for (int r = 0; r < R; ++r) acc += S.U[r * R + e] * bv[r * 32 + lane];
-        y1[e * 32 + lane] = acc / (dr + S.lam[e]);
-    }
+    // ---- stages 3 and 4: y1 = diag(1/(d/rho+lam)) U' bv,  h = -U y1 (into bv).
+    // Register-blocked: a warp produces 4 output rows per pass from float4 loads of the padded
+    // matrix rows (warp-uniform addresses) and one shared-memory value per input row.
+    auto mat_apply = [&](const float* __restrict__ Mat, const float* __restrict__ in, float* __restrict__ out, bool scale) {
+        for (int e0 = warp * 4; e0 < R; e0 += nw * 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const float4* m0 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 0, R - 1) * Rp);
+            const float4* m1 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 1, R - 1) * Rp);
+            const float4* m2 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 2, R - 1) * Rp);
+            const float4* m3 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 3, R - 1) * Rp);
+            for (int r4 = 0; r4 < Rp / 4; ++r4) {
+                const float4 w0 = __ldg(m0 + r4), w1 = __ldg(m1 + r4), w2 = __ldg(m2 + r4), w3 = __ldg(m3 + r4);
+                const float b0 = in[(4 * r4 + 0) * 32 + lane], b1 = in[(4 * r4 + 1) * 32 + lane];
+                const float b2 = in[(4 * r4 + 2) * 32 + lane], b3 = in[(4 * r4 + 3) * 32 + lane];
+                a0 += w0.x * b0 + w0.y * b1 + w0.z * b2 + w0.w * b3;
+                a1 += w1.x * b0 + w1.y * b1 + w1.z * b2 + w1.w * b3;
+                a2 += w2.x * b0 + w2.y * b1 + w2.z * b2 + w2.w * b3;
+                a3 += w3.x * b0 + w3.y * b1 + w3.z * b2 + w3.w * b3;
+            }
+            const float acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (e0 + i < R) out[(e0 + i) * 32 + lane] = scale ? acc[i] / (dr + S.lam[e0 + i]) : -acc[i];
+        }
+    };
+    mat_apply(S.Ut, bv, y1, true);
     __syncthreads();
-    // ---- stage 4: h = -U y1 (into bv), Kx = (g - h)/rho, coupling-row v update
-    for (int r = warp; r < R; r += nw) {
-        float acc = 0.f;
-        for (int e = 0; e < R; ++e) acc += S.U[r * R + e] * y1[e * 32 + lane];
-        bv[r * 32 + lane] = -acc;
-    }
+    mat_apply(S.Up, y1, bv, false);
     __syncthreads();
     for (int g = warp; g < NG; g += nw) {
         float acc = 0.f;
@@ -613,6 +630,14 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     const size_t nNT = (size_t)B * N * Tp, nRT = (size_t)B * std::max(R, 1) * Tp, nGT = (size_t)B * NG * Tp;
     const size_t floats = 3 * nNT + 2 * nRT + 3 * nGT + (size_t)B * batch->S_max + 2 * (size_t)B * Tp + (size_t)B * GS_N;
     const size_t bytes = floats * sizeof(float) + (size_t)B * GD_N * sizeof(double) + ((size_t)B * (2 + 2 * N) + 4) * sizeof(int) + 256;
+    {
+        // keep the stream-ordered pool's memory across calls (the default threshold of 0 gives it back at every sync)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, site->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     char* base = nullptr;
     ACB_CUDA(cudaMallocAsync((void**)&base, bytes, st));
     GenWork W;
@@ -633,7 +658,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     k_bounds_general<<<B, 256, 0, st>>>(d, *batch, W.LB, W.UB);
     k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
     const dim3 grow(NG, B), gcol(Tp / 32, B);
-    const size_t smem_cols = (size_t)(NG + 3 * std::max(R, 1)) * 32 * sizeof(float);
+    const size_t smem_cols = (size_t)(NG + std::max(R, 1) + 2 * std::max(d.Rp, 4)) * 32 * sizeof(float);
     if (smem_cols > 48 * 1024) {
         ACB_CUDA(cudaFuncSetAttribute(k_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));

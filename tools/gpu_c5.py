@@ -21,9 +21,11 @@ print(f"host packing {time.time()-t0:.1f}s")
 site = aco._site_for(I, insts[0])
 print("site R", site.R, "NG", site.NG)
 pb = engine.PackedBatch(site, insts).upload()
-pb.solve(); torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); pb.solve(); e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1)
-it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
-print(f"C5 B={B}: {ms:.1f} ms -> {B/ms*1e3:.1f} solves/s; iters mean {it.mean():.0f} max {it.max()}; status {np.bincount(st, minlength=4)}; {ms*1e3/it.max():.1f} us per batch-iteration")
+for kw in (dict(), dict(rho0=0.1, kappa=1.0), dict(rho0=0.2, kappa=1.0), dict(rho0=0.1, kappa=2.0)):
+  opt = _cabi.default_options(**kw)
+  pb.solve(opt); torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(); pb.solve(opt); e1.record(); torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1)
+  it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
+  print(kw, f"C5 B={B}: {ms:.1f} ms -> {B/ms*1e3:.1f} solves/s; iters mean {it.mean():.0f} max {it.max()}; status {np.bincount(st, minlength=4)}; {ms*1e3/it.max():.1f} us per batch-iteration")
