@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 const float* lbp = LB + row * Tp + lane;
                 const float* ubp = UB + row * Tp + lane;
                 const float* hgp = HG + g * Tp + lane;
-                float lb[Q], ub[Q], zo[CHK ? Q : 1];
+                float lb[Q], ub[Q], zo[CHK ? Q : 1], xs[CHK ? Q : 1];
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     lb[q] = lbp[32 * q];
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     float z = clampf(vo - MU_ELEM(SESS_MU, sf, scn, mu0, lane + 32 * q), lb[q], ub[q]);
                     float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
                     v1[k][q] = vo + alpha * (x - z);
-                    if (CHK) { zo[q] = z; rE1 = fmaxf(rE1, fabsf(x - z)); rXm = fmaxf(rXm, fabsf(x)); }
+                    if (CHK) { zo[q] = z; xs[q] = x; rXm = fmaxf(rXm, fabsf(x)); }
                 }
                 // projection onto box ∩ energy rows: one multiplier per session
                 for (int s = sf; s < sf + scn; ++s) {
@@ -620,7 +620,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     if (CHK) {
                         float c = ALPHA[t] + kgc * BETA[t];
                         dPc += (double)(c * zn + qd * zn * zn);
-                        rE2 = fmaxf(rE2, fabsf(zn - zo[q]));
+                        rE1 = fmaxf(rE1, fabsf(xs[q] - zn));  // primal residual x - z
+                        rE2 = fmaxf(rE2, fabsf(zn - zo[q]));  // dual residual / rho1
                         rZm = fmaxf(rZm, fabsf(zn));
                         rYm = fmaxf(rYm, fabsf(rho1 * (vn - zn)));
                         if (!(fabsf(vn) < 1.0e30f)) rNan = 1.f;
@@ -809,7 +810,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             const double tolC = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pc), fabs(Dbest));
             const double tolA = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pa), fabs(Dbest));
             // residual estimates (only used to balance rho)
-            float rp = e1 + e2, rd_ = rho1 * (fabsf(alpha - 1.f) * e1 + e2);
+            float rp = e1, rd_ = rho1 * e2;
             float rp_rel = rp / fmaxf(fmaxf(xm, zm), 1e-6f), rd_rel = rd_ / fmaxf(1.0f, ym);
             float flag = 0.f;
             const bool okC = gapC <= tolC && vC <= opt.viol_tol;

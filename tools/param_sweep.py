@@ -13,8 +13,8 @@ def run(**kw):
     e0.record(); pb.solve(opt); e1.record(); torch.cuda.synchronize()
     it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
     print(f"{str(kw):70s} {e0.elapsed_time(e1):7.1f} ms  iters mean {it.mean():6.0f} p90 {np.percentile(it,90):6.0f} max {it.max():6d} unsolved {(st!=0).sum()}")
-run(rho0=0.07, kappa=0.7)
-for ar in (15, 20, 30):
-    run(rho0=0.07, kappa=0.7, adapt_rho=ar)
-run(rho0=0.07, kappa=0.7, adapt_rho=0)
-run(adapt_rho=20)
+run()
+for ar in (0, 15, 20, 30, 100):
+    run(adapt_rho=ar)
+run(adapt_rho=20, rho0=0.2)
+run(adapt_rho=20, rho0=0.02)
