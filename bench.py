@@ -134,7 +134,7 @@ def run_reference(args):
     cores = max(1, min(os.cpu_count() or 1, 16))
     # bounded sample: one instance per worker, fewer workers per step when many steps are asked
     # for, so that the whole run stays within a few minutes (an oracle solve takes 10-40 s)
-    per_step = int(min(cores, max(2, (cores * 3) // max(args.steps, 1))))
+    per_step = cores if args.steps <= 6 else int(min(cores, max(2, (cores * 6) // max(args.steps, 1))))
     if args.warmup > 0:  # one small warm-up pass is enough to page the interpreter in
         cpu_oracle_throughput(2, 2, seed0=10_000)
     t = time.perf_counter()
