@@ -29,6 +29,8 @@ extern "C" void acb_default_options(acb_options* o) {
     o->adapt_rho = 1;
     o->restart = 1;
     o->avg_every = 5;
+    o->stall_checks = 4;
+    o->max_rescues = 1;
     o->path = 0;
 }
 

@@ -551,6 +551,9 @@ __global__ void k_rescale_vc(SiteDev S, acb_batch B, GenWork W, GenDims D) {
     const float f = sc[GS_E1];
     if (f == 1.f) return;
     const int Tp = D.Tp, R = D.R, t = blockIdx.x * blockDim.x + threadIdx.x, Tb = B.T[b];
+    // mu = (energy-row dual) / rho1 scales with the penalty like v - z does (k_rows<5> ran before this kernel)
+    if (blockIdx.x == 0)
+        for (int s2 = threadIdx.x; s2 < B.S_max; s2 += blockDim.x) W.MU[(size_t)b * B.S_max + s2] *= f;
     if (t >= Tp) return;
     const float rho_old = sc[GS_RHO] * f;  // GS_RHO already holds the new value
     const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], plevel = sc[GS_PLEVEL];

@@ -106,9 +106,9 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 }
 
 // float scalars
-enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS };
+enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE };
 // double scalars
-enum { SD_DBEST = 0, SD_GAPRESTART };
+enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP };
 // per-warp float reduction slots (max-type)
 enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA };
 // per-warp double reduction slots (sum-type)
@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         SCAL[SC_RP] = SCAL[SC_RD] = SCAL[SC_GAP] = SCAL[SC_VIOL] = 0.f;
         SCALD[SD_DBEST] = -1.0e300;
         SCALD[SD_GAPRESTART] = 1.0e300;
+        SCALD[SD_BESTGAP] = 1.0e300;
+        SCAL[SC_STALL] = 0.f;
+        SCAL[SC_NRESCUE] = 0.f;
     }
     __syncthreads();
     const float cs = SCAL[SC_CS];
@@ -823,7 +826,24 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     SCALD[SD_GAPRESTART] = gapA;
                     flag = 5.f;
                 }
-                if (opt.adapt_rho) {
+                // stagnation rescue: the best gap has not improved by 10 % over `stall_checks` checks ->
+                // change the penalty once to 3x and, if that stalls too, once to 1/3 of the start value
+                {
+                    const double gbest = fmin(gapC, haveAvg ? gapA : gapC);
+                    if (gbest < 0.9 * SCALD[SD_BESTGAP]) { SCALD[SD_BESTGAP] = gbest; SCAL[SC_STALL] = 0.f; }
+                    else SCAL[SC_STALL] += 1.f;
+                    if (flag == 0.f && opt.stall_checks > 0 && SCAL[SC_STALL] >= (float)opt.stall_checks && SCAL[SC_NRESCUE] < (float)opt.max_rescues) {
+                        const int k = (int)SCAL[SC_NRESCUE];
+                        const float fac = (k == 0) ? 3.f : 1.f / 9.f;  // first try a stiffer penalty, then a softer one
+                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * fac, 1e-4f), 1e4f);
+                        SCAL[SC_NRESCUE] = (float)(k + 1);
+                        SCAL[SC_STALL] = 0.f;
+                        SCALD[SD_BESTGAP] = 1.0e300;
+                        SCALD[SD_GAPRESTART] = 1.0e300;
+                        flag = 10.f;
+                    }
+                }
+                if (opt.adapt_rho && flag < 10.f) {
                     const float opt_ratio = (opt.adapt_rho > 1) ? 0.1f * (float)opt.adapt_rho : 5.f;  // adapt_rho = 10 x threshold, 1 = default 5
                     float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
                     if (ratio > opt_ratio || ratio < 1.f / opt_ratio) {
@@ -889,6 +909,9 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     }
                 }
             }
+            __syncthreads();  // every row warp has used the old multipliers
+            // mu = (energy-row dual) / rho1 scales with the penalty like v - z does
+            for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] *= f;
             const float pl = SCAL[SC_PLEVEL];
             for (int t = tid; t < Tp; t += nthreads) {
                 int r = 0;

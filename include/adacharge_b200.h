@@ -83,6 +83,8 @@ typedef struct acb_options {
     int32_t adapt_rho;   /* 0 = off, 1 = residual balancing with threshold 5, n > 1 = threshold n/10 */
     int32_t restart;     /* 1 = average the state and restart from the average when its gap halves */
     int32_t avg_every;   /* state is added to the average every avg_every iterations */
+    int32_t stall_checks; /* change rho when the best gap has not improved by 10 % over this many checks (0 = never) */
+    int32_t max_rescues;  /* at most this many stagnation rescues (1st: rho x3, 2nd: rho /9) */
     int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only */
 } acb_options;
 
