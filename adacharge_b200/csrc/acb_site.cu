@@ -26,7 +26,7 @@ extern "C" void acb_default_options(acb_options* o) {
     o->max_iter = 20000;
     o->check_every = 25;
     o->equality = 0;
-    o->adapt_rho = 1;
+    o->adapt_rho = 0;  // residual balancing measured worse than the fixed penalty + stagnation rescue on every workload tried
     o->restart = 1;
     o->avg_every = 5;
     o->stall_checks = 4;

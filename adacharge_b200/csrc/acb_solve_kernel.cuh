@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     // every coupling row exactly, and its objective follows from the per-group column sums.
     const bool canRestore = (SCAL[SC_LBPOS] == 0.f) && (qd == 0.f) && !opt.equality;
     float rho = SCAL[SC_RHO];
+    const float rho_start = rho;  // what a warm start of the next solve inherits (a stagnation rescue is not carried over)
     float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
     const float su = S.has_u ? S.row_scale[rU] : 1.f;
 
@@ -847,7 +848,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     const float opt_ratio = (opt.adapt_rho > 1) ? 0.1f * (float)opt.adapt_rho : 5.f;  // adapt_rho = 10 x threshold, 1 = default 5
                     float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
                     if (ratio > opt_ratio || ratio < 1.f / opt_ratio) {
-                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * ratio, 1e-4f), 1e4f);
+                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * ratio, 0.1f * rho_start), 10.f * rho_start);  // stay within a decade of the start value
                         flag += 10.f;  // combined with a restart: 15
                     }
                 }
@@ -961,7 +962,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     if (B.out_vc) for (int i = tid; i < R * Tp; i += nthreads) B.out_vc[(size_t)b * R * Tp + i] = VC[i];
     if (B.out_mu) for (int i = tid; i < B.S_max; i += nthreads) B.out_mu[(size_t)b * B.S_max + i] = SESS_MU[i];
     if (tid == 0) {
-        if (B.out_scal) { B.out_scal[b * 2] = rho; B.out_scal[b * 2 + 1] = SCAL[SC_PLEVEL]; }
+        if (B.out_scal) { B.out_scal[b * 2] = (SCAL[SC_NRESCUE] > 0.f) ? rho_start : rho; B.out_scal[b * 2 + 1] = SCAL[SC_PLEVEL]; }
         B.status[b] = status;
         B.iters[b] = it;
         float* st = B.stats + (size_t)b * ACB_NSTATS;
