@@ -22,14 +22,14 @@ extern "C" void acb_default_options(acb_options* o) {
     o->viol_tol = 1e-5f;
     o->rho0 = 0.07f;
     o->kappa = 0.7f;
-    o->alpha = 1.6f;
+    o->alpha = 1.7f;
     o->max_iter = 20000;
     o->check_every = 25;
     o->equality = 0;
     o->adapt_rho = 0;  // residual balancing measured worse than the fixed penalty + stagnation rescue on every workload tried
     o->restart = 1;
     o->avg_every = 5;
-    o->stall_checks = 4;
+    o->stall_checks = 3;
     o->max_rescues = 1;
     o->path = 0;
 }

@@ -507,6 +507,11 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         }
     };
 
+    // the running sums are accumulated with fire-and-forget reductions, so they start from zero
+    auto zero_sums = [&]() {
+        if (useAvg) for (int i = tid; i < (N + R) * Tp; i += nthreads) VSUM[i] = 0.f;
+    };
+    zero_sums();
     build_matrix();
     write_part_q();
     __syncthreads();
@@ -619,7 +624,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     if (first) pp[32 * q] = val; else pp[32 * q] += val;
                     if (doAvg) {
                         float* vs = VSUM + (size_t)row * Tp + t;
-                        *vs = avgFirst ? vn : *vs + vn;
+                        atomicAdd(vs, vn);  // result unused -> RED: no load latency on the hot path
                     }
                     if (CHK) {
                         float c = ALPHA[t] + kgc * BETA[t];
@@ -651,7 +656,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     VC[r * Tp + t] = an; VC[(r + 1) * Tp + t] = bn;
                     if (doAvg) {
                         float* vs = VSUM + (size_t)(N + r) * Tp + t;
-                        vs[0] = avgFirst ? an : vs[0] + an; vs[Tp] = avgFirst ? bn : vs[Tp] + bn;
+                        atomicAdd(vs, an); atomicAdd(vs + Tp, bn);
                     }
                     if (chk) {
                         float zan, zbn;
@@ -671,7 +676,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     float v = VC[r * Tp + t], z = clampf(v, capLo, cap), kx = VOUT[r * Tp + t];
                     float vn = v + alpha * (kx - z);
                     VC[r * Tp + t] = vn;
-                    if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
+                    if (doAvg) { atomicAdd(VSUM + (size_t)(N + r) * Tp + t, vn); }
                     if (chk) {
                         float zn = clampf(vn, capLo, cap), y = rho * (vn - zn);
                         VOUT[r * Tp + t] = y;
@@ -686,7 +691,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
                     float vn = v + alpha * (VOUT[r * Tp + t] - z);
                     VC[r * Tp + t] = vn;
-                    if (doAvg) { float* vs = VSUM + (size_t)(N + r) * Tp + t; *vs = avgFirst ? vn : *vs + vn; }
+                    if (doAvg) { atomicAdd(VSUM + (size_t)(N + r) * Tp + t, vn); }
                 }
                 __syncwarp();
                 const float pl = peak_level(plevel);
@@ -886,6 +891,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 float pl = peak_level(SCAL[SC_PLEVEL]);
                 if (lane == 0) SCAL[SC_PLEVEL] = pl;
             }
+            zero_sums();
             if (tid == 0) { SCAL[SC_NSUM] = 0.f; SCAL[SC_NREST] += 1.f; }
             __syncthreads();
             if (flag == 4.f) { status = ACB_SOLVED; if (tid == 0) SCAL[SC_USEDAVG] = 1.f; break; }
@@ -931,6 +937,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             }
             __syncthreads();
             rho = rn; rho1 = kappa * rho; dd = 2.f * qd + rho1; inv_d = 1.f / dd;
+            zero_sums();
             if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_NSUM] = 0.f; }  // the average restarts with the new metric
             build_matrix();
         }

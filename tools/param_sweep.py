@@ -13,7 +13,7 @@ def run(**kw):
     e0.record(); pb.solve(opt); e1.record(); torch.cuda.synchronize()
     it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
     print(f"{str(kw):70s} {e0.elapsed_time(e1):7.1f} ms  iters mean {it.mean():6.0f} p90 {np.percentile(it,90):6.0f} max {it.max():6d} unsolved {(st!=0).sum()}")
-run(stall_checks=0)
-for sc in (4, 6, 8, 12):
-    run(stall_checks=sc, max_rescues=1)
-run(stall_checks=6, max_rescues=2)
+run()
+run(restart=0)
+run(avg_every=3)
+run(avg_every=2)
