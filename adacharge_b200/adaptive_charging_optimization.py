@@ -329,6 +329,10 @@ class AdaptiveChargingOptimization:
 
     def _options(self, inst: Optional[engine.Instance] = None):
         opts = dict(self.solver_options)
+        # The library default (and the benchmark) stop at the metric's 1e-4 relative gap.  The reference's own tests
+        # check per-session energy to 1e-4 relative (tests/test_adaptive_charging_optimization.py:53-65), which a
+        # 1e-4 objective gap does not imply, so the drop-in class asks for 2e-5 unless told otherwise.
+        opts.setdefault("eps_rel", 2e-5)
         if inst is not None and inst.gamma > 0 and "rho0" not in opts and "kappa" not in opts:
             # problems with the aggregate quadratic (load_flattening) like a stiffer penalty: measured
             # 100 vs 153 iterations on the 1000-EVSE config; the library default is tuned

@@ -125,9 +125,10 @@ def test_batch_equals_single_and_is_deterministic(require_gpu):
         aco = ab.AdaptiveChargingOptimization(obj, iface)
         insts.append(aco.build_instance(S, I, None, iface.get_prev_peak()))
         singles.append(aco.solve(S, I, prev_peak=iface.get_prev_peak()))
-    pb = engine.PackedBatch(aco._site_for(I, insts[0]), insts).upload().solve()
+    opt = aco._options(insts[0])  # the drop-in class's defaults (eps_rel 2e-5), same as the single solves
+    pb = engine.PackedBatch(aco._site_for(I, insts[0]), insts).upload().solve(opt)
     a = pb.rates.cpu().numpy().copy()
-    pb.solve()
+    pb.solve(opt)
     np.testing.assert_array_equal(a, pb.rates.cpu().numpy())
     assert (pb.status.cpu().numpy() == 0).all()
     for b, inst in enumerate(insts):
