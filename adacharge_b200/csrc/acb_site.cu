@@ -30,7 +30,13 @@ extern "C" void acb_default_options(acb_options* o) {
     o->restart = 1;
     o->avg_every = 5;
     o->stall_checks = 3;
-    o->max_rescues = 1;
+    o->max_rescues = 1;  // a 2nd rescue (cold reset of a warm-started solve) measured worse on the 1024-site replay
+    o->stall_exit = 0;
+    o->dual_refine = 1;
+    o->term_floor = 0.05f;
+    // development overrides (parameter sweeps without touching the callers)
+    if (const char* e = getenv("ACB_DUAL_REFINE")) o->dual_refine = atoi(e);
+    if (const char* e = getenv("ACB_STALL_EXIT")) o->stall_exit = atoi(e);
     o->path = 0;
 }
 

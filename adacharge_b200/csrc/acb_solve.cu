@@ -21,7 +21,8 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
         size_t k = (size_t)b * B.S_max + s;
         int row = B.sess_row[k], a = B.sess_start[k], len = B.sess_len[k], off = B.sess_rate_off[k];
         for (int j = lane; j < len; j += 32) {
-            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
+            const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
+            float lo = B.min_rates[ri], hi = B.max_rates[ri];
             if (a + j < Tp) { lbb[row * Tp + a + j] = lo; ubb[row * Tp + a + j] = fmaxf(hi, lo); }
         }
     }

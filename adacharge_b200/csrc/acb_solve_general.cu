@@ -507,17 +507,20 @@ __global__ void k_decide(acb_batch B, acb_options opt, GenWork W, GenDims D, int
     double* da = W.dacc + (size_t)b * GD_N;
     const float rho = sc[GS_RHO], rho1 = opt.kappa * rho;
     double P = da[GD_P], Dv = da[GD_D];
+    double mag = fabs(P);  // magnitude of the objective's terms (see the on-chip kernel: the terms can cancel)
     if (D.has_u) {
-        P += (double)sc[GS_GAMMA] * da[GD_UQ] + (double)sc[GS_PKW] * (double)fmaxf(sc[GS_UMAX], sc[GS_PKP0]);
+        const double gterm = (double)sc[GS_GAMMA] * da[GD_UQ] + (double)sc[GS_PKW] * (double)fmaxf(sc[GS_UMAX], sc[GS_PKP0]);
+        P += gterm; mag += fabs(gterm);
         Dv += (double)sc[GS_PKW] * (double)fmaxf(sc[GS_ZUMAX], sc[GS_PKP0]);
     }
+    mag = fmax(fabs(P), (double)opt.term_floor * mag);
     double Dbest = da[GD_DBEST];
     if (Dv == Dv && Dv > Dbest) Dbest = Dv;
-    const double gap = P - Dbest, tol = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(P), fabs(Dbest));
+    const double gap = P - Dbest, tol = (double)opt.eps_abs + (double)opt.eps_rel * fmax(mag, fabs(Dbest));
     const float viol = sc[GS_VIOL] - 4.f;
     const float rp = sc[GS_E1] + sc[GS_E2], rd = rho1 * (fabsf(opt.alpha - 1.f) * sc[GS_E1] + sc[GS_E2]);
     const float rp_rel = rp / fmaxf(sc[GS_XMAX], 1e-6f), rd_rel = rd / fmaxf(1.f, sc[GS_YMAX]);
-    sc[GS_GAP] = (float)(gap / fmax(fmax(fabs(P), fabs(Dbest)), 1e-30));
+    sc[GS_GAP] = (float)(gap / fmax(fmax(mag, fabs(Dbest)), 1e-30));
     sc[GS_RP] = rp_rel; sc[GS_RD] = rd_rel;
     const float viol_out = viol;
     int st = -1;
@@ -618,7 +621,8 @@ __global__ void k_bounds_general(SiteDev S, acb_batch B, float* lb, float* ub) {
         size_t k = (size_t)b * B.S_max + s;
         int row = B.sess_row[k], a = B.sess_start[k], len = B.sess_len[k], off = B.sess_rate_off[k];
         for (int j = lane; j < len; j += 32) {
-            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
+            const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
+            float lo = B.min_rates[ri], hi = B.max_rates[ri];
             if (a + j < Tp) { lbb[row * Tp + a + j] = lo; ubb[row * Tp + a + j] = fmaxf(hi, lo); }
         }
     }

@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         size_t k = (size_t)b * B.S_max + s;
         int row = B.sess_row[k], a = SESS_A[s], len = SESS_B[s] - a, off = B.sess_rate_off[k];
         for (int j = lane; j < len; j += 32) {
-            float lo = B.min_rates[off + j], hi = B.max_rates[off + j];
+            const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
+            float lo = B.min_rates[ri], hi = B.max_rates[ri];
             if (a + j < Tp) { LB[row * Tp + a + j] = lo; UB[row * Tp + a + j] = fmaxf(hi, lo); }
         }
     }
@@ -354,6 +355,50 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             if (step + 1 >= max_evals && nf > 0) break;
         }
         return mu;
+    };
+    // Best energy-row multiplier for the dual bound: the maximiser over lam (>= 0 for inequality rows) of
+    //   -lam Eb + sum_{t in [a,e)} min_{lb <= r <= ub} (aa_t + lam) r + qd r^2,
+    // a concave function of lam whose slope is sum_t r_t(lam) - Eb: bracket around lam0, then bisect.  Any lam
+    // gives a valid bound; the iterate's own multiplier drifts along degenerate dual faces (a site sitting at its
+    // previous peak), this one does not.
+    auto dual_lambda = [&](const float (&aa)[Q], const float (&lb)[Q], const float (&ub)[Q], int a, int e, float Eb, float lam0,
+                           bool single) -> float {
+        auto total = [&](float lam) -> float {
+            float Ssum = 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int t = lane + 32 * q;
+                if (single || (t >= a && t < e)) {
+                    const float rt = aa[q] + lam;
+                    Ssum += (qd > 0.f) ? clampf(-rt / (2.f * qd), lb[q], ub[q]) : (rt < 0.f ? ub[q] : lb[q]);
+                }
+            }
+            return warp_sum(Ssum);
+        };
+        const bool ineq = !opt.equality;
+        const float l0 = ineq ? fmaxf(lam0, 0.f) : lam0;
+        float step = 1e-3f * (1.f + fabsf(l0)), lo, hi;
+        if (total(l0) > Eb) {
+            lo = l0; hi = l0 + step;
+            for (int i = 0; i < 14 && total(hi) > Eb; ++i) { lo = hi; step *= 8.f; hi = lo + step; }
+        } else {
+            if (ineq && l0 <= 0.f) return 0.f;
+            hi = l0; lo = l0 - step;
+            for (int i = 0; i < 14; ++i) {
+                if (ineq && lo <= 0.f) {
+                    lo = 0.f;
+                    if (total(0.f) <= Eb) return 0.f;
+                    break;
+                }
+                if (total(lo) > Eb) break;
+                hi = lo; step *= 8.f; lo = hi - step;
+            }
+        }
+        for (int i = 0; i < 20; ++i) {
+            const float mid = 0.5f * (lo + hi);
+            if (total(mid) > Eb) lo = mid; else hi = mid;
+        }
+        return hi;
     };
     // (NG+R)^2 matrix of the column pass for the current rho:
     //   Sinv = U diag(1/(d/rho + lam)) U',  X = Sinv C,
@@ -729,6 +774,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         // Lagrangian inner minimum over the box and energy-row terms; averaged candidate
         const float nsum = SCAL[SC_NSUM];
         const bool haveAvg = useAvg && nsum >= 2.f;
+        const bool refineDual = opt.dual_refine > 1 || (opt.dual_refine == 1 && SCAL[SC_STALL] >= 1.f);
         double dPa = 0.0;
         if (rowWarp) {
 #pragma unroll
@@ -747,10 +793,31 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     lb[q] = in ? LB[row * Tp + t] : 0.f;
                     ub[q] = in ? UB[row * Tp + t] : 0.f;
                     va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] / nsum : 0.f;
-                    if (in) {
-                        // reduced cost: c + (Khat' y) + lambda_s, lambda_s = rho1 * mu_s on the session window
-                        float lam = rho1 * MU_ELEM(SESS_MU, sf, scn, mu0, t);
-                        float rt = ALPHA[t] + kgc * BETA[t] + HG[g * Tp + t] + lam;
+                }
+                // energy-row multipliers of the dual bound: the iterate's (rho1 * mu_s), or the maximiser given y
+                if (refineDual) {
+                    float aa[Q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        int t = lane + 32 * q;
+                        aa[q] = (t < Tp) ? ALPHA[t] + kgc * BETA[t] + HG[g * Tp + t] : 0.f;
+                    }
+                    for (int s = sf; s < sf + scn; ++s) {
+                        float lam = dual_lambda(aa, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], rho1 * SESS_MU[s], !MULTI);
+                        if (lane == 0) SESS_MU2[s] = lam;
+                    }
+                } else if (lane == 0) {
+                    for (int s = sf; s < sf + scn; ++s) SESS_MU2[s] = rho1 * SESS_MU[s];
+                }
+                __syncwarp();
+                {
+                    const float lam0 = scn ? SESS_MU2[sf] : 0.f;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        int t = lane + 32 * q;
+                        if (t >= Tp) continue;
+                        // reduced cost: c + (Khat' y) + lambda_s on the session window
+                        float rt = ALPHA[t] + kgc * BETA[t] + HG[g * Tp + t] + MU_ELEM(SESS_MU2, sf, scn, lam0, t);
                         float phi;
                         if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lb[q], ub[q]); phi = qd * xs * xs + rt * xs; }
                         else phi = fminf(lb[q] * rt, ub[q] * rt);
@@ -758,7 +825,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     }
                 }
                 if (lane == 0)
-                    for (int s = sf; s < sf + scn; ++s) dD -= (double)(rho1 * SESS_MU[s]) * (double)SESS_E[s];
+                    for (int s = sf; s < sf + scn; ++s) dD -= (double)SESS_MU2[s] * (double)SESS_E[s];
+                __syncwarp();  // SESS_MU2 is reused for the averaged candidate below
                 if (haveAvg) {
                     for (int s = sf; s < sf + scn; ++s) {
                         float mu = newton_mu(va, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], !MULTI, 16);
@@ -808,16 +876,24 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 Pc += rd[RD_PC]; Pa += rd[RD_PA]; D += rd[RD_D]; qC += rd[RD_UQC]; qA += rd[RD_UQA]; lC += rd[RD_PLC]; lA += rd[RD_PLA];
             }
             if (canRestore) { Pc = lC; Pa = lA; }  // objective of the restored (scaled) candidates, from the column sums
+            // The tolerance scale is max(|P|, |D|, opt.term_floor * sum of the |objective terms|): with a demand charge
+            // the sunk peak cost w*p0 and the energy revenue can cancel to ~0 (closed-loop replay sitting at the
+            // previous peak), and a gap relative to that difference alone would ask for more digits than the terms have.
+            double magC = fabs(Pc), magA = fabs(Pa);
             if (S.has_u) {
-                Pc += (double)Gamma * qC + (double)pk_w * (double)fmaxf(uC, pk_p0);
-                Pa += (double)Gamma * qA + (double)pk_w * (double)fmaxf(uA, pk_p0);
+                const double gC = (double)Gamma * qC + (double)pk_w * (double)fmaxf(uC, pk_p0);
+                const double gA = (double)Gamma * qA + (double)pk_w * (double)fmaxf(uA, pk_p0);
+                Pc += gC; Pa += gA;
+                magC += fabs(gC); magA += fabs(gA);
             }
+            magC = fmax(fabs(Pc), (double)opt.term_floor * magC);
+            magA = fmax(fabs(Pa), (double)opt.term_floor * magA);
             double Dbest = SCALD[SD_DBEST];
             if (D == D && D > Dbest) Dbest = D;
             SCALD[SD_DBEST] = Dbest;
             const double gapC = Pc - Dbest, gapA = Pa - Dbest;
-            const double tolC = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pc), fabs(Dbest));
-            const double tolA = (double)opt.eps_abs + (double)opt.eps_rel * fmax(fabs(Pa), fabs(Dbest));
+            const double tolC = (double)opt.eps_abs + (double)opt.eps_rel * fmax(magC, fabs(Dbest));
+            const double tolA = (double)opt.eps_abs + (double)opt.eps_rel * fmax(magA, fabs(Dbest));
             // residual estimates (only used to balance rho)
             float rp = e1, rd_ = rho1 * e2;
             float rp_rel = rp / fmaxf(fmaxf(xm, zm), 1e-6f), rd_rel = rd_ / fmaxf(1.0f, ym);
@@ -838,18 +914,24 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     const double gbest = fmin(gapC, haveAvg ? gapA : gapC);
                     if (gbest < 0.9 * SCALD[SD_BESTGAP]) { SCALD[SD_BESTGAP] = gbest; SCAL[SC_STALL] = 0.f; }
                     else SCAL[SC_STALL] += 1.f;
-                    if (flag == 0.f && opt.stall_checks > 0 && SCAL[SC_STALL] >= (float)opt.stall_checks && SCAL[SC_NRESCUE] < (float)opt.max_rescues) {
-                        const int k = (int)SCAL[SC_NRESCUE];
-                        const float fac = (k == 0) ? 3.f : 1.f / 9.f;  // first try a stiffer penalty, then a softer one
-                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * fac, 1e-4f), 1e4f);
-                        SCAL[SC_NRESCUE] = (float)(k + 1);
+                    // 1st rescue: a stiffer penalty (x3).  2nd, only for warm-started solves: drop the inherited state and
+                    // start over cold, keeping the best dual bound.  (A second penalty change on cold-started solves
+                    // measured worse than none.)
+                    const int nresc = (int)SCAL[SC_NRESCUE];
+                    const bool canRescue = nresc < opt.max_rescues && (nresc == 0 || (nresc == 1 && B.warm_v1 != nullptr));
+                    if (flag == 0.f && opt.stall_checks > 0 && SCAL[SC_STALL] >= (float)opt.stall_checks && canRescue) {
+                        const bool cold = nresc > 0;
+                        SCAL[SC_NEWRHO] = cold ? opt.rho0 : fminf(fmaxf(rho * 3.f, 1e-4f), 1e4f);
+                        SCAL[SC_NRESCUE] = (float)(nresc + 1);
                         SCAL[SC_STALL] = 0.f;
                         SCALD[SD_BESTGAP] = 1.0e300;
                         SCALD[SD_GAPRESTART] = 1.0e300;
-                        flag = 10.f;
+                        flag = cold ? 11.f : 10.f;
+                    } else if (flag == 0.f && opt.stall_exit > 0 && SCAL[SC_STALL] >= (float)opt.stall_exit && !canRescue) {
+                        flag = 2.f;  // stalled for good: stop with the best certified gap so far (status ACB_MAX_ITER)
                     }
                 }
-                if (opt.adapt_rho && flag < 10.f) {
+                if (opt.adapt_rho && flag < 10.f && flag != 2.f) {
                     const float opt_ratio = (opt.adapt_rho > 1) ? 0.1f * (float)opt.adapt_rho : 5.f;  // adapt_rho = 10 x threshold, 1 = default 5
                     float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
                     if (ratio > opt_ratio || ratio < 1.f / opt_ratio) {
@@ -861,13 +943,14 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             SCAL[SC_FLAG] = flag;
             SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel;
             const bool useA = (flag == 4.f);
-            SCAL[SC_GAP] = (float)((useA ? gapA : gapC) / fmax(fmax(fabs(useA ? Pa : Pc), fabs(Dbest)), 1e-30));
+            SCAL[SC_GAP] = (float)((useA ? gapA : gapC) / fmax(fmax(useA ? magA : magC, fabs(Dbest)), 1e-30));
             SCAL[SC_VIOL] = useA ? vA : vC;
         }
         __syncthreads();
         const float flag = SCAL[SC_FLAG];
         if (flag == 1.f) { status = ACB_SOLVED; break; }
         if (flag == 3.f) { status = ACB_NUMERICAL; break; }
+        if (flag == 2.f) break;  // status stays ACB_MAX_ITER
         const bool toAvg = (flag == 4.f) || (flag == 5.f) || (flag == 15.f);
         if (toAvg) {
             // adopt the averaged state: v <- mean v, multipliers of its projection, mean coupling v
@@ -900,6 +983,24 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         if (flag >= 10.f) {
             // keep y: v <- z + (rho/rho_new)(v - z), then rebuild the column matrix
             const float rn = SCAL[SC_NEWRHO], f = rho / rn;
+            if (flag == 11.f) {
+                // cold reset: the state a solve without warm start begins with
+                if (rowWarp) {
+#pragma unroll
+                    for (int k = 0; k < TPW; ++k) {
+                        int row = SLOT[(warp * TPW + k) * 6];
+                        if (row < 0) continue;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            int t = lane + 32 * q;
+                            if (t < Tp) v1[k][q] = clampf(0.f, LB[row * Tp + t], UB[row * Tp + t]);
+                        }
+                    }
+                }
+                for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = 0.f;
+                for (int i = tid; i < R * Tp; i += nthreads) VC[i] = 0.f;
+                if (tid == 0) SCAL[SC_PLEVEL] = pk_p0;
+            } else {
             if (rowWarp) {
 #pragma unroll
                 for (int k = 0; k < TPW; ++k) {
@@ -934,6 +1035,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     float z = ((pk_w > 0.f) ? fminf(a, pl) : a) / su;
                     VC[r * Tp + t] = z + f * (v - z);
                 }
+            }
             }
             __syncthreads();
             rho = rn; rho1 = kappa * rho; dd = 2.f * qd + rho1; inv_d = 1.f / dd;

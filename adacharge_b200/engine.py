@@ -246,6 +246,26 @@ class PackedBatch:
                     raise ValueError("site was built with a peak-limit row but an instance has no peak_limit")
                 a[b, : inst.T] = np.broadcast_to(np.asarray(inst.peak_limit, dtype=np.float64), (inst.T,))
             h["peak_limit"] = a
+        self._allocate(h, want_warm_out)
+
+    @classmethod
+    def from_arrays(cls, site: Site, host: Dict[str, np.ndarray], Tp: int, S_max: int, multi_session=False, want_warm_out=False):
+        """Batch from already-packed host arrays (the acb_batch fields of include/adacharge_b200.h
+        by name; `T`, `n_sessions`, `sess_*`, `min_rates`, `max_rates`, `alpha`, `beta`, `qd`,
+        `gamma`, `peak_w`, `peak_p0` required, `ext` / `peak_limit` optional).  Used by callers
+        that keep their sessions in arrays (replay_fast) instead of SessionInfo objects."""
+        if Tp not in SUPPORTED_HORIZONS:
+            raise ValueError(f"Tp must be one of {SUPPORTED_HORIZONS}")
+        self = cls.__new__(cls)
+        self.site, self.Tp, self.S_max, self.B = site, Tp, S_max, int(host["T"].shape[0])
+        self.multi_session = bool(multi_session)
+        if site.use_peak_row and "peak_limit" not in host:
+            raise ValueError("site was built with a peak-limit row but the batch has no peak_limit")
+        self._allocate(host, want_warm_out)
+        return self
+
+    def _allocate(self, h: Dict[str, np.ndarray], want_warm_out: bool):
+        site, B, Tp_, S_ = self.site, self.B, self.Tp, self.S_max
         self.host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in h.items()}
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
         dev = torch.device("cuda", site.device)

@@ -19,6 +19,9 @@ from .adaptive_charging_optimization import AdaptiveChargingOptimization, Object
 from .interface import InfrastructureInfo, SessionInfo, TestingInterface
 
 
+REPLAY_SOLVER_DEFAULTS = dict(term_floor=1.0, stall_exit=40)
+
+
 @dataclass
 class EV:
     station: int
@@ -63,7 +66,9 @@ class SiteReplay:
                  solver_options: Optional[dict] = None, device=None, mean_sessions: int = 40):
         self.infra, self.objective, self.n_sites, self.steps, self.period = infra, objective, n_sites, steps, period
         self.warm_start, self.device = warm_start, device
-        self.options = _cabi.default_options(**(solver_options or {}))
+        # closed loop: the sunk demand charge w * prev_peak is a constant of every step's objective and can cancel the
+        # energy term, so the gap is taken relative to the terms' magnitude; a stalled instance stops after 40 checks
+        self.options = _cabi.default_options(**{**REPLAY_SOLVER_DEFAULTS, **(solver_options or {})})
         from .generators import sce_tou_prices
 
         self.prices = sce_tou_prices(2 * steps, period) if prices is None else np.asarray(prices, dtype=float)

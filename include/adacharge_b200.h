@@ -84,8 +84,13 @@ typedef struct acb_options {
     int32_t restart;     /* 1 = average the state and restart from the average when its gap halves */
     int32_t avg_every;   /* state is added to the average every avg_every iterations */
     int32_t stall_checks; /* change rho when the best gap has not improved by 10 % over this many checks (0 = never) */
-    int32_t max_rescues;  /* at most this many stagnation rescues (1st: rho x3, 2nd: rho /9) */
+    int32_t max_rescues;  /* at most this many stagnation rescues (1st: rho x3; 2nd, warm-started solves only: restart cold) */
     int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only */
+    int32_t stall_exit;  /* with all rescues used: stop (ACB_MAX_ITER, stats[2] = certified gap) after this many checks without a 10 % better gap; 0 = never */
+    int32_t dual_refine; /* dual bound uses the best energy-row multipliers given y: 0 = never, 1 = when the gap stalled at the last check, 2 = at every check */
+    float term_floor;    /* the gap tolerance is eps_abs + eps_rel * max(|P|, |D|, term_floor * sum of |objective terms|); default 0.05.
+                          * 1 = relative to the terms' magnitude (closed-loop replay: the sunk demand charge w*p0 is a constant
+                          * that can cancel the energy term), 0 = relative to |P| alone */
 } acb_options;
 
 void acb_default_options(acb_options* o);
@@ -105,7 +110,7 @@ typedef struct acb_batch {
     const int32_t* sess_start;   /* [B*S_max] arrival_offset */
     const int32_t* sess_len;     /* [B*S_max] remaining_time */
     const float* sess_energy;    /* [B*S_max] remaining_demand in A*periods */
-    const int32_t* sess_rate_off;/* [B*S_max] offset into min_rates/max_rates */
+    const int32_t* sess_rate_off;/* [B*S_max] offset o into min_rates/max_rates; o < 0: constant limits, the pair at index -(o+1) */
     const float* min_rates;      /* flat, per session remaining_time entries */
     const float* max_rates;
     const float* alpha;          /* [B*Tp] */

@@ -167,3 +167,45 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_cabi.NativeLibraryMissing):
         _cabi.lib()
+
+
+def test_fleet_replay_packing_matches_object_packing():
+    """replay_fast packs with array operations what replay.SiteReplay packs through SessionInfo /
+    build_instance: same session tables, energies, horizons and objective vectors."""
+    import adacharge_b200 as ab
+    from adacharge_b200.adaptive_charging_optimization import AdaptiveChargingOptimization
+    from adacharge_b200.generators import caltech_acn_infrastructure
+    from adacharge_b200.interface import TestingInterface
+    from adacharge_b200.replay import SiteReplay
+    from adacharge_b200.replay_fast import FleetReplay
+
+    obj = [ab.ObjectiveComponent(ab.quick_charge), ab.ObjectiveComponent(ab.tou_energy_cost, 2.0), ab.ObjectiveComponent(ab.demand_charge, 1 / 30)]
+    infra = caltech_acn_infrastructure()
+    slow = SiteReplay(infra, obj, n_sites=4, steps=288, seed0=50)
+    fast = FleetReplay(infra, obj, n_sites=4, steps_per_day=288, seed0=50, Tp=160)
+    fast.prev_peak[:] = slow.prev_peak[:] = [0.0, 120.0, 40.0, 300.0]
+    for t in (20, 90, 150):
+        h, idx, s, pos, n_sess = fast._pack(t)
+        for b in range(4):
+            sess = slow._active(b, t)
+            assert len(sess) == n_sess[b]
+            if not sess:
+                assert h["T"][b] == 1
+                continue
+            iface = TestingInterface({"active_sessions": [], "infrastructure_info": infra, "current_time": t, "period": 5,
+                                      "prices": slow.prices, "demand_charge": slow.demand_charge, "prev_peak": float(slow.prev_peak[b])})
+            inst = AdaptiveChargingOptimization(obj, iface).build_instance(sess, slow.info, None, float(slow.prev_peak[b]))
+            k = len(sess)
+            assert h["T"][b] == inst.T
+            np.testing.assert_array_equal(h["sess_row"][b, :k], inst.sess_row)
+            np.testing.assert_array_equal(h["sess_len"][b, :k], inst.sess_len)
+            np.testing.assert_array_equal(h["sess_start"][b, :k], inst.sess_start)
+            np.testing.assert_allclose(h["sess_energy"][b, :k], inst.sess_energy.astype(np.float32), rtol=1e-7)
+            np.testing.assert_allclose(h["alpha"][b, : inst.T], inst.alpha.astype(np.float32), rtol=1e-7)
+            np.testing.assert_allclose(h["beta"][b, : inst.T], inst.beta.astype(np.float32), rtol=1e-7)
+            assert (h["alpha"][b, inst.T:] == 0).all() and (h["beta"][b, inst.T:] == 0).all()
+            assert h["peak_w"][b] == np.float32(inst.peak_w) and h["peak_p0"][b] == np.float32(inst.peak_p0)
+            ro = h["sess_rate_off"][b, :k]
+            assert (ro < 0).all()
+            np.testing.assert_array_equal(h["max_rates"][-(ro + 1)], [mx[0] for mx in inst.max_rates])
+            assert all((mx == mx[0]).all() for mx in inst.max_rates)
