@@ -82,6 +82,9 @@ class FleetReplay:
         self.ev_req = np.array(cols["req"], dtype=np.float64)[order]
         self.ev_max = np.array(cols["maxrate"], dtype=np.float64)[order]
         self.ev_dlv = np.zeros_like(self.ev_req)
+        # sessions never span midnight (synthetic_day), so step t only has to look at its own day's EVs
+        day = self.ev_arr // steps_per_day
+        self._day_idx = [np.nonzero(day == d)[0] for d in range(days)]
         self.prev_peak = np.zeros(n_sites)  # A
         self.site: Optional[engine.Site] = None
         self._prev = None  # (warm_out tensors, EV index / site / position of the previous step's sessions, had-sessions mask)
@@ -116,8 +119,10 @@ class FleetReplay:
 
     def _pack(self, t: int):
         B, S_, i32, f32 = self.n_sites, self.N, np.int32, np.float32
-        remaining = self.ev_req - self.ev_dlv
-        idx = np.nonzero((self.ev_arr <= t) & (t < self.ev_dep) & (remaining > 1e-6))[0]
+        cand = self._day_idx[min(t // self.steps_per_day, self.days - 1)]
+        rem_c = self.ev_req[cand] - self.ev_dlv[cand]
+        keep = (self.ev_arr[cand] <= t) & (t < self.ev_dep[cand]) & (rem_c > 1e-6)
+        idx, rem = cand[keep], rem_c[keep]
         s = self.ev_site[idx]
         n_sess = np.bincount(s, minlength=B)
         offs = np.concatenate(([0], np.cumsum(n_sess)[:-1]))
@@ -130,7 +135,7 @@ class FleetReplay:
             raise ValueError(f"a session needs a horizon of {T.max()} periods > Tp = {self.Tp}")
         h = dict(T=T.astype(i32), n_sessions=n_sess.astype(i32))
         for name, vals, dt in (("sess_row", st, i32), ("sess_len", ln, i32),
-                               ("sess_energy", remaining[idx] / (self.volt[st] * self.period / 1e3 / 60), f32),
+                               ("sess_energy", rem / (self.volt[st] * self.period / 1e3 / 60), f32),
                                ("sess_rate_off", -(np.arange(len(idx)) + 1), i32)):
             a = np.zeros((B, S_), dtype=dt)
             a[s, pos] = vals
@@ -166,7 +171,8 @@ class FleetReplay:
         ev1.synchronize()
         t2 = time.perf_counter()
         # the simulator side: first-period pilots charge the EVs that are plugged in
-        present = np.nonzero((self.ev_arr <= t) & (t < self.ev_dep))[0]
+        cand = self._day_idx[min(t // self.steps_per_day, self.days - 1)]
+        present = cand[(self.ev_arr[cand] <= t) & (t < self.ev_dep[cand])]
         w = self.volt[self.ev_station[present]] * self.period / 1e3 / 60
         e = np.minimum(first[self.ev_site[present], self.ev_station[present]] * w, self.ev_req[present] - self.ev_dlv[present])
         self.ev_dlv[present] += np.maximum(e, 0.0)

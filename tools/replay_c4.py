@@ -48,7 +48,7 @@ timed = dict(steps=len(stats.device_ms) - n_before, device_ms=sum(stats.device_m
 if world > 1:
     t = torch.tensor([wall, timed["device_ms"], timed["host_ms"]], device="cuda", dtype=torch.float64)
     torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    c = torch.tensor([timed["site_steps"], s["unsolved"], float(np.sum(stats.delivered_frac >= 0.9999)), s["iters_max"]], device="cuda", dtype=torch.float64)
+    c = torch.tensor([timed["site_steps"], s["unsolved"], float(np.sum(stats.delivered_frac)), s["iters_max"]], device="cuda", dtype=torch.float64)
     mx = c[3:].clone()
     torch.distributed.all_reduce(c, op=torch.distributed.ReduceOp.SUM)
     torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
@@ -56,12 +56,12 @@ if world > 1:
     site_steps, unsolved, full = c[:3].tolist()
     it_max = mx.item()
 else:
-    dms, hms, site_steps, unsolved, full, it_max = timed["device_ms"], timed["host_ms"], timed["site_steps"], s["unsolved"], float(np.sum(stats.delivered_frac >= 0.9999)), s["iters_max"]
+    dms, hms, site_steps, unsolved, full, it_max = timed["device_ms"], timed["host_ms"], timed["site_steps"], s["unsolved"], float(np.sum(stats.delivered_frac)), s["iters_max"]
 if rank == 0:
     print(json.dumps(dict(workload="C4 replay", n_sites=n_sites, n_gpus=world, steps=timed["steps"], Tp=Tp, days=days,
                           control_steps_per_s=round(timed["steps"] / wall, 2), site_steps_per_s=round(site_steps / wall, 1),
                           wall_s=round(wall, 2), device_ms_per_step=round(dms / max(timed["steps"], 1), 2),
                           host_ms_per_step=round(hms / max(timed["steps"], 1), 2), iters_mean_rank0=round(s["iters_mean"], 1),
-                          iters_max=it_max, unsolved=unsolved, sites_fully_served=full)))
+                          iters_max=it_max, unsolved=unsolved, mean_delivered_fraction=round(full / n_sites, 4))))
 if world > 1:
     torch.distributed.destroy_process_group()
