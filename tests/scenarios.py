@@ -53,6 +53,7 @@ def make_interface(sc):
     sessions, infra = sc["data"]
     ct = sc.get("current_time", 0)
     d = {"active_sessions": sessions, "infrastructure_info": infra, "current_time": ct, "period": PERIOD}
+    d.update(sc.get("iface_extra", {}))
     iface = TestingInterface(d)
     if "prices" in sc:
         prices = np.array(sc["prices"], dtype=float)
@@ -90,3 +91,62 @@ def check_properties(rates, sc, iface, tol_rate=1e-3, tol_line=1e-3):
         assert np.allclose(rates[:, : sc["no_charge_cols"]], 0, atol=1e-3)
         if sc.get("positive_after"):
             assert np.all(rates[:, sc["no_charge_cols"] :] > 1e-4)
+
+
+def random_scenario(seed):
+    """Seeded small instance mixing everything the path supports: single-/three-phase networks, SOC or
+    LINEAR rows, staggered windows, a second session on an EVSE, minimum rates, energy equality, scalar
+    or vector peak limits and random objective mixes (incl. the aggregate-quadratic and peak terms)."""
+    rng = np.random.default_rng(1000 + seed)
+    three = bool(rng.integers(0, 2))
+    if three:
+        per = int(rng.integers(1, 4))
+        n = 3 * per
+    else:
+        n = int(rng.integers(2, 10))
+    T = int(rng.integers(8, 40))
+    equality = rng.random() < 0.25
+    with_min = (not equality) and rng.random() < 0.2
+    tight = rng.uniform(0.7, 0.95) if (equality or with_min) else rng.uniform(0.3, 0.9)
+    limit = tight * 32 * n / (3 if three else 1) * (1.5 if three else 1.0)
+    infra = three_phase_balanced_network(n // 3, limit) if three else single_phase_single_constraint(n, limit)
+    k = int(rng.integers(1, n + 1))
+    stations = [str(i) for i in rng.permutation(n)[:k]]
+    arr = rng.integers(0, max(1, T // 2), k)
+    dep = np.minimum(arr + rng.integers(3, T, k), T)
+    dep[rng.integers(0, k)] = T
+    deliverable = (dep - arr) * 32 * 208 / 1000 * PERIOD / 60
+    frac = rng.uniform(0.05, 0.3, k) if equality else rng.uniform(0.1, 0.9, k)
+    energy = frac * deliverable
+    arr, dep, energy = list(map(int, arr)), list(map(int, dep)), list(map(float, energy))
+    if rng.random() < 0.3 and dep[0] + 3 <= T:  # a second session on the first EVSE, after the first one left
+        stations.append(stations[0]); arr.append(dep[0]); dep.append(T); energy.append(float(0.2 * (T - dep[0]) * 32 * 208 / 1000 * PERIOD / 60))
+    m = len(stations)
+    mins = [6.0] * m if with_min else None
+    if with_min:
+        energy = [max(e, 1.05 * 6 * (d - a) * 208 / 1000 * PERIOD / 60) for e, a, d in zip(energy, arr, dep)]
+    sessions = session_generator(m, arr, dep, energy, energy, [MAX_RATE] * m, min_rates=mins, station_ids=stations)
+    obj = []
+    pool = rng.permutation(5)[: int(rng.integers(1, 4))]
+    for p in pool:
+        if p == 0:
+            obj.append(("quick_charge", 1.0, {}))
+        elif p == 1:
+            obj.append(("equal_share", float(rng.choice([1e-3, 1e-2, 0.05])), {}))
+        elif p == 2:
+            obj += [("tou_energy_cost", 1.0, {}), ("total_energy", 0.3, {})]
+        elif p == 3:
+            obj.append(("demand_charge", 1 / 30, {}))
+            if not any(o[0] in ("quick_charge", "total_energy") for o in obj):
+                obj.append(("total_energy", 0.3, {}))
+        else:
+            obj.append(("load_flattening", 1e-3, {"external_signal": (20 + 10 * np.sin(np.arange(T) / 5.0)).tolist()}))
+            if not any(o[0] in ("quick_charge", "total_energy") for o in obj):
+                obj.append(("quick_charge", 1.0, {}))
+    sc = dict(data=(sessions, infra), objective=obj, constraint_type="LINEAR" if rng.random() < 0.4 else "SOC", equality=equality,
+              iface_extra=dict(prices=(0.05 + 0.25 * rng.random(T + 4)).tolist(), demand_charge=15.51,
+                               prev_peak=float(rng.choice([0.0, 0.0, 20.0, 60.0]))))
+    if not (equality or with_min) and rng.random() < 0.3:
+        cap = 0.6 * 32 * m
+        sc["peak_limit"] = float(cap) if rng.random() < 0.5 else np.linspace(cap, 0.8 * cap, T)
+    return sc

@@ -82,3 +82,36 @@ def test_objective_components_against_direct_formulas():
     direct = (2.0 * (c @ R.sum(axis=0)) - 0.1 * (R ** 2).sum() - 1.5 * (prices @ (u * 5 / 60)) + 3.0 * (u * 5 / 60).sum()
               - 0.7 * 15.51 * max(u.max(), prev) - 0.2 * ((u + ext) ** 2).sum() - 0.4 * unmet)
     assert abs(mpc.evaluate_objective(R, obj, I, iface, S, iface.get_prev_peak()) - direct) < 1e-8 * abs(direct)
+
+
+def _lp_random_seeds(limit=12):
+    """Seeds of tests/scenarios.py::random_scenario that HiGHS can take (no quadratic term; LINEAR rows or single-phase SOC)."""
+    from tests.scenarios import random_scenario
+
+    out = []
+    for seed in range(80):
+        sc = random_scenario(seed)
+        if any(o[0] in ("equal_share", "load_flattening") for o in sc["objective"]):
+            continue
+        if sc["constraint_type"] == "SOC" and len(set(np.asarray(sc["data"][1]["phases"]).tolist())) > 1:
+            continue
+        out.append(seed)
+        if len(out) == limit:
+            break
+    return out
+
+
+@pytest.mark.parametrize("seed", _lp_random_seeds())
+def test_random_lp_instances_match_highs(seed):
+    """The interior-point oracle against HiGHS on random instances with staggered windows, repeated EVSEs,
+    minimum rates, equality rows, peak limits, TOU prices and the demand-charge epigraph."""
+    from tests.scenarios import random_scenario
+
+    sc = random_scenario(seed)
+    iface = make_interface(sc)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    args = (sc["objective"], S, I, iface, sc["constraint_type"], sc.get("equality", False), sc.get("peak_limit"), iface.get_prev_peak())
+    R = mpc.solve_mpc(*args)
+    Rh, fh = mpc.solve_lp_highs(*args)
+    f = mpc.evaluate_objective(R, sc["objective"], I, iface, S, iface.get_prev_peak())
+    assert abs(f - fh) <= 1e-6 * max(1.0, abs(fh)), (f, fh)
