@@ -34,9 +34,6 @@ extern "C" void acb_default_options(acb_options* o) {
     o->stall_exit = 0;
     o->dual_refine = 1;
     o->term_floor = 0.05f;
-    // development overrides (parameter sweeps without touching the callers)
-    if (const char* e = getenv("ACB_DUAL_REFINE")) o->dual_refine = atoi(e);
-    if (const char* e = getenv("ACB_STALL_EXIT")) o->stall_exit = atoi(e);
     o->path = 0;
 }
 
@@ -210,7 +207,6 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
     d.NG = NG;
     // slots: EVSEs ordered by group, TPW per warp
     int TPW = 3;  // EVSE rows per warp of the on-chip kernel (3 rows, 768-thread blocks, 80 registers: fastest of 2/3/4 measured)
-    if (const char* e = getenv("ACB_TPW")) TPW = std::max(1, atoi(e));
     while ((N + TPW - 1) / TPW > ACB_MAX_WARPS) ++TPW;
     d.TPW = TPW;
     d.nRowWarps = (N + TPW - 1) / TPW;

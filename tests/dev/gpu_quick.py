@@ -1,6 +1,6 @@
 """DEV: first GPU contact — CUDA solve vs oracle on a few instances."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import adacharge_b200 as ab
 from adacharge_b200.generators import *

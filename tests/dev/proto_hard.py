@@ -1,6 +1,6 @@
 """DEV-ONLY: the replay instances the kernel stalls on (gpurun_out/fleet_hard.npz), in the numpy model."""
 import sys
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/dev')
 import numpy as np
 import proto_restart as pr
 from oracle import mpc

@@ -1,7 +1,7 @@
 """DEV-ONLY numpy model of the CUDA solve kernel, phase by phase (same state, same
 algebra, float32 optional).  Not imported by the product, the tests or the bench."""
 import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/dev')
 import numpy as np
 from oracle import mpc
 from proto_admm import pack

@@ -1,7 +1,7 @@
 """DEV-ONLY numpy model: restarted-averaging ADMM with the rigorous Lagrangian gap as
 stopping rule (what the CUDA kernel implements)."""
 import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests/dev')
 import numpy as np
 import proto_kernel_model as pk
 from proto_admm import pack
