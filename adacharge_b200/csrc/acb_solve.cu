@@ -28,6 +28,8 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
     }
 }
 
+int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 
@@ -47,8 +49,8 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     const int nCT_ = d.nDisc + d.nLin + d.has_pl + d.has_u;
     const int nCT = nCT_;
     const int Q = batch->Tp / 32;
-    if (Q != 5 && Q != 9) {
-        acb_set_error("acb_solve_batch: Tp must be 160 or 288 (pad the horizon up)");
+    if (batch->Tp % 32 != 0 || (Q != 2 && Q != 4 && Q != 5 && Q != 9)) {
+        acb_set_error("acb_solve_batch: Tp must be 64, 128, 160 or 288 (pad the horizon up)");
         return ACB_E_INVALID;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -67,6 +69,8 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
         return ACB_E_TOO_LARGE;
     }
     const bool multi = batch->multi_session != 0;
+    if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, nthreads, smem, st, multi, nch);
+    if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, nthreads, smem, st, multi, nch);
     if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, nthreads, smem, st, multi, nch);
     return acb_launch_solve_q9(site, batch, &opt, nthreads, smem, st, multi, nch);
 }

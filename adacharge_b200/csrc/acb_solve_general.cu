@@ -705,8 +705,10 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
 
 int acb_solve_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st) {
     const int Q = batch->Tp / 32;
+    if (Q == 2) return run_general<2>(site, batch, opt, st);
+    if (Q == 4) return run_general<4>(site, batch, opt, st);
     if (Q == 5) return run_general<5>(site, batch, opt, st);
     if (Q == 9) return run_general<9>(site, batch, opt, st);
-    acb_set_error("acb_solve_batch (general path): Tp must be 160 or 288");
+    acb_set_error("acb_solve_batch (general path): Tp must be 64, 128, 160 or 288");
     return ACB_E_INVALID;
 }

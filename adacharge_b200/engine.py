@@ -182,7 +182,7 @@ def pack_sessions(sessions, infra, period) -> dict:
     return out
 
 
-SUPPORTED_HORIZONS = (160, 288)  # padded horizons the solve kernel is instantiated for
+SUPPORTED_HORIZONS = (64, 128, 160, 288)  # padded horizons the solve kernel is instantiated for
 
 
 class PackedBatch:

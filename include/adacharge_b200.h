@@ -96,7 +96,7 @@ typedef struct acb_options {
 void acb_default_options(acb_options* o);
 
 /* One batch of independent MPC instances on one site.  Horizon arrays are padded to
- * Tp (160 or 288, >= every T[b]); session arrays to S_max.  Objective in
+ * Tp (64, 128, 160 or 288, >= every T[b]); session arrays to S_max.  Objective in
  * minimisation form per instance:
  *   sum_it (alpha_t + k_i beta_t) r_it + qd sum r_it^2 + gamma sum_t (u_t + ext_t)^2
  *   + peak_w * max(max_t u_t, peak_p0),           u_t = sum_i k_i r_it  (kW)

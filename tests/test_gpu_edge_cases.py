@@ -109,3 +109,29 @@ def test_invalid_arguments_raise(require_gpu):
         ab.AdaptiveChargingOptimization(QC, iface, constraint_type="SOC").solve(S, I)
     with pytest.raises(ValueError):
         ab.AdaptiveChargingOptimization(QC, iface).solve(iface.active_sessions(), iface.infrastructure_info(), peak_limit=[10.0, 10.0])
+
+
+@pytest.mark.parametrize("Tp", [64, 128, 160, 288])
+def test_every_padded_horizon_gives_the_same_schedule(require_gpu, Tp):
+    """The kernel is instantiated per padded horizon (Tp = 32 Q); the result must not depend on the padding."""
+    import adacharge_b200 as ab
+    from adacharge_b200 import engine
+    from adacharge_b200.generators import config_c1
+
+    iface = ab.TestingInterface(config_c1(seed=5, n=9, T=40))
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    aco = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(ab.quick_charge), ab.ObjectiveComponent(ab.equal_share, 0.05)], iface)
+    inst = aco.build_instance(S, I, None, 0)
+    site = aco._site_for(I, inst)
+    ref = aco.solve(S, I)  # smallest fitting horizon (64)
+    pb = engine.PackedBatch(site, [inst], Tp=Tp).upload().solve(aco._options(inst))
+    assert int(pb.status[0]) == 0
+    got = pb.rates[0, :, : inst.T].cpu().numpy().astype(np.float64)
+    assert (pb.rates[0, :, inst.T:] == 0).all()
+    assert np.abs(got - ref).max() <= 2e-3  # same optimum (unique: strongly concave), different reduction trees
+    # the general (streaming) path accepts the same horizons
+    from adacharge_b200 import _cabi
+
+    pg = engine.PackedBatch(site, [inst], Tp=Tp).upload().solve(_cabi.default_options(path=2, eps_rel=2e-5))
+    assert int(pg.status[0]) == 0
+    assert np.abs(pg.rates[0, :, : inst.T].cpu().numpy() - ref).max() <= 5e-3
