@@ -219,7 +219,12 @@ class PackedBatch:
         for b, inst in enumerate(instances):
             a[b, : len(inst.sess_energy)] = inst.sess_energy
             for s, (mn, mx) in enumerate(zip(inst.min_rates, inst.max_rates)):
-                offs[b, s] = o
+                if len(mn) and mn.min() == mn.max() and mx.min() == mx.max():
+                    # constant limits (the usual case): one (min, max) pair, offset -(p + 1)
+                    offs[b, s] = -(o + 1)
+                    mn, mx = mn[:1], mx[:1]
+                else:
+                    offs[b, s] = o
                 mins.append(mn)
                 maxs.append(mx)
                 o += len(mn)
