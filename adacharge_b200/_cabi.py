@@ -17,7 +17,7 @@ ACB_NSTATS = 8
 EXPORTS = [
     "acb_site_create", "acb_site_destroy", "acb_site_dims", "acb_site_max_horizon", "acb_default_options",
     "acb_solve_batch", "acb_charging_rate_bounds", "acb_project_continuous", "acb_project_discrete",
-    "acb_reallocate", "acb_constraints_feasible", "acb_last_error", "acb_version",
+    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_last_error", "acb_version",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.acb_project_discrete.argtypes = [_P, _P, _P, C.c_int, C.c_int, _P]
     L.acb_reallocate.argtypes = [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]
     L.acb_constraints_feasible.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]
+    L.acb_min_rate_admission.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]
     _lib = L
     return L
 

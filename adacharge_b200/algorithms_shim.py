@@ -70,18 +70,23 @@ except Exception:  # noqa: BLE001
         return new
 
     def apply_minimum_charging_rate(active_sessions, infrastructure, override=float("inf")):
-        from .postprocessing import infrastructure_constraints_feasible
+        """Sessions in arrival order keep their EVSE's minimum pilot in the first period while the network stays
+        feasible (acnportal preprocessing, called at ada.py:149-150).  The sequential feasibility-guarded greedy
+        runs on the device in one launch (acb_min_rate_admission)."""
+        from . import engine
 
         queue = _expand(sorted(active_sessions, key=lambda x: x.arrival))
-        rates = np.zeros(len(infrastructure.station_ids))
+        if not queue:
+            return queue
+        rows = np.array([[infrastructure.get_station_index(s.station_id) for s in queue]], dtype=np.int32)
+        tries = np.array([[min(infrastructure.min_pilot[i], override) for i in rows[0]]], dtype=np.float64)
+        site = engine.get_site(infrastructure, "SOC", False, False)
+        admitted = engine.min_rate_admission(site, [len(queue)], rows, tries)[0]
         for j, s in enumerate(queue):
-            i = infrastructure.get_station_index(s.station_id)
-            rates[i] = min(infrastructure.min_pilot[i], override)
-            if infrastructure_constraints_feasible(rates, infrastructure):
-                s.min_rates[0] = max(rates[i], s.min_rates[0])
+            if admitted[j]:
+                s.min_rates[0] = max(tries[0, j], s.min_rates[0])
                 queue[j] = _reconcile(s)
             else:
-                rates[i] = 0
                 s.min_rates[0] = 0
                 s.max_rates[0] = 0
         return queue

@@ -195,6 +195,31 @@ __global__ void k_feasible(SiteDev S, const double* rates, int B, int T, int col
     if (lane == 0) feasible[b] = ok ? 1 : 0;
 }
 
+// Preprocessing greedy of apply_minimum_charging_rate (acnportal, called at adacharge.py:149-150): sessions are
+// offered in the caller's order; a session keeps its minimum rate if the network stays feasible with everything
+// admitted before it.  One warp per instance.
+__global__ void k_min_rate_admission(SiteDev S, int B, int S_max, const int32_t* n_sessions, const int32_t* sess_row,
+                                     const double* try_rate, int32_t* admitted) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double* col = reinterpret_cast<double*>(smraw);
+    const int b = blockIdx.x, lane = threadIdx.x;
+    for (int i = lane; i < S.N; i += 32) col[i] = 0.0;
+    __syncwarp();
+    const int nS = n_sessions[b];
+    for (int s = 0; s < nS; ++s) {
+        const size_t k = (size_t)b * S_max + s;
+        const int i = sess_row[k];
+        if (lane == 0) col[i] = try_rate[k];
+        __syncwarp();
+        const bool ok = warp_feasible(S, col, lane);
+        if (lane == 0) {
+            if (!ok) col[i] = 0.0;
+            admitted[k] = ok ? 1 : 0;
+        }
+        __syncwarp();
+    }
+}
+
 static int grid_for(size_t total) { return (int)std::min<size_t>((total + 255) / 256, 148 * 16); }
 
 extern "C" int acb_project_continuous(acb_site* site, const double* in, double* out, int B, int T, void* stream) {
@@ -245,6 +270,18 @@ extern "C" int acb_constraints_feasible(acb_site* site, const double* rates, int
     if (!site || !rates || !feasible || B <= 0 || col < 0 || col >= T) { acb_set_error("acb_constraints_feasible: bad arguments"); return ACB_E_INVALID; }
     ACB_CUDA(cudaSetDevice(site->device));
     k_feasible<<<B, 32, site->d.N * sizeof(double), (cudaStream_t)stream>>>(site->d, rates, B, T, col, feasible);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+extern "C" int acb_min_rate_admission(acb_site* site, int B, int S_max, const int32_t* n_sessions, const int32_t* sess_row,
+                                      const double* try_rate, int32_t* admitted, void* stream) {
+    if (!site || !n_sessions || !sess_row || !try_rate || !admitted || B <= 0 || S_max <= 0) {
+        acb_set_error("acb_min_rate_admission: bad arguments");
+        return ACB_E_INVALID;
+    }
+    ACB_CUDA(cudaSetDevice(site->device));
+    k_min_rate_admission<<<B, 32, site->d.N * sizeof(double), (cudaStream_t)stream>>>(site->d, B, S_max, n_sessions, sess_row, try_rate, admitted);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }

@@ -391,3 +391,16 @@ def constraints_feasible(site: Site, rates, col=0) -> torch.Tensor:
     out = torch.empty((r3.shape[0],), dtype=torch.int32, device=r3.device)
     _cabi.check(_cabi.lib().acb_constraints_feasible(site.handle, _ptr(r3), r3.shape[0], r3.shape[2], col, _ptr(out), _stream_ptr(site.device)), "acb_constraints_feasible")
     return out
+
+
+def min_rate_admission(site: Site, n_sessions, sess_row, try_rate) -> np.ndarray:
+    """Batched greedy of apply_minimum_charging_rate: [B, S_max] arrays in offer order -> admitted flags (numpy bool)."""
+    dev = torch.device("cuda", site.device)
+    rows = np.ascontiguousarray(np.asarray(sess_row, dtype=np.int32))
+    B, S_max = rows.shape
+    t = dict(ns=torch.from_numpy(np.ascontiguousarray(np.asarray(n_sessions, dtype=np.int32))).to(dev), row=torch.from_numpy(rows).to(dev),
+             tr=torch.from_numpy(np.ascontiguousarray(np.asarray(try_rate, dtype=np.float64))).to(dev))
+    out = torch.zeros((B, S_max), dtype=torch.int32, device=dev)
+    _cabi.check(_cabi.lib().acb_min_rate_admission(site.handle, B, S_max, _ptr(t["ns"]), _ptr(t["row"]), _ptr(t["tr"]), _ptr(out),
+                                                   _stream_ptr(site.device)), "acb_min_rate_admission")
+    return out.cpu().numpy().astype(bool)

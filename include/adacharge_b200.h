@@ -157,6 +157,14 @@ int acb_reallocate(acb_site* site, int mode, const double* rates_in, double* rat
 /* feasible[b] = 1 iff every SOC line current of column `col` is <= limit + 1e-7. */
 int acb_constraints_feasible(acb_site* site, const double* rates, int B, int T, int col, int32_t* feasible, void* stream);
 
+/* Preprocessing before the solve (reference adacharge/adacharge.py:149-150 -> acnportal's
+ * apply_minimum_charging_rate): per instance, sessions are offered in the caller's order ([B][S_max] arrays,
+ * the reference sorts by arrival); session s asks for try_rate[s] (= min(min_pilot, override)) on EVSE
+ * sess_row[s]; admitted[s] = 1 if the network stays feasible (same check as acb_constraints_feasible) together
+ * with everything admitted before it, else 0 and that EVSE goes back to 0 A. */
+int acb_min_rate_admission(acb_site* site, int B, int S_max, const int32_t* n_sessions, const int32_t* sess_row,
+                           const double* try_rate, int32_t* admitted, void* stream);
+
 const char* acb_last_error(void);
 int acb_version(void);
 

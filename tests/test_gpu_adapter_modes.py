@@ -86,3 +86,54 @@ def test_offline_algorithm_solves_a_whole_day(require_gpu):
     now = [ev for ev in evs if ev.arrival <= 30 < ev.departure]
     out = alg.schedule(now)
     assert out == {ev.station_id: [alg.internal_schedule[ev.station_id][30]] for ev in now}
+
+
+def _reference_min_rate_loop(sessions, infra, override):
+    """The per-session loop as acnportal writes it, one feasibility call per session."""
+    from copy import deepcopy
+
+    queue = deepcopy(sorted(sessions, key=lambda x: x.arrival))
+    rates = np.zeros(len(infra.station_ids))
+    flags = []
+    for s in queue:
+        i = infra.get_station_index(s.station_id)
+        rates[i] = min(infra.min_pilot[i], override)
+        ok = bool(ab.infrastructure_constraints_feasible(rates, infra))
+        if not ok:
+            rates[i] = 0
+        flags.append(ok)
+    return flags
+
+
+@pytest.mark.parametrize("cap,override", [(150, float("inf")), (20, float("inf")), (12, 5), (6, 8)])
+def test_min_rate_admission_matches_the_sequential_loop(require_gpu, cap, override):
+    """acb_min_rate_admission (one launch) against the reference-shaped loop, from slack to heavily congested
+    transformers (some sessions are refused their minimum rate)."""
+    from adacharge_b200 import engine
+
+    d = config_c2(23, infra=caltech_acn_infrastructure(transformer_cap=cap))
+    iface = ab.TestingInterface(d)
+    I = iface.infrastructure_info()
+    S = enforce_pilot_limit(iface.active_sessions(), I)
+    want = _reference_min_rate_loop(S, I, override)
+    got = apply_minimum_charging_rate(S, I, override)
+    queue = sorted(S, key=lambda x: x.arrival)
+    assert len(got) == len(want)
+    for s_in, s_out, ok in zip(queue, got, want):
+        assert s_in.session_id == s_out.session_id
+        i = I.get_station_index(s_in.station_id)
+        if ok:
+            assert s_out.min_rates[0] == max(min(I.min_pilot[i], override), s_in.min_rates[0])
+            assert s_out.max_rates[0] >= s_out.min_rates[0]
+        else:
+            assert s_out.min_rates[0] == 0 and s_out.max_rates[0] == 0
+    if cap <= 12:
+        assert not all(want) and any(want)
+    # batched form: the same instance three times plus a reversed offer order
+    rows = np.array([[I.get_station_index(s.station_id) for s in queue]], dtype=np.int32)
+    tries = np.array([[min(I.min_pilot[i], override) for i in rows[0]]])
+    site = engine.get_site(I, "SOC", False, False)
+    B = np.repeat(rows, 3, 0); B[2] = B[2, ::-1]
+    flags = engine.min_rate_admission(site, [rows.shape[1]] * 3, B, np.repeat(tries, 3, 0))
+    assert flags[0].tolist() == want and flags[1].tolist() == want
+    assert flags[2].sum() > 0
