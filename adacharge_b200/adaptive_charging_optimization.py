@@ -333,11 +333,6 @@ class AdaptiveChargingOptimization:
         # check per-session energy to 1e-4 relative (tests/test_adaptive_charging_optimization.py:53-65), which a
         # 1e-4 objective gap does not imply, so the drop-in class asks for 2e-5 unless told otherwise.
         opts.setdefault("eps_rel", 2e-5)
-        if inst is not None and inst.gamma > 0 and "rho0" not in opts and "kappa" not in opts:
-            # problems with the aggregate quadratic (load_flattening) like a stiffer penalty: measured
-            # 100 vs 153 iterations on the 1000-EVSE config; the library default is tuned
-            # for the LP-like cost objectives
-            opts.update(rho0=0.2, kappa=1.0)
         return _cabi.default_options(equality=int(bool(self.enforce_energy_equality)), **opts)
 
     def solve(self, active_sessions: List[SessionInfo], infrastructure: InfrastructureInfo,

@@ -10,6 +10,7 @@
 #define ACB_OPP 8          // outputs per column-pass work item
 #define ACB_NRED 16        // floats per warp in the reduction scratch
 #define ACB_MAX_WARPS 32
+#define ACB_FIRST_CHECK 10  // iteration of the first convergence check (then every check_every)
 
 // Device view of a site (all pointers device).  Row layout of the scaled coupling
 // matrix Khat (R x N): 2*nDisc SOC rows (cos, sin pairs) for rows that mix phases, nLin

@@ -118,7 +118,11 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
     __syncthreads();
     if (tid == 0) {
         float* sc = W.scal + (size_t)b * GS_N;
-        sc[GS_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : opt.rho0;
+        // cold start: rho0, raised to the curvature of the aggregate quadratic seen through the scaled aggregate row
+        // (2 Gamma u^2 with u = su * (Khat r)_u): at rho ~ Gamma su^2 the row's prox is balanced; a 1000-EVSE
+        // load-flattening instance goes from > 1000 iterations at rho0 to the first check
+        const float su0 = D.has_u ? S.row_scale[D.rU] : 0.f;
+        sc[GS_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : fmaxf(opt.rho0, B.gamma[b] * cs * su0 * su0);
         sc[GS_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
         sc[GS_CS] = cs;
         sc[GS_QD] = B.qd[b] * cs; sc[GS_GAMMA] = B.gamma[b] * cs; sc[GS_PKW] = B.peak_w[b] * cs; sc[GS_PKP0] = B.peak_p0[b];
@@ -295,20 +299,23 @@ __global__ void __launch_bounds__(256, 3) k_rows(SiteDev S, acb_batch B, acb_opt
     }
 }
 
-// block per (32-period tile, instance).  CHECK = 0: iteration;  CHECK = 1: evaluation of the
+// block per (tile of 32*CPL periods, instance); a lane owns CPL columns (t = tile*32*CPL + c*32 + lane), so every
+// matrix element fetched by a warp feeds CPL columns.  CHECK = 0: iteration;  CHECK = 1: evaluation of the
 // candidate (violation, aggregate-power part of P, conjugate terms of D, HG <- C'y).
+#define ACB_CPL 1  // columns per lane; 2 was measured slower on the 1000-EVSE site (566 vs 345 us per launch: half the resident warps, a ragged last tile)
 template <int CHECK>
 __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
+    constexpr int CPL = ACB_CPL, TW = 32 * CPL;
     const int tile = blockIdx.x, b = blockIdx.y;
     if (W.status[b] >= 0) return;
     extern __shared__ float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const int R = D.R, NG = D.NG, Tp = D.Tp, t = tile * 32 + lane, Tb = B.T[b];
-    float* sa = sm;                 // [NG][32]   group inputs / group sums of z
-    float* gg = sa + NG * 32;       // [R][32]    g (iteration) or y (check)
+    const int R = D.R, NG = D.NG, Tp = D.Tp, t0 = tile * TW + lane, Tb = B.T[b];
+    float* sa = sm;                 // [NG][TW]   group inputs / group sums of z
+    float* gg = sa + NG * TW;       // [R][TW]    g (iteration) or y (check)
     const int Rp = S.Rp;            // R rounded up to a multiple of 4; the padding rows of bv / y1 stay zero
-    float* bv = gg + R * 32;        // [Rp][32]
-    float* y1 = bv + Rp * 32;       // [Rp][32]
+    float* bv = gg + R * TW;        // [Rp][TW]
+    float* y1 = bv + Rp * TW;       // [Rp][TW]
     const float* sc = W.scal + (size_t)b * GS_N;
     const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, dr = dd / rho;
     const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], pk_p0 = sc[GS_PKP0], plevel = sc[GS_PLEVEL];
@@ -331,72 +338,102 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
     };
     double dconj = 0.0, duq = 0.0;
     float viol = -1.f, umax = 0.f, zumax = 0.f;
-    for (int i = tid; i < (Rp - R) * 32; i += blockDim.x) { bv[R * 32 + i] = 0.f; y1[R * 32 + i] = 0.f; }
-    // ---- stage 1: inputs
+    for (int i = tid; i < (Rp - R) * TW; i += blockDim.x) { bv[R * TW + i] = 0.f; y1[R * TW + i] = 0.f; }
+    // ---- stage 1: inputs (columns beyond Tp read as zero and are never written back)
     for (int g = warp; g < NG; g += nw) {
-        float s = (CHECK ? W.SGZ : W.SG)[((size_t)b * NG + g) * Tp + t];
-        sa[g * 32 + lane] = CHECK ? s : rho1 * s - S.ngrp[g] * (AL[t] + S.kg[g] * BE[t]);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int t = t0 + 32 * c;
+            float val = 0.f;
+            if (t < Tp) {
+                float s = (CHECK ? W.SGZ : W.SG)[((size_t)b * NG + g) * Tp + t];
+                val = CHECK ? s : rho1 * s - S.ngrp[g] * (AL[t] + S.kg[g] * BE[t]);
+            }
+            sa[g * TW + 32 * c + lane] = val;
+        }
     }
     for (int r = warp; r < R; r += nw) {
-        float z;
-        if (r < 2 * D.nDisc) {
-            int r0 = r & ~1;
-            float a = VC[r0 * Tp + t], bb = VC[(r0 + 1) * Tp + t], za, zb;
-            proj_disc(a, bb, S.lim[r0], za, zb);
-            z = (r & 1) ? zb : za;
-        } else z = proj_row(r, VC[r * Tp + t], t);
-        float v = VC[r * Tp + t];
-        gg[r * 32 + lane] = CHECK ? rho * (v - z) : rho * (2.f * z - v);
-        if (CHECK) {
-            float y = rho * (v - z);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int t = t0 + 32 * c;
+            if (t >= Tp) { gg[r * TW + 32 * c + lane] = 0.f; continue; }
+            float z;
             if (r < 2 * D.nDisc) {
-                // support function of the disc: after the barrier, from both components
-            } else if (r < 2 * D.nDisc + D.nLin + D.has_pl) {
-                float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
-                if (y != 0.f && cap < 1.0e30f) dconj -= (double)(cap * fabsf(y));
-            } else {
-                // aggregate-power row: Fenchel equality -g*(y) = g(z) - <y, z>; the max term is added in k_decide
-                float zk = z * su;
-                if (t < Tb) { dconj += (double)Gamma * (double)(zk + ebar(t)) * (double)(zk + ebar(t)); zumax = fmaxf(zumax, zk); }
-                dconj -= (double)y * (double)z;
+                int r0 = r & ~1;
+                float a = VC[r0 * Tp + t], bb = VC[(r0 + 1) * Tp + t], za, zb;
+                proj_disc(a, bb, S.lim[r0], za, zb);
+                z = (r & 1) ? zb : za;
+            } else z = proj_row(r, VC[r * Tp + t], t);
+            float v = VC[r * Tp + t];
+            gg[r * TW + 32 * c + lane] = CHECK ? rho * (v - z) : rho * (2.f * z - v);
+            if (CHECK) {
+                float y = rho * (v - z);
+                if (r < 2 * D.nDisc) {
+                    // support function of the disc: after the barrier, from both components
+                } else if (r < 2 * D.nDisc + D.nLin + D.has_pl) {
+                    float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
+                    if (y != 0.f && cap < 1.0e30f) dconj -= (double)(cap * fabsf(y));
+                } else {
+                    // aggregate-power row: Fenchel equality -g*(y) = g(z) - <y, z>; the max term is added in k_decide
+                    float zk = z * su;
+                    if (t < Tb) { dconj += (double)Gamma * (double)(zk + ebar(t)) * (double)(zk + ebar(t)); zumax = fmaxf(zumax, zk); }
+                    dconj -= (double)y * (double)z;
+                }
             }
         }
     }
     __syncthreads();
     if (CHECK) {
         // disc support functions need both components
-        for (int j = warp; j < D.nDisc; j += nw) {
-            float ya = gg[(2 * j) * 32 + lane], yb = gg[(2 * j + 1) * 32 + lane];
-            dconj -= (double)(S.lim[2 * j] * sqrtf(ya * ya + yb * yb));
-        }
+        for (int j = warp; j < D.nDisc; j += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float ya = gg[(2 * j) * TW + 32 * c + lane], yb = gg[(2 * j + 1) * TW + 32 * c + lane];
+                dconj -= (double)(S.lim[2 * j] * sqrtf(ya * ya + yb * yb));
+            }
         // Kz rows: violation and aggregate power of the candidate
-        for (int r = warp; r < R; r += nw) {
-            float ka = 0.f;
-            for (int g = 0; g < NG; ++g) ka += S.C[r * NG + g] * sa[g * 32 + lane];
-            bv[r * 32 + lane] = ka;
-        }
+        for (int r = warp; r < R; r += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float ka = 0.f;
+                for (int g = 0; g < NG; ++g) ka += S.C[r * NG + g] * sa[g * TW + 32 * c + lane];
+                bv[r * TW + 32 * c + lane] = ka;
+            }
         __syncthreads();
-        for (int j = warp; j < D.nDisc; j += nw) {
-            float ka = bv[(2 * j) * 32 + lane], kb = bv[(2 * j + 1) * 32 + lane];
-            if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f);
-        }
-        for (int r = 2 * D.nDisc + warp; r < 2 * D.nDisc + D.nLin + D.has_pl; r += nw) {
-            float ka = bv[r * 32 + lane];
-            float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
-            if (r < 2 * D.nDisc + D.nLin && D.lin_two_sided) ka = fabsf(ka);
-            if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
-        }
-        if (D.has_u && warp == 0 && t < Tb) {
-            float u = bv[D.rU * 32 + lane] * su;
-            umax = fmaxf(umax, u);
-            duq += (double)(u + ebar(t)) * (double)(u + ebar(t));
-        }
+        for (int j = warp; j < D.nDisc; j += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float ka = bv[(2 * j) * TW + 32 * c + lane], kb = bv[(2 * j + 1) * TW + 32 * c + lane];
+                if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f);
+            }
+        for (int r = 2 * D.nDisc + warp; r < 2 * D.nDisc + D.nLin + D.has_pl; r += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int t = t0 + 32 * c;
+                float ka = bv[r * TW + 32 * c + lane];
+                float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
+                if (r < 2 * D.nDisc + D.nLin && D.lin_two_sided) ka = fabsf(ka);
+                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
+            }
+        if (D.has_u && warp == 0)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int t = t0 + 32 * c;
+                if (t < Tb) {
+                    float u = bv[D.rU * TW + 32 * c + lane] * su;
+                    umax = fmaxf(umax, u);
+                    duq += (double)(u + ebar(t)) * (double)(u + ebar(t));
+                }
+            }
         // HG <- C'y
-        for (int g = warp; g < NG; g += nw) {
-            float acc = 0.f;
-            for (int r = 0; r < R; ++r) acc += S.C[r * NG + g] * gg[r * 32 + lane];
-            W.HG[((size_t)b * NG + g) * Tp + t] = acc;
-        }
+        for (int g = warp; g < NG; g += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int t = t0 + 32 * c;
+                float acc = 0.f;
+                for (int r = 0; r < R; ++r) acc += S.C[r * NG + g] * gg[r * TW + 32 * c + lane];
+                if (t < Tp) W.HG[((size_t)b * NG + g) * Tp + t] = acc;
+            }
         viol = wmax(viol); umax = wmax(umax); zumax = wmax(zumax);
         dconj = wsumd(dconj); duq = wsumd(duq);
         if (lane == 0) {
@@ -411,34 +448,51 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
     }
     // ---- stage 2: bv = C sa - (d/rho) g
     for (int r = warp; r < R; r += nw) {
-        float acc = -dr * gg[r * 32 + lane];
-        for (int g = 0; g < NG; ++g) acc += S.C[r * NG + g] * sa[g * 32 + lane];
-        bv[r * 32 + lane] = acc;
+        float acc[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[c] = -dr * gg[r * TW + 32 * c + lane];
+        for (int g = 0; g < NG; ++g) {
+            const float w = S.C[r * NG + g];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) acc[c] += w * sa[g * TW + 32 * c + lane];
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) bv[r * TW + 32 * c + lane] = acc[c];
     }
     __syncthreads();
     // ---- stages 3 and 4: y1 = diag(1/(d/rho+lam)) U' bv,  h = -U y1 (into bv).
-    // Register-blocked: a warp produces 4 output rows per pass from float4 loads of the padded
-    // matrix rows (warp-uniform addresses) and one shared-memory value per input row.
+    // Register-blocked: a warp produces 4 output rows x CPL columns per pass from float4 loads of the padded
+    // matrix rows (warp-uniform addresses) and CPL shared-memory values per input row.
     auto mat_apply = [&](const float* __restrict__ Mat, const float* __restrict__ in, float* __restrict__ out, bool scale) {
         for (int e0 = warp * 4; e0 < R; e0 += nw * 4) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            float a[4][CPL];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) a[i][c] = 0.f;
             const float4* m0 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 0, R - 1) * Rp);
             const float4* m1 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 1, R - 1) * Rp);
             const float4* m2 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 2, R - 1) * Rp);
             const float4* m3 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 3, R - 1) * Rp);
             for (int r4 = 0; r4 < Rp / 4; ++r4) {
                 const float4 w0 = __ldg(m0 + r4), w1 = __ldg(m1 + r4), w2 = __ldg(m2 + r4), w3 = __ldg(m3 + r4);
-                const float b0 = in[(4 * r4 + 0) * 32 + lane], b1 = in[(4 * r4 + 1) * 32 + lane];
-                const float b2 = in[(4 * r4 + 2) * 32 + lane], b3 = in[(4 * r4 + 3) * 32 + lane];
-                a0 += w0.x * b0 + w0.y * b1 + w0.z * b2 + w0.w * b3;
-                a1 += w1.x * b0 + w1.y * b1 + w1.z * b2 + w1.w * b3;
-                a2 += w2.x * b0 + w2.y * b1 + w2.z * b2 + w2.w * b3;
-                a3 += w3.x * b0 + w3.y * b1 + w3.z * b2 + w3.w * b3;
+#pragma unroll
+                for (int c = 0; c < CPL; ++c) {
+                    const float b0 = in[(4 * r4 + 0) * TW + 32 * c + lane], b1 = in[(4 * r4 + 1) * TW + 32 * c + lane];
+                    const float b2 = in[(4 * r4 + 2) * TW + 32 * c + lane], b3 = in[(4 * r4 + 3) * TW + 32 * c + lane];
+                    a[0][c] += w0.x * b0 + w0.y * b1 + w0.z * b2 + w0.w * b3;
+                    a[1][c] += w1.x * b0 + w1.y * b1 + w1.z * b2 + w1.w * b3;
+                    a[2][c] += w2.x * b0 + w2.y * b1 + w2.z * b2 + w2.w * b3;
+                    a[3][c] += w3.x * b0 + w3.y * b1 + w3.z * b2 + w3.w * b3;
+                }
             }
-            const float acc[4] = {a0, a1, a2, a3};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (e0 + i < R) out[(e0 + i) * 32 + lane] = scale ? acc[i] / (dr + S.lam[e0 + i]) : -acc[i];
+                if (e0 + i < R) {
+                    const float inv = scale ? 1.f / (dr + S.lam[e0 + i]) : -1.f;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) out[(e0 + i) * TW + 32 * c + lane] = a[i][c] * inv;
+                }
         }
     };
     mat_apply(S.Ut, bv, y1, true);
@@ -446,17 +500,31 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
     mat_apply(S.Up, y1, bv, false);
     __syncthreads();
     for (int g = warp; g < NG; g += nw) {
-        float acc = 0.f;
-        for (int r = 0; r < R; ++r) acc += S.C[r * NG + g] * bv[r * 32 + lane];
-        W.HG[((size_t)b * NG + g) * Tp + t] = acc - (AL[t] + S.kg[g] * BE[t]);
+        float acc[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float w = S.C[r * NG + g];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) acc[c] += w * bv[r * TW + 32 * c + lane];
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int t = t0 + 32 * c;
+            if (t < Tp) W.HG[((size_t)b * NG + g) * Tp + t] = acc[c] - (AL[t] + S.kg[g] * BE[t]);
+        }
     }
-    for (int r = warp; r < R; r += nw) {
-        float g_ = gg[r * 32 + lane], v = VC[r * Tp + t];
-        float kx = (g_ - bv[r * 32 + lane]) / rho;
-        float z = 0.5f * (g_ / rho + v);  // g = rho (2z - v)
-        KX[r * Tp + t] = kx;
-        VC[r * Tp + t] = v + opt.alpha * (kx - z);
-    }
+    for (int r = warp; r < R; r += nw)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int t = t0 + 32 * c;
+            if (t >= Tp) continue;
+            float g_ = gg[r * TW + 32 * c + lane], v = VC[r * Tp + t];
+            float kx = (g_ - bv[r * TW + 32 * c + lane]) / rho;
+            float z = 0.5f * (g_ / rho + v);  // g = rho (2z - v)
+            KX[r * Tp + t] = kx;
+            VC[r * Tp + t] = v + opt.alpha * (kx - z);
+        }
 }
 
 // one warp per instance: peak-epigraph level of the aggregate-power row
@@ -664,8 +732,8 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     ACB_CUDA(cudaMemsetAsync(W.HG, 0, nGT * sizeof(float), st));
     k_bounds_general<<<B, 256, 0, st>>>(d, *batch, W.LB, W.UB);
     k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
-    const dim3 grow(NG, B), gcol(Tp / 32, B);
-    const size_t smem_cols = (size_t)(NG + std::max(R, 1) + 2 * std::max(d.Rp, 4)) * 32 * sizeof(float);
+    const dim3 grow(NG, B), gcol((Tp + 32 * ACB_CPL - 1) / (32 * ACB_CPL), B);
+    const size_t smem_cols = (size_t)(NG + std::max(R, 1) + 2 * std::max(d.Rp, 4)) * 32 * ACB_CPL * sizeof(float);
     if (smem_cols > 48 * 1024) {
         ACB_CUDA(cudaFuncSetAttribute(k_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
@@ -673,7 +741,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     k_rows<Q, 1><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
     int h_done = 0, it = 0;
     while (it < opt.max_iter) {
-        const int burst = std::min(opt.check_every, opt.max_iter - it);
+        const int burst = std::min(it == 0 ? std::min(ACB_FIRST_CHECK, opt.check_every) : opt.check_every, opt.max_iter - it);
         for (int k = 0; k < burst; ++k) {
             k_cols<0><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
             k_level<<<B, 32, 0, st>>>(d, *batch, W, D);

@@ -250,7 +250,11 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         float m = 0.f;
         for (int w = 0; w < nwarps; ++w) m = fmaxf(m, REDF[w * ACB_NRED]);
         SCAL[SC_CS] = (m > 1e-20f) ? 1.0f / m : 1.0f;
-        SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : opt.rho0;
+        // cold start: rho0, raised to the curvature of the aggregate quadratic seen through the scaled aggregate row
+        // (see acb_solve_general.cu: k_setup)
+        const float su0 = S.has_u ? S.row_scale[rU] : 0.f;
+        SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2]
+                                                                   : fmaxf(opt.rho0, B.gamma[b] * SCAL[SC_CS] * su0 * su0);
         SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
         SCAL[SC_FLAG] = 0.f;
         SCAL[SC_NSUM] = 0.f;
@@ -621,7 +625,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             }
         }
         __syncthreads();
-        const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter);
+        const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter) || (it == ACB_FIRST_CHECK);  // easy / warm-started instances stop early
         const bool doAvg = useAvg && (it % avgEvery == 0);
         const bool avgFirst = SCAL[SC_NSUM] == 0.f;
         float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f;

@@ -92,6 +92,8 @@ def test_config_c5_full_size_properties(require_gpu):
     stats = pb.stats.cpu().numpy()
     assert (status == 0).all(), (status, stats[:, :4], pb.iters.cpu().numpy())
     assert (stats[:, 2] <= 1.05e-4).all() and (stats[:, 3] <= VIOL_TOL).all()
+    # the cold-start penalty follows the curvature of the aggregate quadratic; at the plain rho0 this takes > 1000 iterations
+    assert pb.iters.cpu().numpy().max() <= 150, pb.iters.cpu().numpy()
     R = pb.rates.cpu().numpy().astype(np.float64)
     for b, (iface, S, I) in enumerate(ifaces):
         v = mpc.violations(R[b][:, : insts[b].T], S, I, iface)

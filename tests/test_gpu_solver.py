@@ -171,3 +171,20 @@ def test_schedule_adapter_end_to_end(require_gpu):
         if kw:
             for i, s in enumerate(I.station_ids):
                 assert np.isin(sched[s], I.allowable_pilots[i]).all()
+
+
+def test_custom_component_with_kernel_spec(require_gpu):
+    """A user component whose kernel_spec restates quick_charge solves to the built-in's optimum."""
+    sc = SCENARIOS["large_three_soc"]
+    iface = make_interface(sc)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+
+    def my_quick(rates, infrastructure, interface, **kw):
+        return ab.quick_charge(rates, infrastructure, interface)
+
+    my_quick.kernel_spec = lambda infra, interface, T, **kw: dict(alpha=-np.array([(T - t) / T for t in range(T)]))
+    Ra = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(my_quick)], iface).solve(S, I)
+    Rb = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(ab.quick_charge)], iface).solve(S, I)
+    np.testing.assert_array_equal(Ra, Rb)
+    with pytest.raises(TypeError):
+        ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(lambda rates, **kw: 0.0)], iface).solve(S, I)

@@ -209,3 +209,26 @@ def test_fleet_replay_packing_matches_object_packing():
             assert (ro < 0).all()
             np.testing.assert_array_equal(h["max_rates"][-(ro + 1)], [mx[0] for mx in inst.max_rates])
             assert all((mx == mx[0]).all() for mx in inst.max_rates)
+
+
+def test_custom_objective_component_protocol():
+    """User-defined components carry a `kernel_spec` (the restatement of the reference's open-ended
+    ObjectiveComponent.function, aco.py:200-218); anything else is rejected loudly; kwargs merge like aco.py:203-217."""
+    import adacharge_b200 as ab
+    from adacharge_b200.adaptive_charging_optimization import pack_objective
+    from tests.scenarios import SCENARIOS, make_interface
+
+    sc = SCENARIOS["tiny_feasible"]
+    iface = make_interface(sc)
+    I = iface.infrastructure_info()
+
+    def late_charge(rates, infrastructure, interface, weight=1.0, **kw):
+        T = np.shape(rates)[1]
+        return float(weight * (np.arange(T) / T) @ np.asarray(rates).sum(axis=0))
+
+    late_charge.kernel_spec = lambda infra, interface, T, weight=1.0, **kw: dict(alpha=-weight * np.arange(T) / T)
+    ob = pack_objective([ab.ObjectiveComponent(late_charge, 2.0, {"weight": 3.0}), ab.ObjectiveComponent(ab.equal_share, 0.5)], I, iface, 12, weight=100.0)
+    np.testing.assert_allclose(ob["alpha"], -6.0 * np.arange(12) / 12)  # component kwargs win over caller kwargs
+    assert ob["qd"] == 0.5
+    with pytest.raises(TypeError, match="kernel spec"):
+        pack_objective([ab.ObjectiveComponent(lambda rates, **kw: 0.0)], I, iface, 12)
