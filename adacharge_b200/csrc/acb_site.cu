@@ -34,6 +34,7 @@ extern "C" void acb_default_options(acb_options* o) {
     o->stall_exit = 0;
     o->dual_refine = 1;
     o->term_floor = 0.05f;
+    o->rho_curv = 1.0f;
     o->path = 0;
 }
 

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         // (see acb_solve_general.cu: k_setup)
         const float su0 = S.has_u ? S.row_scale[rU] : 0.f;
         SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2]
-                                                                   : fmaxf(opt.rho0, B.gamma[b] * SCAL[SC_CS] * su0 * su0);
+                                                                   : fmaxf(opt.rho0, opt.rho_curv * B.gamma[b] * SCAL[SC_CS] * su0 * su0);
         SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
         SCAL[SC_FLAG] = 0.f;
         SCAL[SC_NSUM] = 0.f;

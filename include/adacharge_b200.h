@@ -91,6 +91,8 @@ typedef struct acb_options {
     float term_floor;    /* the gap tolerance is eps_abs + eps_rel * max(|P|, |D|, term_floor * sum of |objective terms|); default 0.05.
                           * 1 = relative to the terms' magnitude (closed-loop replay: the sunk demand charge w*p0 is a constant
                           * that can cancel the energy term), 0 = relative to |P| alone */
+    float rho_curv;      /* cold start: rho = max(rho0, rho_curv * Gamma * s_u^2), the curvature of the aggregate quadratic seen
+                          * through the scaled aggregate-power row (default 1; 0 = plain rho0) */
 } acb_options;
 
 void acb_default_options(acb_options* o);
