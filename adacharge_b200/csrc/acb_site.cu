@@ -22,14 +22,14 @@ extern "C" void acb_default_options(acb_options* o) {
     o->viol_tol = 1e-5f;
     o->rho0 = 0.07f;
     o->kappa = 0.7f;
-    o->alpha = 1.7f;
+    o->alpha = 1.8f;
     o->max_iter = 20000;
     o->check_every = 25;
     o->equality = 0;
     o->adapt_rho = 0;  // residual balancing measured worse than the fixed penalty + stagnation rescue on every workload tried
     o->restart = 1;
     o->avg_every = 5;
-    o->stall_checks = 3;
+    o->stall_checks = 2;
     o->max_rescues = 1;  // a 2nd rescue (cold reset of a warm-started solve) measured worse on the 1024-site replay
     o->stall_exit = 0;
     o->dual_refine = 1;

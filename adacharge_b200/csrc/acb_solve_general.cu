@@ -594,7 +594,7 @@ __global__ void k_decide(acb_batch B, acb_options opt, GenWork W, GenDims D, int
     int st = -1;
     float ratio_out = 1.f;
     if (!(P == P)) st = ACB_NUMERICAL;
-    else if (gap <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;
+    else if (fabs(gap) <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;  // |gap|: a negative value is rounding noise
     else if (last) st = ACB_MAX_ITER;
     else if (opt.adapt_rho) {
         float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
