@@ -46,7 +46,7 @@ __device__ __forceinline__ void atomic_max_pos(float* addr, float v) {  // v >= 
 
 // per-instance scalars
 enum { GS_RHO = 0, GS_PLEVEL, GS_CS, GS_QD, GS_GAMMA, GS_PKW, GS_PKP0, GS_E1, GS_E2, GS_XMAX, GS_YMAX, GS_VIOL, GS_UMAX, GS_ZUMAX, GS_GAP, GS_RP, GS_RD, GS_N };
-enum { GD_P = 0, GD_D, GD_UQ, GD_DBEST, GD_N };
+enum { GD_P = 0, GD_D, GD_UQ, GD_DBEST, GD_PMAX, GD_N };
 
 struct GenWork {
     float *V, *LB, *UB, *VC, *KX, *SG, *SGZ, *HG, *MU, *AL, *BE;  // AL/BE: cost-scaled alpha, beta [B][Tp]
@@ -116,8 +116,46 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
         if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) infeas = 1;
     }
     __syncthreads();
+    // infeasibility certificate (see the on-chip kernel): maximum of the objective over the box, in scaled units
+    __shared__ double redd[32];
+    __shared__ float redu[32];
+    {
+        double pm = 0.0;
+        float cmax = 0.f;
+        const float qd_s = B.qd[b] * cs, gam_s = B.gamma[b] * cs;
+        for (int i = tid; i < S.nSlots * Tp; i += blockDim.x) {
+            const int s = i / Tp, t = i - s * Tp, row = S.slot_row[s];
+            if (row < 0) continue;
+            const float c = W.AL[(size_t)b * Tp + t] + S.kg[S.slot_grp[s]] * W.BE[(size_t)b * Tp + t];
+            const float lo = W.LB[((size_t)b * D.N + row) * Tp + t], hi = W.UB[((size_t)b * D.N + row) * Tp + t];
+            pm += (double)fmaxf(c * lo, c * hi) + (double)qd_s * (double)fmaxf(lo * lo, hi * hi);
+        }
+        if (D.has_u && (gam_s > 0.f || B.peak_w[b] > 0.f)) {
+            for (int t = tid; t < Tb; t += blockDim.x) {
+                float umax = 0.f, umin = 0.f;
+                for (int s = 0; s < S.nSlots; ++s) {
+                    const int row = S.slot_row[s];
+                    if (row < 0) continue;
+                    const float k = S.kg[S.slot_grp[s]];
+                    umax += k * W.UB[((size_t)b * D.N + row) * Tp + t]; umin += k * W.LB[((size_t)b * D.N + row) * Tp + t];
+                }
+                const float e = B.ext ? B.ext[(size_t)b * Tp + t] : 0.f;
+                pm += (double)gam_s * (double)fmaxf((umax + e) * (umax + e), (umin + e) * (umin + e));
+                cmax = fmaxf(cmax, umax);
+            }
+        }
+        pm = wsumd(pm); cmax = wmax(cmax);
+        if (lane == 0) { redd[warp] = pm; redu[warp] = cmax; }
+        __syncthreads();
+    }
     if (tid == 0) {
         float* sc = W.scal + (size_t)b * GS_N;
+        {
+            double tot = 0.0;
+            float um = 0.f;
+            for (int w = 0; w < nw; ++w) { tot += redd[w]; um = fmaxf(um, redu[w]); }
+            W.dacc[(size_t)b * GD_N + GD_PMAX] = tot + (double)(B.peak_w[b] * cs) * (double)fmaxf(um, B.peak_p0[b]);
+        }
         // cold start: rho0, raised to the curvature of the aggregate quadratic seen through the scaled aggregate row
         // (2 Gamma u^2 with u = su * (Khat r)_u): at rho ~ Gamma su^2 the row's prox is balanced; a 1000-EVSE
         // load-flattening instance goes from > 1000 iterations at rho0 to the first check
@@ -594,6 +632,7 @@ __global__ void k_decide(acb_batch B, acb_options opt, GenWork W, GenDims D, int
     int st = -1;
     float ratio_out = 1.f;
     if (!(P == P)) st = ACB_NUMERICAL;
+    else if (Dbest > da[GD_PMAX] + 1e-3 * (fabs(da[GD_PMAX]) + 1.0)) st = ACB_INFEASIBLE;  // dual bound above the box maximum
     else if (fabs(gap) <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;  // |gap|: a negative value is rounding noise
     else if (last) st = ACB_MAX_ITER;
     else if (opt.adapt_rho) {

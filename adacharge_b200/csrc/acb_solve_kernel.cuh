@@ -108,7 +108,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 // float scalars
 enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE };
 // double scalars
-enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP };
+enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP, SD_PMAX };
 // per-warp float reduction slots (max-type)
 enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA };
 // per-warp double reduction slots (sum-type)
@@ -280,6 +280,45 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     const float rho_start = rho;  // what a warm start of the next solve inherits (a stagnation rescue is not carried over)
     float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
     const float su = S.has_u ? S.row_scale[rU] : 1.f;
+
+    // Infeasibility certificate: the Lagrangian bound D is a lower bound of the optimal value over the feasible set, and
+    // no feasible point can cost more than the maximum of the objective over the box.  D > that maximum => infeasible
+    // (the duals of an infeasible instance diverge, so D gets there quickly).  PMAX = that maximum, in scaled units.
+    {
+        __syncthreads();  // scaled ALPHA / BETA
+        double pm = 0.0;
+        float cmax = 0.f;
+        for (int i = tid; i < S.nSlots * Tp; i += nthreads) {
+            const int s = i / Tp, t = i - s * Tp, row = SLOT[s * 6];
+            if (row < 0) continue;
+            const float c = ALPHA[t] + KG[SLOT[s * 6 + 1]] * BETA[t], lo = LB[row * Tp + t], hi = UB[row * Tp + t];
+            pm += (double)fmaxf(c * lo, c * hi) + (double)qd * (double)fmaxf(lo * lo, hi * hi);
+        }
+        if (S.has_u && (Gamma > 0.f || pk_w > 0.f)) {
+            for (int t = tid; t < Tb; t += nthreads) {
+                float umax = 0.f, umin = 0.f;
+                for (int s = 0; s < S.nSlots; ++s) {
+                    const int row = SLOT[s * 6];
+                    if (row < 0) continue;
+                    const float k = KG[SLOT[s * 6 + 1]];
+                    umax += k * UB[row * Tp + t]; umin += k * LB[row * Tp + t];
+                }
+                const float e = EBAR[t];
+                pm += (double)Gamma * (double)fmaxf((umax + e) * (umax + e), (umin + e) * (umin + e));
+                cmax = fmaxf(cmax, umax);
+            }
+        }
+        pm = warp_sum(pm); cmax = warp_max(cmax);
+        if (lane == 0) { REDD[warp * ACB_NRED] = pm; REDF[warp * ACB_NRED] = cmax; }
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            float um = 0.f;
+            for (int w = 0; w < nwarps; ++w) { tot += REDD[w * ACB_NRED]; um = fmaxf(um, REDF[w * ACB_NRED]); }
+            SCALD[SD_PMAX] = tot + (double)pk_w * (double)fmaxf(um, pk_p0);
+        }
+        __syncthreads();
+    }
 
     // per-lane state: v for this warp's EVSE rows
     float v1[TPW][Q];
@@ -906,6 +945,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             const bool okC = fabs(gapC) <= tolC && vC <= opt.viol_tol;
             const bool okA = haveAvg && fabs(gapA) <= tolA && vA <= opt.viol_tol;
             if (nn > 0.f || !(Pc == Pc)) flag = 3.f;
+            else if (Dbest > SCALD[SD_PMAX] + 1e-3 * (fabs(SCALD[SD_PMAX]) + 1.0)) flag = 6.f;  // infeasibility certificate
             else if (okC && (!okA || gapC <= gapA)) flag = 1.f;
             else if (okA) flag = 4.f;
             else {
@@ -955,6 +995,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         const float flag = SCAL[SC_FLAG];
         if (flag == 1.f) { status = ACB_SOLVED; break; }
         if (flag == 3.f) { status = ACB_NUMERICAL; break; }
+        if (flag == 6.f) { status = ACB_INFEASIBLE; break; }
         if (flag == 2.f) break;  // status stays ACB_MAX_ITER
         const bool toAvg = (flag == 4.f) || (flag == 5.f) || (flag == 15.f);
         if (toAvg) {

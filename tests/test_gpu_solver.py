@@ -188,3 +188,17 @@ def test_custom_component_with_kernel_spec(require_gpu):
     np.testing.assert_array_equal(Ra, Rb)
     with pytest.raises(TypeError):
         ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(lambda rates, **kw: 0.0)], iface).solve(S, I)
+
+
+@pytest.mark.parametrize("path", [0, 2])
+def test_infrastructure_infeasibility_is_certified_early(require_gpu, path):
+    """Energy equality against a line limit that cannot carry it (t_aco.py:148-175): no row-level check sees it;
+    the dual bound climbs past the maximum of the objective over the box, which proves infeasibility long
+    before the iteration limit.  Both kernels."""
+    sc = INFEASIBLE["infeasible_infrastructure"]
+    iface = make_interface(sc)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    aco = ab.AdaptiveChargingOptimization(_components(sc["objective"]), iface, "SOC", True, solver_options=dict(path=path))
+    with pytest.raises(ab.InfeasibilityException, match="INFEASIBLE|infeasible"):
+        aco.solve(S, I)
+    assert aco.last_info["status"] == 2 and aco.last_info["iters"] <= 3000, aco.last_info
