@@ -341,6 +341,43 @@ class PackedBatch:
         return lb, ub
 
 
+class HostPipeline:
+    """Host-to-host solve of a large batch: the instances are split into chunks, each with its own stream, so the
+    host->device copy of one chunk and the device->host copy of another overlap the solve of a third.  `run()`
+    enqueues one full pass and makes the current stream wait for it; results land in the pinned `host_rates`
+    ([B, N, Tp] float32), `host_status`, `host_iters` (valid after a synchronize of the current stream)."""
+
+    def __init__(self, site: Site, instances: Sequence[Instance], chunks: int = 4, Tp: Optional[int] = None):
+        B = len(instances)
+        chunks = max(1, min(chunks, B))
+        if Tp is None:
+            Tmax = max(i.T for i in instances)
+            Tp = [t for t in SUPPORTED_HORIZONS if t >= Tmax][0]
+        S_max = max(4, max(len(i.sess_row) for i in instances))
+        bounds = [round(k * B / chunks) for k in range(chunks + 1)]
+        self.parts = [PackedBatch(site, instances[a:b], Tp=Tp, S_max=S_max) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        self.slices = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        self.streams = [torch.cuda.Stream(device=site.device) for _ in self.parts]
+        self.host_rates = torch.empty((B, site.N, Tp), dtype=torch.float32).pin_memory()
+        self.host_status = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.host_iters = torch.empty((B,), dtype=torch.int32).pin_memory()
+        self.h2d_bytes = sum(p.h2d_bytes for p in self.parts)
+        self.d2h_bytes = self.host_rates.numel() * 4 + self.host_status.numel() * 4 + self.host_iters.numel() * 4
+
+    def run(self, options: Optional[Options] = None):
+        cur = torch.cuda.current_stream(self.parts[0].site.device)
+        for p, (a, b), st in zip(self.parts, self.slices, self.streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                p.upload().solve(options)
+                self.host_rates[a:b].copy_(p.rates, non_blocking=True)
+                self.host_status[a:b].copy_(p.status, non_blocking=True)
+                self.host_iters[a:b].copy_(p.iters, non_blocking=True)
+        for st in self.streams:  # only after everything is enqueued: the chunks must not serialise through `cur`
+            cur.wait_stream(st)
+        return self
+
+
 # ------------------------------------------------------------------------ postprocessing
 def _as_dev_f64(site: Site, rates) -> torch.Tensor:
     if isinstance(rates, torch.Tensor):

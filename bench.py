@@ -189,8 +189,6 @@ def main():
     opt = _cabi.default_options()
     pb = engine.PackedBatch(site, insts).upload()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    host_rates = torch.empty(pb.rates.shape, dtype=torch.float32).pin_memory()
-    host_status = torch.empty(pb.status.shape, dtype=torch.int32).pin_memory()
 
     def barrier():
         if world > 1:
@@ -213,11 +211,12 @@ def main():
     def step_resident():
         pb.solve(opt)
 
+    # end to end through the public host-to-host call: pinned host inputs -> device -> solve -> pinned host results,
+    # in 4 chunks on their own streams so the copies overlap the solves (engine.HostPipeline)
+    pipe = engine.HostPipeline(site, insts, chunks=4)
+
     def step_e2e():
-        pb.upload()
-        pb.solve(opt)
-        host_rates.copy_(pb.rates, non_blocking=True)
-        host_status.copy_(pb.status, non_blocking=True)
+        pipe.run(opt)
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -270,8 +269,8 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                          "kernel": "acb_solve_kernel", "algorithmic_bytes_per_iteration": b_iter,
                          "note": "effective bandwidth: state is on-chip resident, DRAM sees load/store only (SURVEY.md 8(d)); per-GPU figure"},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pb.h2d_bytes) * world,
-                    "d2h_bytes_per_step": int(host_rates.numel() * 4 + host_status.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes) * world,
+                    "d2h_bytes_per_step": int(pipe.d2h_bytes) * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": args.steps, "clocks": clk,
         }
         if world == 1 and not args.no_cpu_baseline:
