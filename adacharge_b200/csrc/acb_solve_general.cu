@@ -633,7 +633,7 @@ __global__ void k_decide(acb_batch B, acb_options opt, GenWork W, GenDims D, int
     float ratio_out = 1.f;
     if (!(P == P)) st = ACB_NUMERICAL;
     else if (Dbest > da[GD_PMAX] + 1e-3 * (fabs(da[GD_PMAX]) + 1.0)) st = ACB_INFEASIBLE;  // dual bound above the box maximum
-    else if (fabs(gap) <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;  // |gap|: a negative value is rounding noise
+    else if (gap <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;  // a slightly negative gap is rounding noise and passes
     else if (last) st = ACB_MAX_ITER;
     else if (opt.adapt_rho) {
         float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));

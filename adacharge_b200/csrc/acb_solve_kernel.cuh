@@ -941,9 +941,10 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             float rp = e1, rd_ = rho1 * e2;
             float rp_rel = rp / fmaxf(fmaxf(xm, zm), 1e-6f), rd_rel = rd_ / fmaxf(1.0f, ym);
             float flag = 0.f;
-            // |gap|: a negative value is rounding noise (P >= D always), not a certificate below the requested tolerance
-            const bool okC = fabs(gapC) <= tolC && vC <= opt.viol_tol;
-            const bool okA = haveAvg && fabs(gapA) <= tolA && vA <= opt.viol_tol;
+            // a (slightly) negative gap is rounding noise around a converged pair and passes; negative tolerances
+            // therefore mean "never stop on the gap" (run the whole iteration budget)
+            const bool okC = gapC <= tolC && vC <= opt.viol_tol;
+            const bool okA = haveAvg && gapA <= tolA && vA <= opt.viol_tol;
             if (nn > 0.f || !(Pc == Pc)) flag = 3.f;
             else if (Dbest > SCALD[SD_PMAX] + 1e-3 * (fabs(SCALD[SD_PMAX]) + 1.0)) flag = 6.f;  // infeasibility certificate
             else if (okC && (!okA || gapC <= gapA)) flag = 1.f;

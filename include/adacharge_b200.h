@@ -71,8 +71,9 @@ int acb_site_max_horizon(const acb_site* site);
 
 typedef struct acb_options {
     float eps_abs;      /* absolute gap tolerance in cost-scaled units (largest |cost coefficient| = 1) */
-    float eps_rel;      /* relative duality-gap tolerance: P - D <= eps_abs + eps_rel * max(|P|, |D|), where P is the
-                           objective of the returned schedule and D a Lagrangian lower bound */
+    float eps_rel;      /* relative duality-gap tolerance: P - D <= eps_abs + eps_rel * max(|P|, |D|, term_floor * terms), where
+                           P is the objective of the returned schedule and D a Lagrangian lower bound; negative
+                           tolerances never pass: the solve runs its whole iteration budget (status ACB_MAX_ITER) */
     float viol_tol;     /* max relative infrastructure / peak violation of the returned schedule */
     float rho0;         /* initial penalty */
     float kappa;        /* identity-block penalty = kappa * rho */

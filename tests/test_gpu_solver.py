@@ -78,15 +78,15 @@ def test_oracle_golden_objective_and_feasibility(require_gpu, mpc_golden):
 def test_unique_optimum_rates_within_1e3(require_gpu, mpc_golden):
     """quick_charge + c * equal_share is strictly concave, so the optimum is unique and the
     schedule itself must match the oracle: within 1e-3 A for c = 0.05 when the iteration is
-    run past the point where the float32 gap estimate can certify anything (eps_rel below
-    float32 resolution => the iteration cap ends the run, accepted as 'inaccurate').  For the
+    run past the point where the float32 gap estimate can certify anything (negative
+    tolerances => the iteration cap ends the run, accepted as 'inaccurate').  For the
     nearly linear c = 1e-3 the optimal face is so flat that a 1e-4 gap allows ~1 A of play;
     there only the objective is compared.  DESIGN.md "precision" has the numbers."""
     for g in [g for g in mpc_golden if g["config"].startswith("c1")]:
         iface, S, I = _golden_case(g)
         obj = [tuple(o) for o in g["objective"]]
         strong = g["config"] == "c1s"
-        opts = dict(eps_rel=1e-9, eps_abs=1e-12, max_iter=12000) if strong else dict(eps_rel=1e-6, eps_abs=1e-9, max_iter=12000)
+        opts = dict(eps_rel=-1.0, eps_abs=-1.0, max_iter=3000) if strong else dict(eps_rel=1e-6, eps_abs=1e-9, max_iter=12000)
         aco = ab.AdaptiveChargingOptimization(_components(obj), iface, solver_options=opts)
         try:
             R = aco.solve(S, I)
