@@ -181,8 +181,23 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 prints exactly one JSON line on stdout.  NCCL writes its version banner to stdout when NCCL_DEBUG is
+        # VERSION (the GPU boxes export that) and to NCCL_DEBUG_FILE at WARN/INFO: raise VERSION to WARN, point the
+        # log at stderr, and keep fd 1 on stderr while the communicator comes up.
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     _cabi.lib()
 
     site, insts, ifaces = build_instances(args.batch, seed0=rank * args.batch)

@@ -26,7 +26,9 @@ rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
 _r = sharding.shard_range(n_sites, rank, world)
 lo, hi = _r.start, _r.stop
