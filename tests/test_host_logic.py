@@ -232,3 +232,29 @@ def test_custom_objective_component_protocol():
     assert ob["qd"] == 0.5
     with pytest.raises(TypeError, match="kernel spec"):
         pack_objective([ab.ObjectiveComponent(lambda rates, **kw: 0.0)], I, iface, 12)
+
+
+def test_fleet_replay_shards_are_the_unsharded_fleet():
+    """tools/replay_c4.py gives rank r the sites shard_range(n, r, world) through `site_offset`: the shards'
+    EV tables concatenate to the single-process fleet (same seeds per site), so sharding changes no result."""
+    import adacharge_b200 as ab
+    from adacharge_b200.generators import caltech_acn_infrastructure
+    from adacharge_b200.replay_fast import FleetReplay
+    from adacharge_b200.sharding import shard_range
+
+    obj = [ab.ObjectiveComponent(ab.quick_charge)]
+    infra = caltech_acn_infrastructure()
+    full = FleetReplay(infra, obj, n_sites=7, days=2, seed0=40, Tp=128)
+    parts = []
+    for r in range(3):
+        rg = shard_range(7, r, 3)
+        parts.append((rg, FleetReplay(infra, obj, n_sites=len(rg), days=2, seed0=40, Tp=128, site_offset=rg.start)))
+    assert sum(len(rg) for rg, _ in parts) == 7
+    for name in ("ev_station", "ev_arr", "ev_dep", "ev_req", "ev_max"):
+        np.testing.assert_array_equal(np.concatenate([getattr(p, name) for _, p in parts]), getattr(full, name))
+    np.testing.assert_array_equal(np.concatenate([p.ev_site + rg.start for rg, p in parts]), full.ev_site)
+    # and the packed batch of a step is the concatenation of the shards' batches
+    h_full = full._pack(130)[0]
+    hs = [p._pack(130)[0] for _, p in parts]
+    for k in ("T", "n_sessions", "sess_row", "sess_len", "sess_energy", "alpha", "beta", "peak_w", "peak_p0"):
+        np.testing.assert_array_equal(np.concatenate([h[k] for h in hs]), h_full[k])
