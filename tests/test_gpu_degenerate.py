@@ -1,4 +1,4 @@
-"""Degenerate closed-loop instances captured from the 1024-site replay (tools/fleet_debug2.py):
+"""Degenerate closed-loop instances captured from the 1024-site replay (tests/golden/make_replay_degenerate.py):
 one EV whose remaining energy is exactly what the site's previous peak lets it draw, so the sunk
 demand charge w*p0 cancels the energy revenue (|P| << |terms|) and the LP optimum is a vertex a
 few mA away from the flat schedule.  Each instance is a 1-EV LP, so the exact optimum comes from

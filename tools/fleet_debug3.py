@@ -6,7 +6,7 @@ from adacharge_b200 import engine, _cabi
 from adacharge_b200.generators import caltech_acn_infrastructure
 from adacharge_b200.interface import InfrastructureInfo
 
-h = dict(np.load(sys.argv[1] if len(sys.argv) > 1 else "tools/_variants/fleet_hard.npz"))
+h = dict(np.load(sys.argv[1] if len(sys.argv) > 1 else "tests/golden/replay_degenerate_instances.npz"))
 infra = caltech_acn_infrastructure()
 info = InfrastructureInfo(np.asarray(infra["constraint_matrix"]), np.asarray(infra["constraint_limits"]), np.asarray(infra["phases"]),
                           np.asarray(infra["voltages"], float), infra["constraint_ids"], infra["station_ids"], np.asarray(infra["max_pilot"]), np.asarray(infra["min_pilot"]))
