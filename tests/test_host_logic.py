@@ -258,3 +258,34 @@ def test_fleet_replay_shards_are_the_unsharded_fleet():
     hs = [p._pack(130)[0] for _, p in parts]
     for k in ("T", "n_sessions", "sess_row", "sess_len", "sess_energy", "alpha", "beta", "peak_w", "peak_p0"):
         np.testing.assert_array_equal(np.concatenate([h[k] for h in hs]), h_full[k])
+
+
+def test_status_mapping_and_inaccurate_exit():
+    """aco.py:319-320: anything but optimal / optimal_inaccurate raises.  Iteration-limit exits with a small
+    certified gap and violation count as 'inaccurate' and are returned."""
+    from adacharge_b200.adaptive_charging_optimization import check_status
+
+    check_status(_cabi.ACB_SOLVED, dict(gap=1.0, violation=1.0))
+    check_status(_cabi.ACB_MAX_ITER, dict(gap=5e-3, violation=5e-4))
+    for status, info in ((_cabi.ACB_MAX_ITER, dict(gap=5e-2, violation=0.0)), (_cabi.ACB_MAX_ITER, dict(gap=0.0, violation=1e-2)),
+                         (_cabi.ACB_INFEASIBLE, dict(gap=0.0, violation=0.0)), (_cabi.ACB_NUMERICAL, dict(gap=0.0, violation=0.0))):
+        with pytest.raises(ab.InfeasibilityException, match="Solve failed with status"):
+            check_status(status, info)
+
+
+def test_options_struct_matches_header_order():
+    """The ctypes mirror of acb_options lists the header's fields in the header's order (a silent mismatch would
+    shift every option after it)."""
+    hdr = open(os.path.join(ROOT, "include", "adacharge_b200.h")).read()
+    body = hdr[hdr.index("typedef struct acb_options {"):hdr.index("} acb_options;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:float|int32_t)\s+(\w+)\s*;", body)
+    assert fields == [n for n, _ in _cabi.Options._fields_]
+    body = hdr[hdr.index("typedef struct acb_batch {"):hdr.index("} acb_batch;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in re.findall(r"(?:const\s+)?(?:int32_t|float)\s*\*?\s*([^;]+);", body):
+        names += [x.strip().lstrip("*").split()[-1].lstrip("*") for x in decl.split(",")]
+    assert names == [n for n, _ in _cabi.Batch._fields_], (names, [n for n, _ in _cabi.Batch._fields_])
+    d = _cabi.default_options()
+    assert d.eps_rel == pytest.approx(1e-4) and d.check_every == 25 and d.term_floor == pytest.approx(0.05) and d.rho_curv == pytest.approx(1.0)
