@@ -293,6 +293,19 @@ class PackedBatch:
             )
         self.struct = Batch()
 
+    def refill(self, h: Dict[str, np.ndarray]):
+        """Overwrite the pinned staging buffers in place with a new batch of the same shape (same field names, shapes
+        and dtypes as at construction): callers that solve a fresh batch every step (the replay) keep one PackedBatch
+        instead of pinning new host memory each time.  Follow with upload() / solve()."""
+        if set(h) != set(self.host):
+            raise ValueError(f"refill needs exactly the fields of the original batch: {sorted(self.host)}")
+        for k, v in h.items():
+            dst = self.host[k].numpy()
+            if dst.shape != v.shape or dst.dtype != v.dtype:
+                raise ValueError(f"refill: field {k} changed shape or dtype ({dst.shape} {dst.dtype} -> {v.shape} {v.dtype})")
+            dst[...] = v
+        return self
+
     def upload(self):
         for k, t in self.host.items():
             d = self.dev.get(k)

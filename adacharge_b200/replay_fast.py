@@ -73,21 +73,25 @@ class FleetReplay:
                     cols["dep"].append(ev.departure + d * steps_per_day)
                     cols["req"].append(ev.requested)
                     cols["maxrate"].append(ev.max_rate)
-        # EV table sorted by (site, station): any active subset is then grouped by site and ordered by EVSE row
-        order = np.lexsort((np.array(cols["arr"]), np.array(cols["station"]), np.array(cols["site"])))
+        # EV table sorted by (day, site, station): a day is a contiguous slice (sessions never span midnight, so step t
+        # only looks at its own day) and any active subset of it is grouped by site and ordered by EVSE row
+        arr_all = np.array(cols["arr"], dtype=np.int64)
+        order = np.lexsort((np.array(cols["station"]), np.array(cols["site"]), arr_all // steps_per_day))
         self.ev_site = np.array(cols["site"], dtype=np.int64)[order]
         self.ev_station = np.array(cols["station"], dtype=np.int64)[order]
-        self.ev_arr = np.array(cols["arr"], dtype=np.int64)[order]
+        self.ev_arr = arr_all[order]
         self.ev_dep = np.array(cols["dep"], dtype=np.int64)[order]
         self.ev_req = np.array(cols["req"], dtype=np.float64)[order]
         self.ev_max = np.array(cols["maxrate"], dtype=np.float64)[order]
         self.ev_dlv = np.zeros_like(self.ev_req)
-        # sessions never span midnight (synthetic_day), so step t only has to look at its own day's EVs
         day = self.ev_arr // steps_per_day
-        self._day_idx = [np.nonzero(day == d)[0] for d in range(days)]
+        edges = np.searchsorted(day, np.arange(days + 1))
+        self._day_slice = [slice(int(edges[d]), int(edges[d + 1])) for d in range(days)]
+        self._w_ev = self.volt[self.ev_station] * period / 1e3 / 60  # kWh per A-period of each EV's EVSE
         self.prev_peak = np.zeros(n_sites)  # A
         self.site: Optional[engine.Site] = None
         self._prev = None  # (warm_out tensors, EV index / site / position of the previous step's sessions, had-sessions mask)
+        self._pb: Optional[engine.PackedBatch] = None  # one batch object for the whole replay (refilled every step)
         self.stats = FleetStats()
 
     # ------------------------------------------------------------------ packing
@@ -101,9 +105,30 @@ class FleetReplay:
         tab = {k: np.zeros((len(uT), Tp)) for k in ("alpha", "beta", "ext")}
         sc = {k: np.zeros(len(uT)) for k in ("qd", "gamma", "peak_w", "peak_p0")}
         has_ext = False
+        # Most components give the same per-period coefficients whatever the horizon (prices, energy, peak terms);
+        # quick_charge does not ((T - t) / T).  Probe the shortest and the longest horizon: if the short one is a
+        # prefix of the long one, one evaluation serves every site (cut at its own T); else evaluate per horizon.
+        ob_hi = pack_objective(self.objective, self.info, iface, int(uT[-1]))
+        ob_lo = pack_objective(self.objective, self.info, iface, int(uT[0])) if len(uT) > 1 else ob_hi
+        n0 = int(uT[0])
+        prefix_ok = all(np.array_equal(ob_lo[k], ob_hi[k][:n0]) for k in ("alpha", "beta")) and \
+            all(ob_lo[k] == ob_hi[k] for k in sc) and \
+            ((ob_lo["ext"] is None and ob_hi["ext"] is None) or (ob_lo["ext"] is not None and ob_hi["ext"] is not None and np.array_equal(ob_lo["ext"][:n0], ob_hi["ext"][:n0])))
+        if prefix_ok:
+            # one coefficient vector for everybody, cut at each site's own horizon
+            f32 = np.float32
+            live = (np.arange(Tp)[None, :] < T[:, None])
+            pad = lambda v: np.pad(np.asarray(v, dtype=f32)[:Tp], (0, max(0, Tp - len(v))))  # noqa: E731
+            out = {k: pad(ob_hi[k])[None, :] * live for k in ("alpha", "beta")}
+            if ob_hi["ext"] is not None:
+                out["ext"] = pad(ob_hi["ext"])[None, :] * live
+            for k in ("qd", "gamma", "peak_w"):
+                out[k] = np.full(B, ob_hi[k], dtype=f32)
+            out["peak_p0"] = np.maximum(self.prev_peak * self.volt[0] / 1000, ob_hi["peak_p0"]).astype(f32)
+            return out
         for j, Tj in enumerate(uT):
-            ob = pack_objective(self.objective, self.info, iface, int(Tj))
-            tab["alpha"][j, :Tj], tab["beta"][j, :Tj] = ob["alpha"], ob["beta"]
+            ob = ob_hi if j == len(uT) - 1 else (ob_lo if j == 0 else pack_objective(self.objective, self.info, iface, int(Tj)))
+            tab["alpha"][j, :Tj], tab["beta"][j, :Tj] = ob["alpha"][:Tj], ob["beta"][:Tj]
             if ob["ext"] is not None:
                 tab["ext"][j, :Tj], has_ext = ob["ext"][:Tj], True
             for k in sc:
@@ -119,10 +144,10 @@ class FleetReplay:
 
     def _pack(self, t: int):
         B, S_, i32, f32 = self.n_sites, self.N, np.int32, np.float32
-        cand = self._day_idx[min(t // self.steps_per_day, self.days - 1)]
-        rem_c = self.ev_req[cand] - self.ev_dlv[cand]
-        keep = (self.ev_arr[cand] <= t) & (t < self.ev_dep[cand]) & (rem_c > 1e-6)
-        idx, rem = cand[keep], rem_c[keep]
+        sl = self._day_slice[min(t // self.steps_per_day, self.days - 1)]
+        rem_c = self.ev_req[sl] - self.ev_dlv[sl]
+        keep = np.nonzero((self.ev_arr[sl] <= t) & (t < self.ev_dep[sl]) & (rem_c > 1e-6))[0]
+        idx, rem = keep + sl.start, rem_c[keep]
         s = self.ev_site[idx]
         n_sess = np.bincount(s, minlength=B)
         offs = np.concatenate(([0], np.cumsum(n_sess)[:-1]))
@@ -134,15 +159,16 @@ class FleetReplay:
         if T.max() > self.Tp:
             raise ValueError(f"a session needs a horizon of {T.max()} periods > Tp = {self.Tp}")
         h = dict(T=T.astype(i32), n_sessions=n_sess.astype(i32))
+        flat = s * S_ + pos  # 1-D scatter index into the padded [B, S_max] tables
         for name, vals, dt in (("sess_row", st, i32), ("sess_len", ln, i32),
-                               ("sess_energy", rem / (self.volt[st] * self.period / 1e3 / 60), f32),
+                               ("sess_energy", rem / self._w_ev[idx], f32),
                                ("sess_rate_off", -(np.arange(len(idx)) + 1), i32)):
-            a = np.zeros((B, S_), dtype=dt)
-            a[s, pos] = vals
-            h[name] = a
+            a = np.zeros(B * S_, dtype=dt)
+            a[flat] = vals
+            h[name] = a.reshape(B, S_)
         h["sess_start"] = np.zeros((B, S_), dtype=i32)
-        h["min_rates"] = np.zeros(max(len(idx), 1), dtype=f32)
-        h["max_rates"] = np.zeros(max(len(idx), 1), dtype=f32)
+        h["min_rates"] = np.zeros(B * S_, dtype=f32)  # fixed length (one slot per possible session): the staging buffers are reused
+        h["max_rates"] = np.zeros(B * S_, dtype=f32)
         h["max_rates"][: len(idx)] = self.ev_max[idx]
         h.update(self._objective_arrays(t, T))
         return h, idx, s, pos, n_sess
@@ -154,7 +180,12 @@ class FleetReplay:
         if self.site is None:
             use_u = bool((h["gamma"] > 0).any() or (h["peak_w"] > 0).any())
             self.site = engine.get_site(self.info, "SOC", False, use_u, self.device)
-        pb = engine.PackedBatch.from_arrays(self.site, h, self.Tp, self.N, multi_session=False, want_warm_out=True)
+        if self._pb is None:
+            self._pb = engine.PackedBatch.from_arrays(self.site, h, self.Tp, self.N, multi_session=False, want_warm_out=True)
+        else:
+            self._pb.refill(h)  # same shapes every step: reuse the pinned staging and the device buffers
+        pb = self._pb
+        pb.warm = None
         dev = pb.device
         t1 = time.perf_counter()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -171,10 +202,9 @@ class FleetReplay:
         ev1.synchronize()
         t2 = time.perf_counter()
         # the simulator side: first-period pilots charge the EVs that are plugged in
-        cand = self._day_idx[min(t // self.steps_per_day, self.days - 1)]
-        present = cand[(self.ev_arr[cand] <= t) & (t < self.ev_dep[cand])]
-        w = self.volt[self.ev_station[present]] * self.period / 1e3 / 60
-        e = np.minimum(first[self.ev_site[present], self.ev_station[present]] * w, self.ev_req[present] - self.ev_dlv[present])
+        sl = self._day_slice[min(t // self.steps_per_day, self.days - 1)]
+        present = np.nonzero((self.ev_arr[sl] <= t) & (t < self.ev_dep[sl]))[0] + sl.start
+        e = np.minimum(first[self.ev_site[present], self.ev_station[present]] * self._w_ev[present], self.ev_req[present] - self.ev_dlv[present])
         self.ev_dlv[present] += np.maximum(e, 0.0)
         self.prev_peak = np.maximum(self.prev_peak, first.sum(axis=1))
         self._prev = (pb.warm_out, idx_d, s_d, pos_d, torch.from_numpy(n_sess > 0).to(dev))

@@ -169,7 +169,8 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         _cabi.lib()
 
 
-def test_fleet_replay_packing_matches_object_packing():
+@pytest.mark.parametrize("with_quick_charge", [True, False])
+def test_fleet_replay_packing_matches_object_packing(with_quick_charge):
     """replay_fast packs with array operations what replay.SiteReplay packs through SessionInfo /
     build_instance: same session tables, energies, horizons and objective vectors."""
     import adacharge_b200 as ab
@@ -179,7 +180,10 @@ def test_fleet_replay_packing_matches_object_packing():
     from adacharge_b200.replay import SiteReplay
     from adacharge_b200.replay_fast import FleetReplay
 
-    obj = [ab.ObjectiveComponent(ab.quick_charge), ab.ObjectiveComponent(ab.tou_energy_cost, 2.0), ab.ObjectiveComponent(ab.demand_charge, 1 / 30)]
+    # quick_charge's coefficients depend on the horizon (one evaluation per distinct T); without it one evaluation serves all sites
+    obj = [ab.ObjectiveComponent(ab.tou_energy_cost, 2.0), ab.ObjectiveComponent(ab.total_energy, 0.3), ab.ObjectiveComponent(ab.demand_charge, 1 / 30)]
+    if with_quick_charge:
+        obj.insert(0, ab.ObjectiveComponent(ab.quick_charge))
     infra = caltech_acn_infrastructure()
     slow = SiteReplay(infra, obj, n_sites=4, steps=288, seed0=50)
     fast = FleetReplay(infra, obj, n_sites=4, steps_per_day=288, seed0=50, Tp=160)
@@ -250,9 +254,13 @@ def test_fleet_replay_shards_are_the_unsharded_fleet():
         rg = shard_range(7, r, 3)
         parts.append((rg, FleetReplay(infra, obj, n_sites=len(rg), days=2, seed0=40, Tp=128, site_offset=rg.start)))
     assert sum(len(rg) for rg, _ in parts) == 7
+    # tables are day-major: compare after sorting both sides by (site, arrival)
+    site_cat = np.concatenate([p.ev_site + rg.start for rg, p in parts])
+    arr_cat = np.concatenate([p.ev_arr for _, p in parts])
+    oc, of = np.lexsort((arr_cat, site_cat)), np.lexsort((full.ev_arr, full.ev_site))
+    np.testing.assert_array_equal(site_cat[oc], full.ev_site[of])
     for name in ("ev_station", "ev_arr", "ev_dep", "ev_req", "ev_max"):
-        np.testing.assert_array_equal(np.concatenate([getattr(p, name) for _, p in parts]), getattr(full, name))
-    np.testing.assert_array_equal(np.concatenate([p.ev_site + rg.start for rg, p in parts]), full.ev_site)
+        np.testing.assert_array_equal(np.concatenate([getattr(p, name) for _, p in parts])[oc], getattr(full, name)[of])
     # and the packed batch of a step is the concatenation of the shards' batches
     h_full = full._pack(130)[0]
     hs = [p._pack(130)[0] for _, p in parts]
