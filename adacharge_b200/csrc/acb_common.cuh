@@ -50,6 +50,8 @@ struct SiteDev {
 struct acb_site {
     int device;
     SiteDev d;
+    SiteDev d6;          // same site with 6 EVSE rows per warp (slot tables only differ): the compact-bounds kernel, 2 blocks per SM
+    int has_d6;
     std::vector<void*> allocs;
     int constraint_type;
     const int* grp_off_dev;  // [NG+1] offsets of each group's rows in the (group-sorted) slot list

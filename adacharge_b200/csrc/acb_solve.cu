@@ -31,6 +31,8 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
 int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_compact_q4(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, int);
+int acb_launch_solve_compact_q9(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, int);
 int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
 
 extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* opt_in, void* stream) {
@@ -60,6 +62,22 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
     int nthreads = std::min(768, ((want + 31) / 32) * 32);
+    if (opt.path == 3) {
+        // experimental compact-bounds kernel: no materialised lb/ub (constant limits, one session per EVSE), 6 rows per
+        // warp, 384 threads, two blocks per SM.  Opt-in only; the caller guarantees the batch qualifies.
+        if (!site->has_d6 || batch->multi_session || (Q != 4 && Q != 9)) {
+            acb_set_error("acb_solve_batch: path 3 (compact bounds) needs a site of <= 192 EVSEs, one session per EVSE and Tp 128 or 288");
+            return ACB_E_INVALID;
+        }
+        const SiteDev& e = site->d6;
+        const int nt = 384;
+        const size_t sm6 = (size_t)make_layout(e.N, e.R, e.NG, e.NP, e.nSlots, batch->Tp, batch->S_max, nt / 32, true).total * sizeof(float);
+        if (e.nRowWarps * 32 > nt || nCT_ > 32 || sm6 > 113 * 1024) {
+            acb_set_error("acb_solve_batch: path 3 (compact bounds) does not fit two blocks per SM for this site (" + std::to_string(sm6) + " B)");
+            return ACB_E_TOO_LARGE;
+        }
+        return (Q == 4) ? acb_launch_solve_compact_q4(site, batch, &opt, nt, sm6, st, nch) : acb_launch_solve_compact_q9(site, batch, &opt, nt, sm6, st, nch);
+    }
     size_t smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
     const bool fits = d.TPW == 3 && nCT_ <= 32 && nthreads <= 768 && d.nRowWarps * 32 <= nthreads && smem <= 232448;
     if (opt.path == 2 || (!fits && opt.path == 0)) return acb_solve_general(site, batch, opt, st);

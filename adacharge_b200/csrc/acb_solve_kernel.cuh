@@ -65,13 +65,15 @@ struct SmemLayout {
         SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
     int OP;  // padded output count of MFT
 };
-__host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps) {
+// compact: no materialised bounds; each EVSE row keeps (window start, window end, min, max) instead (constant limits,
+// at most one session per row)
+__host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps, bool compact = false) {
     SmemLayout L;
     int o = 0;
     auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
     L.OP = ((NG + R + 3 * ACB_OPP - 1) / (3 * ACB_OPP)) * (3 * ACB_OPP);  // multiple of 24: any NCH in {1,3} divides it
-    L.LB = take(N * Tp);
-    L.UB = take(N * Tp);
+    L.LB = take(compact ? 4 * N : N * Tp);
+    L.UB = compact ? L.LB : take(N * Tp);
     // PART doubles as scratch for Sinv (R*R) and X (R*NG) while the column matrix is rebuilt
     const int scratch = R * R + R * NG + 8;
     L.PART = take(NP * Tp > scratch ? NP * Tp : scratch);
@@ -114,8 +116,8 @@ enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, 
 // per-warp double reduction slots (sum-type)
 enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA, RD_PLC, RD_PLA };
 
-template <int Q, int TPW, bool MULTI, int NCH>
-__global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L) {
+template <int Q, int TPW, bool MULTI, int NCH, bool COMPACT = false>
+__global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -156,8 +158,41 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
     const bool useAvg = opt.restart && VSUM != nullptr;
 
+    // bounds of element (row, t): the materialised arrays, or (COMPACT) the row's window and constant limits
+    auto lbv = [&](int row, int t) -> float {
+        if constexpr (COMPACT) { const float* rb = LB + 4 * row; return (t >= (int)rb[0] && t < (int)rb[1]) ? rb[2] : 0.f; }
+        else return LB[row * Tp + t];
+    };
+    auto ubv = [&](int row, int t) -> float {
+        if constexpr (COMPACT) { const float* rb = LB + 4 * row; return (t >= (int)rb[0] && t < (int)rb[1]) ? rb[3] : 0.f; }
+        else return UB[row * Tp + t];
+    };
+    // the lane's Q elements of a row (t = lane + 32 q)
+    auto load_bounds = [&](int row, float (&lb)[Q], float (&ub)[Q]) {
+        if constexpr (COMPACT) {
+            const float* rb = LB + 4 * row;
+            const int a = (int)rb[0], e = (int)rb[1];
+            const float lo = rb[2], hi = rb[3];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const int t = lane + 32 * q;
+                const bool in = t >= a && t < e;
+                lb[q] = in ? lo : 0.f;
+                ub[q] = in ? hi : 0.f;
+            }
+        } else {
+            const float* lbp = LB + row * Tp + lane;
+            const float* ubp = UB + row * Tp + lane;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                lb[q] = lbp[32 * q];
+                ub[q] = ubp[32 * q];
+            }
+        }
+    };
+
     // ------------------------------------------------------------------ prologue
-    for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
+    for (int i = tid; i < (COMPACT ? 4 * N : 2 * N * Tp); i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
     for (int i = tid; i < R * Tp; i += nthreads) {
         VC[i] = B.warm_vc ? B.warm_vc[(size_t)b * R * Tp + i] : 0.f;
         VOUT[i] = 0.f;
@@ -193,10 +228,20 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     for (int s = warp; s < nS; s += nwarps) {
         size_t k = (size_t)b * B.S_max + s;
         int row = B.sess_row[k], a = SESS_A[s], len = SESS_B[s] - a, off = B.sess_rate_off[k];
+        if constexpr (COMPACT) {
+            // constant limits only (off < 0); the host routes other batches to the standard kernel
+            if (lane == 0) {
+                const int ri = off >= 0 ? off : -(off + 1);
+                const float lo = B.min_rates[ri], hi = B.max_rates[ri];
+                float* rb = LB + 4 * row;
+                rb[0] = (float)a; rb[1] = (float)min(a + len, Tp); rb[2] = lo; rb[3] = fmaxf(hi, lo);
+            }
+        } else {
         for (int j = lane; j < len; j += 32) {
             const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
             float lo = B.min_rates[ri], hi = B.max_rates[ri];
             if (a + j < Tp) { LB[row * Tp + a + j] = lo; UB[row * Tp + a + j] = fmaxf(hi, lo); }
+        }
         }
     }
     if (tid < S.nSlots) {
@@ -212,7 +257,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     __syncthreads();
     {
         bool pos = false;
-        for (int i = tid; i < N * Tp; i += nthreads) pos |= (LB[i] != 0.f);
+        if constexpr (COMPACT) { for (int i = tid; i < N; i += nthreads) pos |= (LB[4 * i + 2] != 0.f && LB[4 * i + 1] > LB[4 * i]); }
+        else for (int i = tid; i < N * Tp; i += nthreads) pos |= (LB[i] != 0.f);
         if (pos) SCAL[SC_LBPOS] = 1.f;  // benign race: every writer stores the same value
     }
     // row-level infeasibility: a session whose window cannot hold its energy equality, or whose
@@ -220,7 +266,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     for (int s = warp; s < nS; s += nwarps) {
         int row = B.sess_row[(size_t)b * B.S_max + s];
         float slo = 0.f, shi = 0.f;
-        for (int t = SESS_A[s] + lane; t < min(SESS_B[s], Tp); t += 32) { slo += LB[row * Tp + t]; shi += UB[row * Tp + t]; }
+        for (int t = SESS_A[s] + lane; t < min(SESS_B[s], Tp); t += 32) { slo += lbv(row, t); shi += ubv(row, t); }
         slo = warp_sum(slo); shi = warp_sum(shi);
         const float Eb = SESS_E[s], tol = 1e-5f * (fabsf(Eb) + 1.f);
         if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) SCAL[SC_FLAG] = 1.f;
@@ -291,7 +337,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         for (int i = tid; i < S.nSlots * Tp; i += nthreads) {
             const int s = i / Tp, t = i - s * Tp, row = SLOT[s * 6];
             if (row < 0) continue;
-            const float c = ALPHA[t] + KG[SLOT[s * 6 + 1]] * BETA[t], lo = LB[row * Tp + t], hi = UB[row * Tp + t];
+            const float c = ALPHA[t] + KG[SLOT[s * 6 + 1]] * BETA[t], lo = lbv(row, t), hi = ubv(row, t);
             pm += (double)fmaxf(c * lo, c * hi) + (double)qd * (double)fmaxf(lo * lo, hi * hi);
         }
         if (S.has_u && (Gamma > 0.f || pk_w > 0.f)) {
@@ -301,7 +347,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     const int row = SLOT[s * 6];
                     if (row < 0) continue;
                     const float k = KG[SLOT[s * 6 + 1]];
-                    umax += k * UB[row * Tp + t]; umin += k * LB[row * Tp + t];
+                    umax += k * ubv(row, t); umin += k * lbv(row, t);
                 }
                 const float e = EBAR[t];
                 pm += (double)Gamma * (double)fmaxf((umax + e) * (umax + e), (umin + e) * (umin + e));
@@ -332,7 +378,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             float v = 0.f;
             if (row >= 0) {
                 if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
-                else v = clampf(0.f, LB[row * Tp + t], UB[row * Tp + t]);
+                else v = clampf(0.f, lbv(row, t), ubv(row, t));
             }
             v1[k][q] = v;
         }
@@ -543,7 +589,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             for (int q = 0; q < Q; ++q) {
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sf, scn, mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
+                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sf, scn, mu0, t), lbv(row, t), ubv(row, t));
                 float val = 2.f * z - v1[k][q];
                 if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
             }
@@ -680,14 +726,11 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 if (row < 0) continue;
                 const int g = sl[1], prow = sl[2], first = sl[3], sf = sl[4], scn = sl[5];
                 const float mu0 = scn ? SESS_MU[sf] : 0.f;
-                const float* lbp = LB + row * Tp + lane;
-                const float* ubp = UB + row * Tp + lane;
                 const float* hgp = HG + g * Tp + lane;
                 float lb[Q], ub[Q], zo[CHK ? Q : 1], xs[CHK ? Q : 1];
+                load_bounds(row, lb, ub);
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    lb[q] = lbp[32 * q];
-                    ub[q] = ubp[32 * q];
                     float vo = v1[k][q];
                     float z = clampf(vo - MU_ELEM(SESS_MU, sf, scn, mu0, lane + 32 * q), lb[q], ub[q]);
                     float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
@@ -833,8 +876,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 for (int q = 0; q < Q; ++q) {
                     int t = lane + 32 * q;
                     bool in = t < Tp;
-                    lb[q] = in ? LB[row * Tp + t] : 0.f;
-                    ub[q] = in ? UB[row * Tp + t] : 0.f;
+                    lb[q] = in ? lbv(row, t) : 0.f;
+                    ub[q] = in ? ubv(row, t) : 0.f;
                     va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] / nsum : 0.f;
                 }
                 // energy-row multipliers of the dual bound: the iterate's (rho1 * mu_s), or the maximiser given y
@@ -1040,7 +1083,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 #pragma unroll
                         for (int q = 0; q < Q; ++q) {
                             int t = lane + 32 * q;
-                            if (t < Tp) v1[k][q] = clampf(0.f, LB[row * Tp + t], UB[row * Tp + t]);
+                            if (t < Tp) v1[k][q] = clampf(0.f, lbv(row, t), ubv(row, t));
                         }
                     }
                 }
@@ -1059,7 +1102,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
                         if (t >= Tp) continue;
-                        float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
+                        float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
                         v1[k][q] = z + f * (v1[k][q] - z);
                     }
                 }
@@ -1109,7 +1152,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             for (int q = 0; q < Q; ++q) {
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), LB[row * Tp + t], UB[row * Tp + t]);
+                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
                 B.rates[((size_t)b * N + row) * Tp + t] = z * THX[t];
                 if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
             }
@@ -1129,12 +1172,14 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 
 
 // explicit launch helper used by the per-horizon translation units
-template <int Q, int TPW, bool MULTI, int NCH>
+template <int Q, int TPW, bool MULTI, int NCH, bool COMPACT = false>
 int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads, size_t smem, cudaStream_t st) {
-    auto kern = acb_solve_kernel<Q, TPW, MULTI, NCH>;
+    auto kern = acb_solve_kernel<Q, TPW, MULTI, NCH, COMPACT>;
     ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const SiteDev& d = site->d;
-    SmemLayout L = make_layout(d.N, d.R, d.NG, d.NP, d.nSlots, 32 * Q, batch->S_max, nthreads / 32);
+    if (COMPACT)  // two blocks per SM need the large shared-memory carve-out
+        ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    const SiteDev& d = COMPACT ? site->d6 : site->d;
+    SmemLayout L = make_layout(d.N, d.R, d.NG, d.NP, d.nSlots, 32 * Q, batch->S_max, nthreads / 32, COMPACT);
     kern<<<batch->B, nthreads, smem, st>>>(d, *batch, *opt, L);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
@@ -1146,4 +1191,11 @@ int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_o
         if (!multi && nch == 3) return acb_launch_solve_t<QQ, 3, false, 3>(site, batch, opt, nthreads, smem, st);           \
         if (multi && nch == 1) return acb_launch_solve_t<QQ, 3, true, 1>(site, batch, opt, nthreads, smem, st);             \
         return acb_launch_solve_t<QQ, 3, true, 3>(site, batch, opt, nthreads, smem, st);                                    \
+    }
+// compact-bounds kernel (experimental, acb_options.path = 3): 6 rows per warp, 384 threads, two blocks per SM
+#define ACB_INSTANTIATE_COMPACT_Q(QQ)                                                                                      \
+    int acb_launch_solve_compact_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads, \
+                                       size_t smem, cudaStream_t st, int nch) {                                            \
+        if (nch == 1) return acb_launch_solve_t<QQ, 6, false, 1, true>(site, batch, opt, nthreads, smem, st);               \
+        return acb_launch_solve_t<QQ, 6, false, 3, true>(site, batch, opt, nthreads, smem, st);                             \
     }

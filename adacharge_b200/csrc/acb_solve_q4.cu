@@ -1,3 +1,4 @@
 // Instantiations of the solve kernel for the padded horizon Tp = 128.
 #include "acb_solve_kernel.cuh"
 ACB_INSTANTIATE_Q(4)
+ACB_INSTANTIATE_COMPACT_Q(4)

@@ -86,7 +86,8 @@ typedef struct acb_options {
     int32_t avg_every;   /* state is added to the average every avg_every iterations */
     int32_t stall_checks; /* change rho when the best gap has not improved by 10 % over this many checks (0 = never) */
     int32_t max_rescues;  /* at most this many stagnation rescues (1st: rho x3; 2nd, warm-started solves only: restart cold) */
-    int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only */
+    int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only;
+                          * 3 = experimental compact-bounds on-chip kernel (constant limits, one session per EVSE, Tp 128/288) */
     int32_t stall_exit;  /* with all rescues used: stop (ACB_MAX_ITER, stats[2] = certified gap) after this many checks without a 10 % better gap; 0 = never */
     int32_t dual_refine; /* dual bound uses the best energy-row multipliers given y: 0 = never, 1 = when the gap stalled at the last check, 2 = at every check */
     float term_floor;    /* the gap tolerance is eps_abs + eps_rel * max(|P|, |D|, term_floor * sum of |objective terms|); default 0.05.
