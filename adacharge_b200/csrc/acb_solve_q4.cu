@@ -1,4 +1,3 @@
 // Instantiations of the solve kernel for the padded horizon Tp = 128.
 #include "acb_solve_kernel.cuh"
 ACB_INSTANTIATE_Q(4)
-ACB_INSTANTIATE_COMPACT_Q(4)
