@@ -79,7 +79,7 @@ typedef struct acb_options {
     float kappa;        /* identity-block penalty = kappa * rho */
     float alpha;        /* over-relaxation in (0, 2) */
     int32_t max_iter;
-    int32_t check_every; /* residual check period (iterations) */
+    int32_t check_every; /* convergence-check period in iterations (the first check is at iteration 10) */
     int32_t equality;    /* enforce_energy_equality */
     int32_t adapt_rho;   /* 0 = off, 1 = residual balancing with threshold 5, n > 1 = threshold n/10 */
     int32_t restart;     /* 1 = average the state and restart from the average when its gap halves */
