@@ -16,7 +16,8 @@ or objective value at this boundary, and cvxpy/ECOS cannot run
 this image, so this oracle is pinned by (i) every property the reference's solver
 tests assert (tests/test_oracle_mpc.py restates all scenarios of
 tests/test_adaptive_charging_optimization.py), (ii) analytic unique optima of
-those scenarios, (iii) HiGHS agreement on LP-representable cases.  No output of the
+those scenarios, (iii) HiGHS agreement on LP-representable cases, (iv) agreement with an
+independent SLSQP solve on mixed-phase second-order-cone cases.  No output of the
 reference solver itself is available: *solver parity is pinned to the reference's
 tests and formulation, not to reference-produced vectors*.
 

@@ -115,3 +115,81 @@ def test_random_lp_instances_match_highs(seed):
     Rh, fh = mpc.solve_lp_highs(*args)
     f = mpc.evaluate_objective(R, sc["objective"], I, iface, S, iface.get_prev_peak())
     assert abs(f - fh) <= 1e-6 * max(1.0, abs(fh)), (f, fh)
+
+
+def _soc_random_seeds(limit=6):
+    from tests.scenarios import random_scenario
+
+    out = []
+    for seed in range(120):
+        sc = random_scenario(seed)
+        if sc["constraint_type"] != "SOC" or len(set(np.asarray(sc["data"][1]["phases"]).tolist())) < 2:
+            continue
+        if any(o[0] in ("demand_charge", "load_flattening") for o in sc["objective"]):
+            continue
+        iface = make_interface(sc)
+        if iface.infrastructure_info().num_stations * mpc.horizon(iface.active_sessions()) > 130:
+            continue
+        out.append(seed)
+        if len(out) == limit:
+            break
+    return out
+
+
+def _independent_soc_solve(sc):
+    """The scenario solved without the oracle's canonicalisation or interior-point method: scipy SLSQP on the
+    reference formulation written out directly (norm-squared line-current constraints with analytic Jacobians, the
+    objective as the quadratic it is for these components)."""
+    from scipy.optimize import minimize
+
+    iface = make_interface(sc); S, I = iface.active_sessions(), iface.infrastructure_info()
+    T = mpc.horizon(S); N = I.num_stations; n = N * T
+    lb, ub = mpc.bounds(S, I.station_ids, T); ub = np.maximum(ub, lb)
+    obj = sc["objective"]; pp = iface.get_prev_peak()
+    F = lambda x: -mpc.evaluate_objective(x.reshape(N, T), obj, I, iface, S, pp)
+    # the admitted objectives are linear + diagonal quadratic: recover the coefficients from 2n evaluations around a point inside the box
+    xm = (0.5 * (lb + ub)).ravel(); f0 = F(xm); a = np.zeros(n); q = np.zeros(n)
+    for i in range(n):
+        e = np.zeros(n); e[i] = 1.0
+        fp, fm = F(xm + e), F(xm - e)
+        q[i] = 0.5 * (fp + fm) - f0; a[i] = 0.5 * (fp - fm)
+    f = lambda x: f0 + a @ (x - xm) + q @ (x - xm) ** 2
+    g = lambda x: a + 2 * q * (x - xm)
+    cons = []
+    for (i, s0, s1, w, e) in mpc.session_rows(S, I, iface.period):
+        row = np.zeros((N, T)); row[i, s0:s1] = w; row = row.ravel()
+        if sc.get("equality"): cons.append(dict(type="eq", fun=lambda x, r=row, e=e: r @ x - e, jac=lambda x, r=row: r))
+        else: cons.append(dict(type="ineq", fun=lambda x, r=row, e=e: e - r @ x, jac=lambda x, r=row: -r))
+    rows = mpc.soc_rows(I); lim = np.asarray(I.constraint_limits, float); M = rows.shape[0]
+    def soc(x):
+        cur = np.einsum("mkn,nt->mkt", rows, x.reshape(N, T))
+        return (lim[:, None] ** 2 - (cur ** 2).sum(axis=1)).ravel()
+    def soc_jac(x):
+        cur = np.einsum("mkn,nt->mkt", rows, x.reshape(N, T))
+        J = np.zeros((M, T, N, T))
+        for t in range(T):
+            J[:, t, :, t] = -2 * np.einsum("mk,mkn->mn", cur[:, :, t], rows)
+        return J.reshape(M * T, n)
+    cons.append(dict(type="ineq", fun=soc, jac=soc_jac))
+    if sc.get("peak_limit") is not None:
+        pl = np.broadcast_to(np.asarray(sc["peak_limit"], float), (T,)).copy()
+        A = np.zeros((T, n))
+        for t in range(T): A[t, t::T] = 1
+        cons.append(dict(type="ineq", fun=lambda x: pl - A @ x, jac=lambda x: -A))
+    res = minimize(f, lb.ravel().copy(), jac=g, method="SLSQP", bounds=list(zip(lb.ravel(), ub.ravel())), constraints=cons, options=dict(maxiter=2000, ftol=1e-14))
+    assert abs(F(res.x) - f(res.x)) <= 1e-7 * max(1, abs(f0))  # the quadratic model is the objective
+    return -res.fun, res, (iface, S, I)
+
+
+
+@pytest.mark.parametrize("seed", _soc_random_seeds())
+def test_mixed_phase_soc_instances_match_slsqp(seed):
+    """True second-order-cone cases (three-phase rows mixing phase angles), where HiGHS cannot help: the oracle
+    against an independent SLSQP solve of the directly written problem."""
+    from tests.scenarios import random_scenario
+
+    sc = random_scenario(seed)
+    fs, res, (iface, S, I) = _independent_soc_solve(sc)
+    R = mpc.solve_mpc(sc["objective"], S, I, iface, "SOC", sc.get("equality", False), sc.get("peak_limit"), iface.get_prev_peak())
+    fo = mpc.evaluate_objective(R, sc["objective"], I, iface, S, iface.get_prev_peak())
+    assert abs(fs - fo) <= 1e-6 * max(1.0, abs(fo)), (fs, fo, res.status)
