@@ -117,15 +117,13 @@ def test_random_lp_instances_match_highs(seed):
     assert abs(f - fh) <= 1e-6 * max(1.0, abs(fh)), (f, fh)
 
 
-def _soc_random_seeds(limit=10):
+def _soc_random_seeds(limit=14):
     from tests.scenarios import random_scenario
 
     out = []
     for seed in range(120):
         sc = random_scenario(seed)
         if sc["constraint_type"] != "SOC" or len(set(np.asarray(sc["data"][1]["phases"]).tolist())) < 2:
-            continue
-        if any(o[0] == "load_flattening" for o in sc["objective"]):
             continue
         iface = make_interface(sc)
         if iface.infrastructure_info().num_stations * mpc.horizon(iface.active_sessions()) > 130:
@@ -146,7 +144,8 @@ def _independent_soc_solve(sc):
     T = mpc.horizon(S); N = I.num_stations; n = N * T
     lb, ub = mpc.bounds(S, I.station_ids, T); ub = np.maximum(ub, lb)
     pp = iface.get_prev_peak()
-    obj = [o for o in sc["objective"] if o[0] != "demand_charge"]
+    obj = [o for o in sc["objective"] if o[0] not in ("demand_charge", "load_flattening")]
+    flat = [(o[1], np.asarray(o[2].get("external_signal", np.zeros(T)), float)[:T]) for o in sc["objective"] if o[0] == "load_flattening"]
     # demand_charge = -dc * max(max_t u_t, prev_peak kW): an epigraph variable tau appended to x (aco.py:387-400)
     w_peak = sum(o[1] for o in sc["objective"] if o[0] == "demand_charge") * iface.get_demand_charge()
     k = np.asarray(I.voltages, float) / 1000.0
@@ -158,8 +157,19 @@ def _independent_soc_solve(sc):
         e = np.zeros(n); e[i] = 1.0
         fp, fm = F(xm + e), F(xm - e)
         q[i] = 0.5 * (fp + fm) - f0; a[i] = 0.5 * (fp - fm)
-    f = lambda x: f0 + a @ (x - xm) + q @ (x - xm) ** 2
-    g = lambda x: a + 2 * q * (x - xm)
+    kk = np.asarray(I.voltages, float) / 1000.0
+
+    def f(x):  # linear + diagonal quadratic part, plus load_flattening written out: coef * sum_t (u_t + ext_t)^2  (aco.py:403-408)
+        val = f0 + a @ (x - xm) + q @ (x - xm) ** 2
+        for coef, ext in flat:
+            val += coef * ((kk @ x.reshape(N, T) + ext) ** 2).sum()
+        return val
+
+    def g(x):
+        grad = a + 2 * q * (x - xm)
+        for coef, ext in flat:
+            grad = grad + (2 * coef * np.outer(kk, kk @ x.reshape(N, T) + ext)).ravel()
+        return grad
     cons = []
     for (i, s0, s1, w, e) in mpc.session_rows(S, I, iface.period):
         row = np.zeros((N, T)); row[i, s0:s1] = w; row = row.ravel()
