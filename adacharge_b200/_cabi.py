@@ -17,8 +17,12 @@ ACB_NSTATS = 8
 EXPORTS = [
     "acb_site_create", "acb_site_destroy", "acb_site_dims", "acb_site_max_horizon", "acb_default_options",
     "acb_solve_batch", "acb_charging_rate_bounds", "acb_project_continuous", "acb_project_discrete",
-    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_last_error", "acb_version",
+    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_pack_sessions", "acb_last_error", "acb_version",
 ]
+ACB_MAX_COMPONENTS = 16
+# acb_objective.kind values (include/adacharge_b200.h)
+OBJ_KIND = {"quick_charge": 0, "equal_share": 1, "tou_energy_cost": 2, "total_energy": 3, "peak": 4, "demand_charge": 5,
+            "load_flattening": 6, "non_completion_penalty": 7}
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -30,6 +34,7 @@ class Options(C.Structure):
         ("eps_abs", C.c_float), ("eps_rel", C.c_float), ("viol_tol", C.c_float), ("rho0", C.c_float),
         ("kappa", C.c_float), ("alpha", C.c_float), ("max_iter", C.c_int32), ("check_every", C.c_int32),
         ("equality", C.c_int32), ("adapt_rho", C.c_int32), ("restart", C.c_int32), ("avg_every", C.c_int32), ("stall_checks", C.c_int32), ("max_rescues", C.c_int32), ("path", C.c_int32), ("stall_exit", C.c_int32), ("dual_refine", C.c_int32), ("term_floor", C.c_float), ("rho_curv", C.c_float),
+        ("rate_tol", C.c_float), ("polish_min_qd", C.c_float), ("phase_iters", C.c_int32),
     ]
 
 
@@ -45,8 +50,20 @@ class Batch(C.Structure):
         ("peak_limit", _P), ("work", _P),
         ("warm_v1", _P), ("warm_vc", _P), ("warm_mu", _P), ("warm_scal", _P),
         ("out_v1", _P), ("out_vc", _P), ("out_mu", _P), ("out_scal", _P),
-        ("rates", _P), ("status", _P), ("iters", _P), ("stats", _P),
+        ("rates", _P), ("pilots", _P), ("rate_est", _P), ("status", _P), ("iters", _P), ("stats", _P),
     ]
+
+
+class Sessions(C.Structure):
+    _fields_ = [("B", C.c_int32), ("S_max", C.c_int32), ("station", _P), ("arrival_offset", _P), ("remaining_time", _P),
+                ("remaining_demand", _P), ("min_rate", _P), ("max_rate", _P)]
+
+
+class Objective(C.Structure):
+    _fields_ = [("n", C.c_int32), ("kind", C.c_int32 * ACB_MAX_COMPONENTS), ("coef", C.c_double * ACB_MAX_COMPONENTS),
+                ("param", C.c_double * ACB_MAX_COMPONENTS), ("period", C.c_double), ("prices", _P), ("prices_stride", C.c_int32),
+                ("prev_peak", _P), ("demand_charge", _P), ("demand_charge_scalar", C.c_double), ("external_signal", _P),
+                ("ext_stride", C.c_int32), ("peak_limit", _P), ("pl_stride", C.c_int32)]
 
 
 _lib = None
@@ -77,6 +94,7 @@ def lib():
     L.acb_reallocate.argtypes = [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]
     L.acb_constraints_feasible.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]
     L.acb_min_rate_admission.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]
+    L.acb_pack_sessions.argtypes = [_P, C.POINTER(Sessions), C.POINTER(Objective), C.POINTER(Batch), _P, _P]
     _lib = L
     return L
 
@@ -87,6 +105,13 @@ def check(rc: int, what: str):
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise RuntimeError(f"{what} failed ({rc}): {msg}")
+
+
+def copy_options(o: Options, **over) -> Options:
+    c = Options.from_buffer_copy(o)
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
 
 
 def default_options(**over) -> Options:

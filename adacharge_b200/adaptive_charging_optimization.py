@@ -349,7 +349,8 @@ class AdaptiveChargingOptimization:
         stats = pb.stats[0].cpu().numpy()
         self.last_info = dict(status=status, iters=int(pb.iters[0].item()), r_prim=float(stats[0]), r_dual=float(stats[1]),
                               gap=float(stats[2]), violation=float(stats[3]), rho=float(stats[4]), restarts=int(stats[6]),
-                              averaged=bool(stats[7]))
+                              averaged=bool(stats[7]),
+                              rate_est=None if pb.rate_est is None else float(pb.rate_est[0].item()))
         if verbose:
             print(self.last_info)
         check_status(status, self.last_info)

@@ -43,6 +43,7 @@ struct SiteDev {
     const double* a_sin;    // [M*N]
     const double* limits;   // [M]
     const double* max_pilot;// [N]
+    const double* volt;     // [N] voltages (V), float64 for the device packer
     const int* allow_off;   // [N+1]
     const double* allow_vals;
 };
@@ -50,8 +51,6 @@ struct SiteDev {
 struct acb_site {
     int device;
     SiteDev d;
-    SiteDev d6;          // same site with 6 EVSE rows per warp (slot tables only differ): the compact-bounds kernel, 2 blocks per SM
-    int has_d6;
     std::vector<void*> allocs;
     int constraint_type;
     const int* grp_off_dev;  // [NG+1] offsets of each group's rows in the (group-sorted) slot list
@@ -69,5 +68,13 @@ void acb_set_error(const std::string& s);
         }                                                                             \
     } while (0)
 
+// keep the stream-ordered pool's memory across calls (the default release threshold of 0 gives it back at every sync)
+inline void acb_keep_pool(int device) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+}
 size_t acb_solve_smem_bytes(const SiteDev& s, int Tp, int S_max, int nwarps);
 int acb_solve_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st);

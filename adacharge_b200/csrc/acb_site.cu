@@ -36,6 +36,9 @@ extern "C" void acb_default_options(acb_options* o) {
     o->term_floor = 0.05f;
     o->rho_curv = 1.0f;
     o->path = 0;
+    o->rate_tol = 3e-4f;
+    o->polish_min_qd = 5e-4f;
+    o->phase_iters = 0;
 }
 
 // cyclic Jacobi eigen-decomposition of a symmetric n x n matrix (row-major), double.
@@ -281,35 +284,11 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
         if ((rc = upload(s, ut, &d.Ut)) != ACB_OK) { acb_site_destroy(s); return rc; }
     }
     UP(acos_, a_cos) UP(asin_, a_sin) UP(lim64, limits) UP(mp, max_pilot) UP(aoff, allow_off) UP(avals, allow_vals)
-#undef UP
-    // second slot layout: 6 EVSE rows per warp (half the row warps) for the compact-bounds kernel
-    s->has_d6 = 0;
     {
-        const int TPW6 = 6;
-        if ((N + TPW6 - 1) / TPW6 <= ACB_MAX_WARPS) {
-            SiteDev& e = s->d6;
-            e = d;
-            e.TPW = TPW6;
-            e.nRowWarps = (N + TPW6 - 1) / TPW6;
-            e.nSlots = e.nRowWarps * TPW6;
-            std::vector<int> s_row(e.nSlots, -1), s_grp(e.nSlots, 0), s_prow(e.nSlots, 0), s_first(e.nSlots, 0), p_off(NG + 1, 0);
-            int np6 = 0;
-            for (int sl = 0; sl < e.nSlots && sl < N; ++sl) {
-                const int i = order[sl], g = grp[i];
-                s_row[sl] = i;
-                s_grp[sl] = g;
-                const bool newp = (sl % TPW6 == 0) || s_grp[sl - 1] != g;
-                if (newp) { s_first[sl] = 1; s_prow[sl] = np6++; p_off[g + 1]++; }
-                else s_prow[sl] = s_prow[sl - 1];
-            }
-            for (int g = 0; g < NG; ++g) p_off[g + 1] += p_off[g];
-            e.NP = np6;
-            if ((rc = upload(s, s_row, &e.slot_row)) != ACB_OK || (rc = upload(s, s_grp, &e.slot_grp)) != ACB_OK ||
-                (rc = upload(s, s_prow, &e.slot_prow)) != ACB_OK || (rc = upload(s, s_first, &e.slot_first)) != ACB_OK ||
-                (rc = upload(s, p_off, &e.pg_off)) != ACB_OK) { acb_site_destroy(s); return rc; }
-            s->has_d6 = 1;
-        }
+        std::vector<double> volt64(voltages, voltages + N);
+        UP(volt64, volt)
     }
+#undef UP
     *out = s;
     return ACB_OK;
 }

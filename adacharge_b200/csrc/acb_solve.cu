@@ -28,12 +28,38 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
     }
 }
 
-int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
-int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
-int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
-int acb_launch_solve_compact_q4(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, int);
-int acb_launch_solve_compact_q9(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, int);
-int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+
+// Between the launches of a phased solve: the parked (still running) instances, ordered by the relative gap of their
+// last convergence check, largest first (a counting sort over 256 logarithmic buckets; one block).  The gap after the
+// first phase is the best available predictor of the iterations an instance still needs, so the relaunch approximates
+// longest-processing-time-first scheduling and the longest instances no longer start last.
+__global__ void acb_phase_list_kernel(const int32_t* status, const float* stats, int B, int* list, int* count) {
+    __shared__ int hist[256], base[256];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    auto bucket = [&](int b) -> int {
+        const float g = stats[(size_t)b * ACB_NSTATS + 2];
+        int key = (g > 0.f) ? (int)((log2f(g) + 24.f) * 8.f) : 0;  // 2^-24 .. 2^8 in steps of 2^(1/8)
+        key = min(max(key, 0), 255);
+        return 255 - key;
+    };
+    for (int b = tid; b < B; b += blockDim.x)
+        if (status[b] == ACB_RUNNING) atomicAdd(&hist[bucket(b)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < 256; ++i) { base[i] = acc; acc += hist[i]; }
+        *count = acc;
+    }
+    __syncthreads();
+    for (int b = tid; b < B; b += blockDim.x)
+        if (status[b] == ACB_RUNNING) list[atomicAdd(&base[bucket(b)], 1)] = b;
+}
 
 extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* opt_in, void* stream) {
     if (!site || !batch || batch->B <= 0 || batch->Tp <= 0 || batch->Tp % 32 != 0) {
@@ -51,10 +77,7 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     const int nCT_ = d.nDisc + d.nLin + d.has_pl + d.has_u;
     const int nCT = nCT_;
     const int Q = batch->Tp / 32;
-    if (batch->Tp % 32 != 0 || (Q != 2 && Q != 4 && Q != 5 && Q != 9)) {
-        acb_set_error("acb_solve_batch: Tp must be 64, 128, 160 or 288 (pad the horizon up)");
-        return ACB_E_INVALID;
-    }
+    const bool chipQ = (Q == 2 || Q == 4 || Q == 5 || Q == 9);  // horizons the on-chip kernel is instantiated for
     cudaStream_t st = (cudaStream_t)stream;
     const int NIN = d.NG + d.R;
     const int nch = (NIN <= ACB_OPP) ? 1 : 3;
@@ -62,35 +85,62 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
     int nthreads = std::min(768, ((want + 31) / 32) * 32);
-    if (opt.path == 3) {
-        // experimental compact-bounds kernel: no materialised lb/ub (constant limits, one session per EVSE), 6 rows per
-        // warp, 384 threads, two blocks per SM.  Opt-in only; the caller guarantees the batch qualifies.
-        if (!site->has_d6 || batch->multi_session || (Q != 4 && Q != 9)) {
-            acb_set_error("acb_solve_batch: path 3 (compact bounds) needs a site of <= 192 EVSEs, one session per EVSE and Tp 128 or 288");
-            return ACB_E_INVALID;
-        }
-        const SiteDev& e = site->d6;
-        const int nt = 384;
-        const size_t sm6 = (size_t)make_layout(e.N, e.R, e.NG, e.NP, e.nSlots, batch->Tp, batch->S_max, nt / 32, true).total * sizeof(float);
-        if (e.nRowWarps * 32 > nt || nCT_ > 32 || sm6 > 113 * 1024) {
-            acb_set_error("acb_solve_batch: path 3 (compact bounds) does not fit two blocks per SM for this site (" + std::to_string(sm6) + " B)");
-            return ACB_E_TOO_LARGE;
-        }
-        return (Q == 4) ? acb_launch_solve_compact_q4(site, batch, &opt, nt, sm6, st, nch) : acb_launch_solve_compact_q9(site, batch, &opt, nt, sm6, st, nch);
-    }
     size_t smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
-    const bool fits = d.TPW == 3 && nCT_ <= 32 && nthreads <= 768 && d.nRowWarps * 32 <= nthreads && smem <= 232448;
+    const bool fits = chipQ && d.TPW == 3 && nCT_ <= 32 && nthreads <= 768 && d.nRowWarps * 32 <= nthreads && smem <= 232448;
     if (opt.path == 2 || (!fits && opt.path == 0)) return acb_solve_general(site, batch, opt, st);
     if (!fits) {
-        acb_set_error("acb_solve_batch: instance does not fit the on-chip path (N <= ~66 EVSEs, <= 32 coupling tasks, " +
+        acb_set_error("acb_solve_batch: instance does not fit the on-chip path (Tp in {64, 128, 160, 288}, N <= ~66 EVSEs, <= 32 coupling tasks, " +
                       std::to_string(smem) + " B of shared memory needed, 232448 available)");
         return ACB_E_TOO_LARGE;
     }
     const bool multi = batch->multi_session != 0;
-    if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, nthreads, smem, st, multi, nch);
-    if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, nthreads, smem, st, multi, nch);
-    if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, nthreads, smem, st, multi, nch);
-    return acb_launch_solve_q9(site, batch, &opt, nthreads, smem, st, multi, nch);
+    auto launch = [&](const SolvePhase& ph) -> int {
+        if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
+        if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
+        if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
+        return acb_launch_solve_q9(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
+    };
+    // scratch from the stream-ordered pool: the schedule of the previous check (rate polish) and the parked state
+    int nSM = 148;
+    cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, site->device);
+    const int B = batch->B, N = d.N, Tp = batch->Tp, R1 = std::max(d.R, 1);
+    const bool phased = opt.phase_iters > 0 && opt.phase_iters < opt.max_iter && B > nSM;
+    const bool wantZ = opt.rate_tol > 0.f;
+    const size_t nNT = (size_t)B * N * Tp;
+    size_t bytes = 256;
+    if (wantZ) bytes += nNT * 4;
+    if (phased) bytes += nNT * 4 + ((size_t)B * R1 * Tp + (size_t)B * batch->S_max + (size_t)B * ACB_NSTATE + B + 64) * 4;
+    char* base = nullptr;
+    SolvePhase ph{};
+    ph.it_stop = opt.max_iter;
+    if (wantZ || phased) {
+        acb_keep_pool(site->device);
+        ACB_CUDA(cudaMallocAsync((void**)&base, bytes, st));
+        char* p = base;
+        auto take = [&](size_t n) { void* r = p; p += ((n * 4 + 255) / 256) * 256; return r; };
+        if (wantZ) ph.zprev = (float*)take(nNT);
+        if (phased) {
+            ph.st_v1 = (float*)take(nNT);
+            ph.st_vc = (float*)take((size_t)B * R1 * Tp);
+            ph.st_mu = (float*)take((size_t)B * batch->S_max);
+            ph.st_scal = (float*)take((size_t)B * ACB_NSTATE);
+        }
+    }
+    int rc;
+    if (!phased) rc = launch(ph);
+    else {
+        int* list = (int*)(base + bytes - ((size_t)B + 64) * 4);
+        int* count = list + B;
+        ph.it_stop = opt.phase_iters;
+        rc = launch(ph);
+        if (rc == ACB_OK) {
+            acb_phase_list_kernel<<<1, 1024, 0, st>>>(batch->status, batch->stats, B, list, count);
+            ph.it_stop = opt.max_iter; ph.resume = 1; ph.list = list; ph.count = count;
+            rc = launch(ph);
+        }
+    }
+    if (base) ACB_CUDA(cudaFreeAsync(base, st));
+    return rc;
 }
 
 extern "C" int acb_charging_rate_bounds(acb_site* site, const acb_batch* batch, float* lb, float* ub, void* stream) {

@@ -195,13 +195,38 @@ __device__ __forceinline__ float mu_at(const float* MU, const int* SA, const int
 // MODE 0: iteration (x, v update, projection, SG <- sums of q);  MODE 1: init (SG <- sums of q from V);
 // MODE 2: check (SGZ <- sums of z, P_lin);  MODE 3: check (Lagrangian inner terms with HG = C'y);
 // MODE 4: write the schedule;  MODE 5: rescale V for a new rho (scal[GS_E1] holds rho_old/rho_new)
+//
+// Q > 0: padded horizon 32*Q known at compile time, a row lives in registers (Q values per lane).
+// Q = 0: any horizon that is a multiple of 32 (the offline algorithm, sessions longer than a day; reference
+//        aco.py:243-245 puts no limit on T): a row is staged in the warp's slice of dynamic shared memory instead
+//        (v, lb, ub and the partial group sums: 4 Tp floats per warp), everything else is the same code.
+template <int Q>
+struct RowStore {
+    float v[Q > 0 ? Q : 1], lb[Q > 0 ? Q : 1], ub[Q > 0 ? Q : 1];
+    __device__ __forceinline__ RowStore(float*, int, int) {}
+    __device__ __forceinline__ float& V(int q) { return v[q]; }
+    __device__ __forceinline__ float& LB(int q) { return lb[q]; }
+    __device__ __forceinline__ float& UB(int q) { return ub[q]; }
+};
+template <>
+struct RowStore<0> {
+    float *v, *lb, *ub;
+    __device__ __forceinline__ RowStore(float* base, int Tp, int lane) : v(base + lane), lb(base + Tp + lane), ub(base + 2 * Tp + lane) {}
+    __device__ __forceinline__ float& V(int q) { return v[32 * q]; }
+    __device__ __forceinline__ float& LB(int q) { return lb[32 * q]; }
+    __device__ __forceinline__ float& UB(int q) { return ub[32 * q]; }
+};
+
 template <int Q, int MODE>
-__global__ void __launch_bounds__(256, 3) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
+__global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
     const int g = blockIdx.x, b = blockIdx.y;
     if (W.status[b] >= 0 && MODE != 4) return;
-    constexpr int Tp = 32 * Q;
+    constexpr bool DYN = (Q == 0);
+    const int Tp = DYN ? D.Tp : 32 * Q, nq = DYN ? D.Tp / 32 : Q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    __shared__ float part[8][Tp];
+    extern __shared__ float dsm[];                      // DYN: [nw][4][Tp] (v, lb, ub, partial sums); else [nw][Tp] partial sums
+    float* part = DYN ? dsm + (size_t)warp * 4 * Tp + 3 * Tp : dsm + (size_t)warp * Tp;
+    const int part_stride = DYN ? 4 * Tp : Tp;
     const float* sc = W.scal + (size_t)b * GS_N;
     const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, inv_d = 1.f / dd, alpha = opt.alpha;
     const float kgc = S.kg[g];
@@ -210,29 +235,31 @@ __global__ void __launch_bounds__(256, 3) k_rows(SiteDev S, acb_batch B, acb_opt
     const int* SA = B.sess_start + (size_t)b * B.S_max;
     const int* SL = B.sess_len + (size_t)b * B.S_max;
     float* MU = W.MU + (size_t)b * B.S_max;
-    float acc[Q];
+    float acc[Q > 0 ? Q : 1];  // Q > 0: the warp's partial group sums stay in registers until the end
 #pragma unroll
-    for (int q = 0; q < Q; ++q) acc[q] = 0.f;
+    for (int q = 0; q < nq; ++q) { if constexpr (DYN) part[lane + 32 * q] = 0.f; else acc[q] = 0.f; }
+    auto add_part = [&](int q, float val) { if constexpr (DYN) part[lane + 32 * q] += val; else acc[q] += val; };
     float e1 = 0.f, e2 = 0.f, xm = 0.f, ym = 0.f;
     double dsum = 0.0;
     const float rescale = (MODE == 5) ? sc[GS_E1] : 1.f;
     if (MODE == 5 && rescale == 1.f) return;
+    RowStore<Q> rs(DYN ? dsm + (size_t)warp * 4 * Tp : nullptr, Tp, lane);
     for (int k = grp_off[g] + warp; k < grp_off[g + 1]; k += nw) {
         const int row = S.slot_row[k];
         const size_t base = ((size_t)b * D.N + row) * Tp + lane;
         const int sf = W.row_first[(size_t)b * D.N + row], scn = W.row_cnt[(size_t)b * D.N + row];
-        float v[Q], lb[Q], ub[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) { v[q] = W.V[base + 32 * q]; lb[q] = W.LB[base + 32 * q]; ub[q] = W.UB[base + 32 * q]; }
+        for (int q = 0; q < nq; ++q) { rs.V(q) = W.V[base + 32 * q]; rs.LB(q) = W.LB[base + 32 * q]; rs.UB(q) = W.UB[base + 32 * q]; }
         if (MODE == 0) {
-            float zo[Q];
+            float zo[Q > 0 ? Q : 1];  // previous z for the dual residual (register path only; long horizons report r_dual = 0)
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
+            for (int q = 0; q < nq; ++q) {
                 const int t = lane + 32 * q;
-                float z = clampf(v[q] - mu_at(MU, SA, SL, sf, scn, t), lb[q], ub[q]);
-                float x = (rho1 * (2.f * z - v[q]) + W.HG[((size_t)b * D.NG + g) * Tp + t]) * inv_d;
-                v[q] += alpha * (x - z);
-                zo[q] = z;
+                const float vq = rs.V(q);
+                float z = clampf(vq - mu_at(MU, SA, SL, sf, scn, t), rs.LB(q), rs.UB(q));
+                float x = (rho1 * (2.f * z - vq) + W.HG[((size_t)b * D.NG + g) * Tp + t]) * inv_d;
+                rs.V(q) = vq + alpha * (x - z);
+                if constexpr (!DYN) zo[q] = z;
                 e1 = fmaxf(e1, fabsf(x - z));
                 xm = fmaxf(xm, fabsf(x));
             }
@@ -247,12 +274,12 @@ __global__ void __launch_bounds__(256, 3) k_rows(SiteDev S, acb_batch B, acb_opt
                     float E = 0.f;
                     int nf = 0;
 #pragma unroll
-                    for (int q = 0; q < Q; ++q) {
+                    for (int q = 0; q < nq; ++q) {
                         const int t = lane + 32 * q;
                         if (t >= a && t < e) {
-                            float w = v[q] - mu;
-                            E += clampf(w, lb[q], ub[q]);
-                            nf += (w > lb[q] && w < ub[q]) ? 1 : 0;
+                            float w = rs.V(q) - mu;
+                            E += clampf(w, rs.LB(q), rs.UB(q));
+                            nf += (w > rs.LB(q) && w < rs.UB(q)) ? 1 : 0;
                         }
                     }
                     E = wsum(E);
@@ -275,52 +302,54 @@ __global__ void __launch_bounds__(256, 3) k_rows(SiteDev S, acb_batch B, acb_opt
                 __syncwarp();
             }
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
+            for (int q = 0; q < nq; ++q) {
                 const int t = lane + 32 * q;
-                float zn = clampf(v[q] - mu_at(MU, SA, SL, sf, scn, t), lb[q], ub[q]);
-                acc[q] += 2.f * zn - v[q];
-                W.V[base + 32 * q] = v[q];
-                e2 = fmaxf(e2, fabsf(zn - zo[q]));
-                ym = fmaxf(ym, fabsf(rho1 * (v[q] - zn)));
+                const float vq = rs.V(q);
+                float zn = clampf(vq - mu_at(MU, SA, SL, sf, scn, t), rs.LB(q), rs.UB(q));
+                add_part(q, 2.f * zn - vq);
+                W.V[base + 32 * q] = vq;
+                if constexpr (!DYN) e2 = fmaxf(e2, fabsf(zn - zo[q]));
+                ym = fmaxf(ym, fabsf(rho1 * (vq - zn)));
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
+            for (int q = 0; q < nq; ++q) {
                 const int t = lane + 32 * q;
                 const float mu = mu_at(MU, SA, SL, sf, scn, t);
-                const float z = clampf(v[q] - mu, lb[q], ub[q]);
-                if (MODE == 1) acc[q] += 2.f * z - v[q];
+                const float vq = rs.V(q), lbq = rs.LB(q), ubq = rs.UB(q);
+                const float z = clampf(vq - mu, lbq, ubq);
+                if (MODE == 1) add_part(q, 2.f * z - vq);
                 if (MODE == 2) {
-                    acc[q] += z;
+                    add_part(q, z);
                     float c = AL[t] + kgc * BE[t];
                     dsum += (double)(c * z + qd * z * z);
                 }
                 if (MODE == 3) {
                     float rt = AL[t] + kgc * BE[t] + W.HG[((size_t)b * D.NG + g) * Tp + t] + rho1 * mu;
                     float phi;
-                    if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lb[q], ub[q]); phi = qd * xs * xs + rt * xs; }
-                    else phi = fminf(lb[q] * rt, ub[q] * rt);
+                    if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lbq, ubq); phi = qd * xs * xs + rt * xs; }
+                    else phi = fminf(lbq * rt, ubq * rt);
                     dsum += (double)phi;
                 }
                 if (MODE == 4) B.rates[base + 32 * q] = z;
-                if (MODE == 5) W.V[base + 32 * q] = z + rescale * (v[q] - z);
+                if (MODE == 5) W.V[base + 32 * q] = z + rescale * (vq - z);
+                if (MODE == 4 && B.out_v1) B.out_v1[base + 32 * q] = vq;
             }
             if (MODE == 3 && lane == 0)
                 for (int s = sf; s < sf + scn; ++s) dsum -= (double)(rho1 * MU[s]) * (double)B.sess_energy[(size_t)b * B.S_max + s];
-            if (MODE == 4 && B.out_v1) {
-#pragma unroll
-                for (int q = 0; q < Q; ++q) B.out_v1[base + 32 * q] = v[q];
-            }
         }
     }
     if (MODE <= 2) {
+        if constexpr (!DYN) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) part[warp][lane + 32 * q] = acc[q];
+            for (int q = 0; q < nq; ++q) part[lane + 32 * q] = acc[q];
+        }
         __syncthreads();
         float* out = (MODE == 2 ? W.SGZ : W.SG) + ((size_t)b * D.NG + g) * Tp;
+        const float* p0 = DYN ? dsm + 3 * Tp : dsm;
         for (int t = tid; t < Tp; t += blockDim.x) {
             float s = 0.f;
-            for (int w = 0; w < nw; ++w) s += part[w][t];
+            for (int w = 0; w < nw; ++w) s += p0[(size_t)w * part_stride + t];
             out[t] = s;
         }
     }
@@ -738,7 +767,7 @@ __global__ void k_bounds_general(SiteDev S, acb_batch B, float* lb, float* ub) {
 template <int Q>
 int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st) {
     const SiteDev& d = site->d;
-    const int B = batch->B, Tp = 32 * Q, N = d.N, R = d.R, NG = d.NG;
+    const int B = batch->B, Tp = batch->Tp, N = d.N, R = d.R, NG = d.NG;
     GenDims D{N, R, NG, Tp, Tp / 32, batch->S_max, d.nDisc, d.nLin, d.has_pl, d.has_u, 2 * d.nDisc + d.nLin, 2 * d.nDisc + d.nLin + d.has_pl, d.lin_two_sided};
     // workspace
     const size_t nNT = (size_t)B * N * Tp, nRT = (size_t)B * std::max(R, 1) * Tp, nGT = (size_t)B * NG * Tp;
@@ -769,6 +798,25 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     W.ndone = (int*)take(1, 4);
     ACB_CUDA(cudaMemsetAsync(W.ndone, 0, sizeof(int), st));
     ACB_CUDA(cudaMemsetAsync(W.HG, 0, nGT * sizeof(float), st));
+    // row kernels: registers (Q > 0: 8 warps, Tp floats of partial sums each) or shared-memory staging (Q = 0: as many
+    // warps as fit, 4 Tp floats each)
+    int row_threads = 256;
+    size_t row_smem = (size_t)8 * Tp * sizeof(float);
+    if (Q == 0) {
+        const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)232448 / ((size_t)16 * Tp)));
+        row_threads = 32 * nw;
+        row_smem = (size_t)nw * 4 * Tp * sizeof(float);
+        if (row_smem > 232448) { acb_set_error("acb_solve_batch (general path): horizon too long for the shared-memory row staging"); cudaFreeAsync(base, st); return ACB_E_TOO_LARGE; }
+    }
+    if (row_smem > 48 * 1024) {
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+    }
+#define ROWS(MODE) k_rows<Q, MODE><<<grow, row_threads, row_smem, st>>>(d, *batch, opt, W, D, site->grp_off_dev)
     k_bounds_general<<<B, 256, 0, st>>>(d, *batch, W.LB, W.UB);
     k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
     const dim3 grow(NG, B), gcol((Tp + 32 * ACB_CPL - 1) / (32 * ACB_CPL), B);
@@ -777,7 +825,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
         ACB_CUDA(cudaFuncSetAttribute(k_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     }
-    k_rows<Q, 1><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+    ROWS(1);
     int h_done = 0, it = 0;
     while (it < opt.max_iter) {
         const int burst = std::min(it == 0 ? std::min(ACB_FIRST_CHECK, opt.check_every) : opt.check_every, opt.max_iter - it);
@@ -785,27 +833,28 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
             k_cols<0><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
             k_level<<<B, 32, 0, st>>>(d, *batch, W, D);
             if (k == burst - 1) k_clear_check<<<(B + 127) / 128, 128, 0, st>>>(W, B);
-            k_rows<Q, 0><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+            ROWS(0);
         }
         it += burst;
         // check
-        k_rows<Q, 2><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        ROWS(2);
         k_cols<1><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
-        k_rows<Q, 3><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        ROWS(3);
         k_decide<<<(B + 127) / 128, 128, 0, st>>>(*batch, opt, W, D, it, it >= opt.max_iter ? 1 : 0);
-        k_rows<Q, 5><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+        ROWS(5);
         k_rescale_vc<<<dim3((Tp + 127) / 128, B), 128, 0, st>>>(d, *batch, W, D);
-        k_rows<Q, 1><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);  // SG for the next column pass
+        ROWS(1);  // SG for the next column pass
         ACB_CUDA(cudaMemcpyAsync(&h_done, W.ndone, sizeof(int), cudaMemcpyDeviceToHost, st));
         ACB_CUDA(cudaStreamSynchronize(st));
         if (h_done >= B) break;
     }
-    k_rows<Q, 4><<<grow, 256, 0, st>>>(d, *batch, opt, W, D, site->grp_off_dev);
+    ROWS(4);
     k_finish<<<(B + 127) / 128, 128, 0, st>>>(*batch, W, D);
     if (batch->out_vc) ACB_CUDA(cudaMemcpyAsync(batch->out_vc, W.VC, nRT * sizeof(float), cudaMemcpyDeviceToDevice, st));
     ACB_CUDA(cudaGetLastError());
     ACB_CUDA(cudaFreeAsync(base, st));
     return ACB_OK;
+#undef ROWS
 }
 
 }  // namespace
@@ -816,6 +865,5 @@ int acb_solve_general(acb_site* site, const acb_batch* batch, const acb_options&
     if (Q == 4) return run_general<4>(site, batch, opt, st);
     if (Q == 5) return run_general<5>(site, batch, opt, st);
     if (Q == 9) return run_general<9>(site, batch, opt, st);
-    acb_set_error("acb_solve_batch (general path): Tp must be 64, 128, 160 or 288");
-    return ACB_E_INVALID;
+    return run_general<0>(site, batch, opt, st);  // any other multiple of 32: rows staged in shared memory
 }

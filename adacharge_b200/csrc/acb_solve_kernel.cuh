@@ -65,15 +65,13 @@ struct SmemLayout {
         SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
     int OP;  // padded output count of MFT
 };
-// compact: no materialised bounds; each EVSE row keeps (window start, window end, min, max) instead (constant limits,
-// at most one session per row)
-__host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps, bool compact = false) {
+__host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, int nSlots, int Tp, int S_max, int nwarps) {
     SmemLayout L;
     int o = 0;
     auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
     L.OP = ((NG + R + 3 * ACB_OPP - 1) / (3 * ACB_OPP)) * (3 * ACB_OPP);  // multiple of 24: any NCH in {1,3} divides it
-    L.LB = take(compact ? 4 * N : N * Tp);
-    L.UB = compact ? L.LB : take(N * Tp);
+    L.LB = take(N * Tp);
+    L.UB = take(N * Tp);
     // PART doubles as scratch for Sinv (R*R) and X (R*NG) while the column matrix is rebuilt
     const int scratch = R * R + R * NG + 8;
     L.PART = take(NP * Tp > scratch ? NP * Tp : scratch);
@@ -108,16 +106,45 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 }
 
 // float scalars
-enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE };
+enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE,
+       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST };
 // double scalars
 enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP, SD_PMAX };
 // per-warp float reduction slots (max-type)
-enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA };
+enum { RF_E1 = 0, RF_E2, RF_XMAX, RF_ZMAX, RF_YMAX, RF_NAN, RF_VIOLC, RF_VIOLA, RF_UMAXC, RF_UMAXA, RF_DZ };
 // per-warp double reduction slots (sum-type)
 enum { RD_PC = 0, RD_PA, RD_D, RD_UQC, RD_UQA, RD_PLC, RD_PLA };
 
-template <int Q, int TPW, bool MULTI, int NCH, bool COMPACT = false>
-__global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L) {
+// One launch of a (possibly multi-launch) solve.  A batch can be solved in phases: a launch leaves the iteration loop
+// after iteration `it_stop` and parks the complete solver state of every unfinished instance (status ACB_RUNNING);
+// a later launch with `resume` continues those instances exactly where they stopped (the straggler tail of a batch
+// is then rescheduled longest-expected-first, see acb_solve.cu).
+#define ACB_RUNNING (-1)
+#define ACB_NSTATE 64  // floats of parked scalar state per instance: SCAL (32) + SCALD (16 doubles)
+struct SolvePhase {
+    int it_stop;       // park unfinished instances after this iteration (>= max_iter: never)
+    int resume;        // 1: continue from the parked state
+    const int* list;   // instance of block i (NULL: i); blocks >= *count exit
+    const int* count;
+    float* st_v1;      // parked state: [B][N][Tp], [B][R][Tp], [B][S_max], [B][ACB_NSTATE]
+    float* st_vc;
+    float* st_mu;
+    float* st_scal;
+    float* zprev;      // [B][N][Tp] schedule at the previous check (rate polish) or NULL
+};
+
+#ifdef ACB_TRACE
+// development build only (tools/trace_solve.py): per-warp clock64() stamps of block 0 at the phase boundaries
+#define ACB_TR_IT0 101
+#define ACB_TR_NIT 16
+__device__ long long g_acb_trace[ACB_TR_NIT * 32 * 8];
+#define ACB_TR(k) do { if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT && lane == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + warp) * 8 + (k)] = clock64(); } while (0)
+#else
+#define ACB_TR(k) do { } while (0)
+#endif
+
+template <int Q, int TPW, bool MULTI, int NCH>
+__global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L, const SolvePhase P) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -135,7 +162,8 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     double* SCALD = (double*)(sm + L.SCALD);
     const int OP = L.OP, NIN = NG + R;
 
-    const int b = blockIdx.x;
+    if (P.count && (int)blockIdx.x >= *P.count) return;
+    const int b = P.list ? P.list[blockIdx.x] : blockIdx.x;
     const int Tb = B.T[b];
     const int nS = B.n_sessions[b];
     const int nDisc = S.nDisc, nLin = S.nLin;
@@ -158,41 +186,22 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
     const bool useAvg = opt.restart && VSUM != nullptr;
 
-    // bounds of element (row, t): the materialised arrays, or (COMPACT) the row's window and constant limits
-    auto lbv = [&](int row, int t) -> float {
-        if constexpr (COMPACT) { const float* rb = LB + 4 * row; return (t >= (int)rb[0] && t < (int)rb[1]) ? rb[2] : 0.f; }
-        else return LB[row * Tp + t];
-    };
-    auto ubv = [&](int row, int t) -> float {
-        if constexpr (COMPACT) { const float* rb = LB + 4 * row; return (t >= (int)rb[0] && t < (int)rb[1]) ? rb[3] : 0.f; }
-        else return UB[row * Tp + t];
-    };
+    // bounds of element (row, t)
+    auto lbv = [&](int row, int t) -> float { return LB[row * Tp + t]; };
+    auto ubv = [&](int row, int t) -> float { return UB[row * Tp + t]; };
     // the lane's Q elements of a row (t = lane + 32 q)
     auto load_bounds = [&](int row, float (&lb)[Q], float (&ub)[Q]) {
-        if constexpr (COMPACT) {
-            const float* rb = LB + 4 * row;
-            const int a = (int)rb[0], e = (int)rb[1];
-            const float lo = rb[2], hi = rb[3];
+        const float* lbp = LB + row * Tp + lane;
+        const float* ubp = UB + row * Tp + lane;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                const int t = lane + 32 * q;
-                const bool in = t >= a && t < e;
-                lb[q] = in ? lo : 0.f;
-                ub[q] = in ? hi : 0.f;
-            }
-        } else {
-            const float* lbp = LB + row * Tp + lane;
-            const float* ubp = UB + row * Tp + lane;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                lb[q] = lbp[32 * q];
-                ub[q] = ubp[32 * q];
-            }
+        for (int q = 0; q < Q; ++q) {
+            lb[q] = lbp[32 * q];
+            ub[q] = ubp[32 * q];
         }
     };
 
     // ------------------------------------------------------------------ prologue
-    for (int i = tid; i < (COMPACT ? 4 * N : 2 * N * Tp); i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
+    for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
     for (int i = tid; i < R * Tp; i += nthreads) {
         VC[i] = B.warm_vc ? B.warm_vc[(size_t)b * R * Tp + i] : 0.f;
         VOUT[i] = 0.f;
@@ -228,20 +237,10 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     for (int s = warp; s < nS; s += nwarps) {
         size_t k = (size_t)b * B.S_max + s;
         int row = B.sess_row[k], a = SESS_A[s], len = SESS_B[s] - a, off = B.sess_rate_off[k];
-        if constexpr (COMPACT) {
-            // constant limits only (off < 0); the host routes other batches to the standard kernel
-            if (lane == 0) {
-                const int ri = off >= 0 ? off : -(off + 1);
-                const float lo = B.min_rates[ri], hi = B.max_rates[ri];
-                float* rb = LB + 4 * row;
-                rb[0] = (float)a; rb[1] = (float)min(a + len, Tp); rb[2] = lo; rb[3] = fmaxf(hi, lo);
-            }
-        } else {
         for (int j = lane; j < len; j += 32) {
             const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
             float lo = B.min_rates[ri], hi = B.max_rates[ri];
             if (a + j < Tp) { LB[row * Tp + a + j] = lo; UB[row * Tp + a + j] = fmaxf(hi, lo); }
-        }
         }
     }
     if (tid < S.nSlots) {
@@ -257,8 +256,7 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     __syncthreads();
     {
         bool pos = false;
-        if constexpr (COMPACT) { for (int i = tid; i < N; i += nthreads) pos |= (LB[4 * i + 2] != 0.f && LB[4 * i + 1] > LB[4 * i]); }
-        else for (int i = tid; i < N * Tp; i += nthreads) pos |= (LB[i] != 0.f);
+        for (int i = tid; i < N * Tp; i += nthreads) pos |= (LB[i] != 0.f);
         if (pos) SCAL[SC_LBPOS] = 1.f;  // benign race: every writer stores the same value
     }
     // row-level infeasibility: a session whose window cannot hold its energy equality, or whose
@@ -312,6 +310,8 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
         SCALD[SD_BESTGAP] = 1.0e300;
         SCAL[SC_STALL] = 0.f;
         SCAL[SC_NRESCUE] = 0.f;
+        SCAL[SC_RHOSTART] = SCAL[SC_RHO];
+        SCAL[SC_DZ] = 0.f; SCAL[SC_KAP] = 1.f; SCAL[SC_NDZ] = 0.f; SCAL[SC_RATE_EST] = -1.f;
     }
     __syncthreads();
     const float cs = SCAL[SC_CS];
@@ -322,10 +322,24 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     // With lb = 0, no quadratic term and inequality energy rows the scaled schedule satisfies box, energy caps and
     // every coupling row exactly, and its objective follows from the per-group column sums.
     const bool canRestore = (SCAL[SC_LBPOS] == 0.f) && (qd == 0.f) && !opt.equality;
-    float rho = SCAL[SC_RHO];
-    const float rho_start = rho;  // what a warm start of the next solve inherits (a stagnation rescue is not carried over)
-    float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
+    // rate polish (strictly convex objective, unique optimum): besides the certified gap the stop also asks that the
+    // schedule has stopped moving -- estimated distance to the fixed point <= rate_tol amperes (see the check path)
+    float* ZPREV = P.zprev ? P.zprev + (size_t)b * N * Tp : nullptr;
+    const bool polish = opt.rate_tol > 0.f && qd >= opt.polish_min_qd && ZPREV != nullptr;
     const float su = S.has_u ? S.row_scale[rU] : 1.f;
+    // resume of a parked instance: the scalar state replaces the cold / warm-start values set above
+    int it0 = 0;
+    if (P.resume) {
+        __syncthreads();
+        const float* stp = P.st_scal + (size_t)b * ACB_NSTATE;
+        if (tid < 32) SCAL[tid] = stp[tid];
+        else if (tid < 64) sm[L.SCALD + tid - 32] = stp[tid];
+        __syncthreads();
+        it0 = B.iters[b];
+    }
+    float rho = SCAL[SC_RHO];
+    const float rho_start = SCAL[SC_RHOSTART];  // what a warm start of the next solve inherits (a stagnation rescue is not carried over)
+    float rho1 = kappa * rho, dd = 2.f * qd + rho1, inv_d = 1.f / dd;
 
     // Infeasibility certificate: the Lagrangian bound D is a lower bound of the optimal value over the feasible set, and
     // no feasible point can cost more than the maximum of the objective over the box.  D > that maximum => infeasible
@@ -377,7 +391,8 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
             int t = lane + 32 * q;
             float v = 0.f;
             if (row >= 0) {
-                if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
+                if (P.resume) v = P.st_v1[((size_t)b * N + row) * Tp + t];
+                else if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
                 else v = clampf(0.f, lbv(row, t), ubv(row, t));
             }
             v1[k][q] = v;
@@ -645,16 +660,24 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     auto zero_sums = [&]() {
         if (useAvg) for (int i = tid; i < (N + R) * Tp; i += nthreads) VSUM[i] = 0.f;
     };
-    zero_sums();
+    if (P.resume) {
+        // (the prologue filled VC / SESS_MU from the warm-start arrays; the PMAX block above ended with a barrier)
+        for (int i = tid; i < R * Tp; i += nthreads) VC[i] = P.st_vc[(size_t)b * R * Tp + i];
+        for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = P.st_mu[(size_t)b * B.S_max + i];
+        __syncthreads();
+    } else zero_sums();
     build_matrix();
     write_part_q();
     __syncthreads();
 
     int it = 0, status = ACB_MAX_ITER;
+    bool parked = false;
     const int nParts = (NIN + ACB_OPP * NCH - 1) / (ACB_OPP * NCH);
     const int avgEvery = max(1, opt.avg_every);
-    for (it = 1; it <= opt.max_iter; ++it) {
+    for (it = it0 + 1; it <= opt.max_iter; ++it) {
+        if (it > P.it_stop) { parked = true; break; }
         const float plevel = SCAL[SC_PLEVEL];
+        ACB_TR(0);
         // ------------------------------------------------------------ column pass
         // work item = (period t, block of 8*NCH outputs); with NIN <= 8*NCH one thread owns a
         // whole column and nothing is loaded twice
@@ -709,11 +732,13 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
                 else if (o < NIN) VOUT[(o - NG) * Tp + t] = out[k] * inv_rho;
             }
         }
+        ACB_TR(1);
         __syncthreads();
+        ACB_TR(2);
         const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter) || (it == ACB_FIRST_CHECK);  // easy / warm-started instances stop early
         const bool doAvg = useAvg && (it % avgEvery == 0);
         const bool avgFirst = SCAL[SC_NSUM] == 0.f;
-        float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f;
+        float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f, rDz = 0.f;
         double dPc = 0.0, dD = 0.0;  // primal (linear + diagonal part) of the current candidate; dual pieces
         // --------------------------------------------------------------- row pass
         // (two instantiations: the hot non-check version keeps fewer values live)
@@ -765,6 +790,11 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
                         rZm = fmaxf(rZm, fabsf(zn));
                         rYm = fmaxf(rYm, fabsf(rho1 * (vn - zn)));
                         if (!(fabsf(vn) < 1.0e30f)) rNan = 1.f;
+                        if (polish) {  // movement of the schedule since the previous check
+                            float* zp = ZPREV + (size_t)row * Tp + t;
+                            rDz = fmaxf(rDz, fabsf(zn - *zp));
+                            *zp = zn;
+                        }
                     }
                 }
             }
@@ -846,7 +876,9 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
             }
         }
         if (!chk) {
+            ACB_TR(3);
             __syncthreads();
+            ACB_TR(4);
             if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;  // next read is after the next barrier
             continue;
         }
@@ -936,7 +968,7 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
         float violA = 3.0e38f, umaxA = -3.0e38f; double uqA = 0.0, plA = 0.0;
         if (haveAvg) eval_columns(false, THA, violA, umaxA, uqA, plA);
         // block reductions
-        rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm); rNan = warp_max(rNan);
+        rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm); rNan = warp_max(rNan); rDz = warp_max(rDz);
         violC = warp_max(violC); umaxC = warp_max(umaxC);
         violA = warp_max(violA); umaxA = warp_max(umaxA);
         dPc = warp_sum(dPc); dPa = warp_sum(dPa); dD = warp_sum(dD); uqC = warp_sum(uqC); uqA = warp_sum(uqA);
@@ -944,20 +976,20 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
         if (lane == 0) {
             float* rf = REDF + warp * ACB_NRED;
             rf[RF_E1] = rE1; rf[RF_E2] = rE2; rf[RF_XMAX] = rXm; rf[RF_ZMAX] = rZm; rf[RF_YMAX] = rYm; rf[RF_NAN] = rNan;
-            rf[RF_VIOLC] = violC; rf[RF_VIOLA] = violA; rf[RF_UMAXC] = umaxC; rf[RF_UMAXA] = umaxA;
+            rf[RF_VIOLC] = violC; rf[RF_VIOLA] = violA; rf[RF_UMAXC] = umaxC; rf[RF_UMAXA] = umaxA; rf[RF_DZ] = rDz;
             double* rd = REDD + warp * ACB_NRED;
             rd[RD_PC] = dPc; rd[RD_PA] = dPa; rd[RD_D] = dD; rd[RD_UQC] = uqC; rd[RD_UQA] = uqA; rd[RD_PLC] = plC; rd[RD_PLA] = plA;
         }
         __syncthreads();
         if (tid == 0) {
-            float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, nn = 0, vC = -1.f, vA = -1.f, uC = -3.0e38f, uA = -3.0e38f;
+            float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, nn = 0, vC = -1.f, vA = -1.f, uC = -3.0e38f, uA = -3.0e38f, dz = 0.f;
             double Pc = 0, Pa = 0, D = 0, qC = 0, qA = 0, lC = 0, lA = 0;
             for (int w = 0; w < nwarps; ++w) {
                 const float* rf = REDF + w * ACB_NRED;
                 e1 = fmaxf(e1, rf[RF_E1]); e2 = fmaxf(e2, rf[RF_E2]); xm = fmaxf(xm, rf[RF_XMAX]); zm = fmaxf(zm, rf[RF_ZMAX]);
                 ym = fmaxf(ym, rf[RF_YMAX]); nn = fmaxf(nn, rf[RF_NAN]); vC = fmaxf(vC, rf[RF_VIOLC]);
                 if (haveAvg) vA = fmaxf(vA, rf[RF_VIOLA]);
-                uC = fmaxf(uC, rf[RF_UMAXC]); uA = fmaxf(uA, rf[RF_UMAXA]);
+                uC = fmaxf(uC, rf[RF_UMAXC]); uA = fmaxf(uA, rf[RF_UMAXA]); dz = fmaxf(dz, rf[RF_DZ]);
                 const double* rd = REDD + w * ACB_NRED;
                 Pc += rd[RD_PC]; Pa += rd[RD_PA]; D += rd[RD_D]; qC += rd[RD_UQC]; qA += rd[RD_UQA]; lC += rd[RD_PLC]; lA += rd[RD_PLA];
             }
@@ -986,13 +1018,32 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
             float flag = 0.f;
             // a (slightly) negative gap is rounding noise around a converged pair and passes; negative tolerances
             // therefore mean "never stop on the gap" (run the whole iteration budget)
-            const bool okC = gapC <= tolC && vC <= opt.viol_tol;
-            const bool okA = haveAvg && gapA <= tolA && vA <= opt.viol_tol;
+            // rate polish: with a linearly converging iteration the movement dz over one check period and the ratio
+            // kap of two consecutive movements give the remaining distance dz kap / (1 - kap); the larger of the last
+            // two ratios is used, and the estimate only counts from the third check after a (re)start
+            bool okRate = true;
+            if (polish) {
+                const float dzp = SCAL[SC_DZ], nd = SCAL[SC_NDZ];
+                const float kap = (nd >= 1.f && dzp > 0.f) ? fminf(dz / dzp, 0.98f) : 0.98f;
+                const float ku = fmaxf(kap, SCAL[SC_KAP]);
+                const float est = (nd >= 2.f) ? dz * ku / (1.f - ku) : 3.0e38f;
+                SCAL[SC_RATE_EST] = est;
+                SCAL[SC_KAP] = (nd >= 1.f) ? kap : 0.f;
+                SCAL[SC_DZ] = dz;
+                SCAL[SC_NDZ] = nd + 1.f;
+                // (a movement at the float32 noise floor of the rates counts as converged whatever the ratio says)
+                okRate = est <= opt.rate_tol || (nd >= 2.f && dz <= 1e-5f);
+            }
+            const bool certC = gapC <= tolC && vC <= opt.viol_tol;  // gap and violation certified; the polish may still be running
+            const bool okC = certC && okRate;
+            const bool okA = haveAvg && !polish && gapA <= tolA && vA <= opt.viol_tol;
             if (nn > 0.f || !(Pc == Pc)) flag = 3.f;
             else if (Dbest > SCALD[SD_PMAX] + 1e-3 * (fabs(SCALD[SD_PMAX]) + 1.0)) flag = 6.f;  // infeasibility certificate
             else if (okC && (!okA || gapC <= gapA)) flag = 1.f;
             else if (okA) flag = 4.f;
-            else {
+            else if (certC) {
+                // only the rate polish is pending: no restarts, rescues or penalty changes (each would reset its history)
+            } else {
                 if (haveAvg && gapA <= 0.5 * SCALD[SD_GAPRESTART] && vA <= fmaxf(vC, opt.viol_tol) + 1e-3f) {
                     SCALD[SD_GAPRESTART] = gapA;
                     flag = 5.f;
@@ -1029,6 +1080,7 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
                     }
                 }
             }
+            if (flag == 5.f || flag >= 10.f) SCAL[SC_NDZ] = 0.f;  // the iterate jumps: the movement history starts over
             SCAL[SC_FLAG] = flag;
             SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel;
             const bool useA = (flag == 4.f);
@@ -1041,7 +1093,8 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
         if (flag == 3.f) { status = ACB_NUMERICAL; break; }
         if (flag == 6.f) { status = ACB_INFEASIBLE; break; }
         if (flag == 2.f) break;  // status stays ACB_MAX_ITER
-        const bool toAvg = (flag == 4.f) || (flag == 5.f) || (flag == 15.f);
+        // (not on the last iteration: the returned schedule and its reported gap / violation must be the current candidate's)
+        const bool toAvg = (flag == 4.f) || ((flag == 5.f || flag == 15.f) && it < opt.max_iter);
         if (toAvg) {
             // adopt the averaged state: v <- mean v, multipliers of its projection, mean coupling v
             if (rowWarp) {
@@ -1137,6 +1190,29 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
         __syncthreads();
     }
     if (it > opt.max_iter) it = opt.max_iter;
+    if (parked) {
+        // park the complete state; PART / VOUT / MFT are rebuilt from it on resume, the running sums stay in B.work
+        --it;
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            const int row = rowWarp ? SLOT[(warp * TPW + k) * 6] : -1;
+            if (row < 0) continue;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) P.st_v1[((size_t)b * N + row) * Tp + lane + 32 * q] = v1[k][q];
+        }
+        for (int i = tid; i < R * Tp; i += nthreads) P.st_vc[(size_t)b * R * Tp + i] = VC[i];
+        for (int i = tid; i < B.S_max; i += nthreads) P.st_mu[(size_t)b * B.S_max + i] = SESS_MU[i];
+        float* stp = P.st_scal + (size_t)b * ACB_NSTATE;
+        if (tid < 32) stp[tid] = SCAL[tid];
+        else if (tid < 64) stp[tid] = sm[L.SCALD + tid - 32];
+        if (tid == 0) {
+            B.status[b] = ACB_RUNNING;
+            B.iters[b] = it;
+            float* st = B.stats + (size_t)b * ACB_NSTATS;  // the scheduler between the launches ranks by the gap of the last check
+            st[2] = SCAL[SC_GAP]; st[3] = SCAL[SC_VIOL];
+        }
+        return;
+    }
 
     // ------------------------------------------------------------------ epilogue
     __syncthreads();  // SC_USEDAVG (written by thread 0 just before leaving the loop) must be visible
@@ -1153,7 +1229,15 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
                 float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
-                B.rates[((size_t)b * N + row) * Tp + t] = z * THX[t];
+                const float rt = z * THX[t];
+                B.rates[((size_t)b * N + row) * Tp + t] = rt;
+                // fused project_into_continuous_feasible_pilots (postprocessing.py:77-94) + the final max(., 0) of schedule()
+                if (B.pilots) {  // same selects as k_project_continuous (acb_post.cu)
+                    double pv = (double)rt;
+                    const double mp = S.max_pilot[row];
+                    pv = (mp < pv) ? mp : pv;
+                    B.pilots[((size_t)b * N + row) * Tp + t] = (pv > 0.0) ? pv : 0.0;
+                }
                 if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
             }
         }
@@ -1162,6 +1246,7 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
     if (B.out_mu) for (int i = tid; i < B.S_max; i += nthreads) B.out_mu[(size_t)b * B.S_max + i] = SESS_MU[i];
     if (tid == 0) {
         if (B.out_scal) { B.out_scal[b * 2] = (SCAL[SC_NRESCUE] > 0.f) ? rho_start : rho; B.out_scal[b * 2 + 1] = SCAL[SC_PLEVEL]; }
+        if (B.rate_est) B.rate_est[b] = SCAL[SC_RATE_EST];
         B.status[b] = status;
         B.iters[b] = it;
         float* st = B.stats + (size_t)b * ACB_NSTATS;
@@ -1172,30 +1257,21 @@ __global__ void __launch_bounds__(COMPACT ? 384 : 768, COMPACT ? 2 : 1) acb_solv
 
 
 // explicit launch helper used by the per-horizon translation units
-template <int Q, int TPW, bool MULTI, int NCH, bool COMPACT = false>
-int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads, size_t smem, cudaStream_t st) {
-    auto kern = acb_solve_kernel<Q, TPW, MULTI, NCH, COMPACT>;
+template <int Q, int TPW, bool MULTI, int NCH>
+int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_options* opt, const SolvePhase* ph, int nthreads, size_t smem, cudaStream_t st) {
+    auto kern = acb_solve_kernel<Q, TPW, MULTI, NCH>;
     ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (COMPACT)  // two blocks per SM need the large shared-memory carve-out
-        ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    const SiteDev& d = COMPACT ? site->d6 : site->d;
-    SmemLayout L = make_layout(d.N, d.R, d.NG, d.NP, d.nSlots, 32 * Q, batch->S_max, nthreads / 32, COMPACT);
-    kern<<<batch->B, nthreads, smem, st>>>(d, *batch, *opt, L);
+    const SiteDev& d = site->d;
+    SmemLayout L = make_layout(d.N, d.R, d.NG, d.NP, d.nSlots, 32 * Q, batch->S_max, nthreads / 32);
+    kern<<<batch->B, nthreads, smem, st>>>(d, *batch, *opt, L, *ph);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }
 #define ACB_INSTANTIATE_Q(QQ)                                                                                              \
-    int acb_launch_solve_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads,         \
-                               size_t smem, cudaStream_t st, bool multi, int nch) {                                        \
-        if (!multi && nch == 1) return acb_launch_solve_t<QQ, 3, false, 1>(site, batch, opt, nthreads, smem, st);           \
-        if (!multi && nch == 3) return acb_launch_solve_t<QQ, 3, false, 3>(site, batch, opt, nthreads, smem, st);           \
-        if (multi && nch == 1) return acb_launch_solve_t<QQ, 3, true, 1>(site, batch, opt, nthreads, smem, st);             \
-        return acb_launch_solve_t<QQ, 3, true, 3>(site, batch, opt, nthreads, smem, st);                                    \
-    }
-// compact-bounds kernel (experimental, acb_options.path = 3): 6 rows per warp, 384 threads, two blocks per SM
-#define ACB_INSTANTIATE_COMPACT_Q(QQ)                                                                                      \
-    int acb_launch_solve_compact_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, int nthreads, \
-                                       size_t smem, cudaStream_t st, int nch) {                                            \
-        if (nch == 1) return acb_launch_solve_t<QQ, 6, false, 1, true>(site, batch, opt, nthreads, smem, st);               \
-        return acb_launch_solve_t<QQ, 6, false, 3, true>(site, batch, opt, nthreads, smem, st);                             \
+    int acb_launch_solve_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, const SolvePhase* ph, \
+                               int nthreads, size_t smem, cudaStream_t st, bool multi, int nch) {                          \
+        if (!multi && nch == 1) return acb_launch_solve_t<QQ, 3, false, 1>(site, batch, opt, ph, nthreads, smem, st);       \
+        if (!multi && nch == 3) return acb_launch_solve_t<QQ, 3, false, 3>(site, batch, opt, ph, nthreads, smem, st);       \
+        if (multi && nch == 1) return acb_launch_solve_t<QQ, 3, true, 1>(site, batch, opt, ph, nthreads, smem, st);         \
+        return acb_launch_solve_t<QQ, 3, true, 3>(site, batch, opt, ph, nthreads, smem, st);                                \
     }

@@ -182,7 +182,20 @@ def pack_sessions(sessions, infra, period) -> dict:
     return out
 
 
-SUPPORTED_HORIZONS = (64, 128, 160, 288)  # padded horizons the solve kernel is instantiated for
+SUPPORTED_HORIZONS = (64, 128, 160, 288)  # padded horizons the on-chip solve kernel is instantiated for
+MAX_HORIZON = 3616  # longest padded horizon of the general (streaming) path: rows are staged in shared memory
+
+
+def padded_horizon(T: int) -> int:
+    """Smallest padded horizon that can hold T periods: one of the on-chip kernel's, else the next multiple of 32
+    (solved by the general path; reference aco.py:243-245 puts no limit on T)."""
+    for t in SUPPORTED_HORIZONS:
+        if t >= T:
+            return t
+    Tp = ((int(T) + 31) // 32) * 32
+    if Tp > MAX_HORIZON:
+        raise ValueError(f"horizon {T} exceeds the longest supported horizon {MAX_HORIZON} periods")
+    return Tp
 
 
 class PackedBatch:
@@ -194,10 +207,7 @@ class PackedBatch:
         B = len(instances)
         Tmax = max(i.T for i in instances)
         if Tp is None:
-            fits = [t for t in SUPPORTED_HORIZONS if t >= Tmax]
-            if not fits:
-                raise ValueError(f"horizon {Tmax} exceeds the largest on-chip horizon {SUPPORTED_HORIZONS[-1]}")
-            Tp = fits[0]
+            Tp = padded_horizon(Tmax)
         self.Tp = Tp
         self.S_max = S_max or max(4, max(len(i.sess_row) for i in instances))
         self.B = B
@@ -259,8 +269,8 @@ class PackedBatch:
         by name; `T`, `n_sessions`, `sess_*`, `min_rates`, `max_rates`, `alpha`, `beta`, `qd`,
         `gamma`, `peak_w`, `peak_p0` required, `ext` / `peak_limit` optional).  Used by callers
         that keep their sessions in arrays (replay_fast) instead of SessionInfo objects."""
-        if Tp not in SUPPORTED_HORIZONS:
-            raise ValueError(f"Tp must be one of {SUPPORTED_HORIZONS}")
+        if Tp % 32 != 0 or Tp <= 0 or Tp > MAX_HORIZON:
+            raise ValueError(f"Tp must be a positive multiple of 32, at most {MAX_HORIZON}")
         self = cls.__new__(cls)
         self.site, self.Tp, self.S_max, self.B = site, Tp, S_max, int(host["T"].shape[0])
         self.multi_session = bool(multi_session)
@@ -282,6 +292,11 @@ class PackedBatch:
         self.iters = torch.empty((B,), dtype=torch.int32, device=dev)
         self.stats = torch.empty((B, _cabi.ACB_NSTATS), dtype=torch.float32, device=dev)
         self.work = torch.empty((B, N + max(R, 1), Tp_), dtype=torch.float32, device=dev)
+        self.pilots = None    # set by want_pilots(): float64 continuous-feasible pilots written by the solve's epilogue
+        self.rate_est = None
+        # the rate polish needs a strictly convex objective: without a quadratic term the library is told not to
+        # allocate its previous-schedule scratch
+        self.any_quadratic = bool(np.any(np.asarray(h["qd"]) > 0))
         self.warm = None
         self.warm_out = None
         if want_warm_out:
@@ -304,6 +319,7 @@ class PackedBatch:
             if dst.shape != v.shape or dst.dtype != v.dtype:
                 raise ValueError(f"refill: field {k} changed shape or dtype ({dst.shape} {dst.dtype} -> {v.shape} {v.dtype})")
             dst[...] = v
+        self.any_quadratic = bool(np.any(np.asarray(h["qd"]) > 0))
         return self
 
     def upload(self):
@@ -328,13 +344,25 @@ class PackedBatch:
         s.out_v1, s.out_vc, s.out_mu, s.out_scal = (_ptr(o.get(k)) for k in ("v1", "vc", "mu", "scal"))
         s.work = _ptr(self.work)
         s.rates, s.status, s.iters, s.stats = _ptr(self.rates), _ptr(self.status), _ptr(self.iters), _ptr(self.stats)
+        s.pilots, s.rate_est = _ptr(self.pilots), _ptr(self.rate_est)
         return s
+
+    def want_pilots(self):
+        """Have the solve also write max(min(rates, max_pilot), 0) in float64 (project_into_continuous_feasible_pilots
+        fused into the solve's epilogue) into `self.pilots` [B, N, Tp]."""
+        if self.pilots is None:
+            self.pilots = torch.empty((self.B, self.site.N, self.Tp), dtype=torch.float64, device=self.device)
+        return self
 
     def solve(self, options: Optional[Options] = None):
         """Enqueue the batched solve on the current stream (asynchronous)."""
         if not self.dev:
             self.upload()
         opt = options or _cabi.default_options()
+        if not self.any_quadratic and opt.rate_tol > 0:
+            opt = _cabi.copy_options(opt, rate_tol=0.0)
+        elif self.any_quadratic and opt.rate_tol > 0 and self.rate_est is None:
+            self.rate_est = torch.full((self.B,), -1.0, dtype=torch.float32, device=self.device)
         _cabi.check(
             _cabi.lib().acb_solve_batch(self.site.handle, C.byref(self._fill_struct()), C.byref(opt), _stream_ptr(self.site.device)),
             "acb_solve_batch",
@@ -364,8 +392,7 @@ class HostPipeline:
         B = len(instances)
         chunks = max(1, min(chunks, B))
         if Tp is None:
-            Tmax = max(i.T for i in instances)
-            Tp = [t for t in SUPPORTED_HORIZONS if t >= Tmax][0]
+            Tp = padded_horizon(max(i.T for i in instances))
         S_max = max(4, max(len(i.sess_row) for i in instances))
         bounds = [round(k * B / chunks) for k in range(chunks + 1)]
         self.parts = [PackedBatch(site, instances[a:b], Tp=Tp, S_max=S_max) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]

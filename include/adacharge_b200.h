@@ -86,8 +86,7 @@ typedef struct acb_options {
     int32_t avg_every;   /* state is added to the average every avg_every iterations */
     int32_t stall_checks; /* change rho when the best gap has not improved by 10 % over this many checks (0 = never) */
     int32_t max_rescues;  /* at most this many stagnation rescues (1st: rho x3; 2nd, warm-started solves only: restart cold) */
-    int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only;
-                          * 3 = experimental compact-bounds on-chip kernel (constant limits, one session per EVSE, Tp 128/288) */
+    int32_t path;        /* 0 = on-chip kernel when the instance fits, else the general path; 1 = on-chip only; 2 = general only */
     int32_t stall_exit;  /* with all rescues used: stop (ACB_MAX_ITER, stats[2] = certified gap) after this many checks without a 10 % better gap; 0 = never */
     int32_t dual_refine; /* dual bound uses the best energy-row multipliers given y: 0 = never, 1 = when the gap stalled at the last check, 2 = at every check */
     float term_floor;    /* the gap tolerance is eps_abs + eps_rel * max(|P|, |D|, term_floor * sum of |objective terms|); default 0.05.
@@ -95,6 +94,14 @@ typedef struct acb_options {
                           * that can cancel the energy term), 0 = relative to |P| alone */
     float rho_curv;      /* cold start: rho = max(rho0, rho_curv * Gamma * s_u^2), the curvature of the aggregate quadratic seen
                           * through the scaled aggregate-power row (default 1; 0 = plain rho0) */
+    float rate_tol;      /* rate polish (on-chip path): when the objective is strictly convex in the rates (equal_share with a
+                          * cost-scaled coefficient >= polish_min_qd) the optimum is unique and the solve additionally runs until
+                          * the estimated distance of the schedule to its limit point is <= rate_tol amperes (default 3e-4; 0 = off) */
+    float polish_min_qd; /* smallest cost-scaled quadratic coefficient for which the rate polish is applied (default 5e-4: the
+                          * reference's 1e-12 tie-breaker does not trigger it, a 1e-3 equal_share weight does) */
+    int32_t phase_iters; /* on-chip path, batches larger than one wave of SMs: first launch stops every instance after this many
+                          * iterations, parks the unfinished ones and relaunches them longest-expected-first (default 100;
+                          * 0 = one launch) */
 } acb_options;
 
 void acb_default_options(acb_options* o);
@@ -132,12 +139,64 @@ typedef struct acb_batch {
     float* out_v1; float* out_vc; float* out_mu; float* out_scal;
     /* results */
     float* rates;                /* [B][N][Tp] */
+    double* pilots;              /* optional [B][N][Tp]: max(min(rates, max_pilot), 0) in float64, i.e. the solve's epilogue also does
+                                  * project_into_continuous_feasible_pilots (postprocessing.py:77-94); on-chip path only, NULL = skip */
+    float* rate_est;             /* optional [B]: estimated distance (A) of the schedule to its limit point when the rate polish ran, else -1 */
     int32_t* status;             /* [B] */
     int32_t* iters;              /* [B] */
     float* stats;                /* [B][ACB_NSTATS] */
 } acb_batch;
 
 int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* opt, void* stream);
+
+/* ---- packing on the device: raw session tables + interface quantities -> the acb_batch input fields ----
+ * What the reference does on the host before every solve (T = max(arrival_offset + remaining_time) aco.py:243-245,
+ * energy rows aco.py:114-122, build_objective over the ObjectiveComponent list aco.py:200-218 with the objective
+ * library aco.py:363-408), for a whole batch, so that a caller only ships the raw arrays.  float64 inputs, the
+ * reference's order of operations, one rounding to float32: bit-identical to the host packer. */
+#define ACB_OBJ_QUICK_CHARGE 0
+#define ACB_OBJ_EQUAL_SHARE 1
+#define ACB_OBJ_TOU_ENERGY_COST 2
+#define ACB_OBJ_TOTAL_ENERGY 3
+#define ACB_OBJ_PEAK 4              /* only with a negative coefficient (concavity) */
+#define ACB_OBJ_DEMAND_CHARGE 5
+#define ACB_OBJ_LOAD_FLATTENING 6
+#define ACB_OBJ_NON_COMPLETION_L1 7 /* build-defined (absent from the reference): -sum_s |remaining_demand_s - E_s| */
+#define ACB_MAX_COMPONENTS 16
+
+typedef struct acb_sessions {      /* [B][S_max] tables, any order within an instance; station < 0 marks an empty slot */
+    int32_t B, S_max;
+    const int32_t* station;         /* EVSE index (InfrastructureInfo.get_station_index) */
+    const int32_t* arrival_offset;  /* SessionInfo.arrival_offset */
+    const int32_t* remaining_time;  /* SessionInfo.remaining_time */
+    const double* remaining_demand; /* SessionInfo.remaining_demand, kWh */
+    const double* min_rate;         /* constant per session (time-varying limits go through the host packer) */
+    const double* max_rate;
+} acb_sessions;
+
+typedef struct acb_objective {     /* the ObjectiveComponent list, in order: sum_c coef[c] * f_kind[c](rates) is maximised */
+    int32_t n;
+    int32_t kind[ACB_MAX_COMPONENTS];
+    double coef[ACB_MAX_COMPONENTS];
+    double param[ACB_MAX_COMPONENTS]; /* baseline_peak of peak / demand_charge components, else unused */
+    double period;                    /* interface.period, minutes */
+    const double* prices;             /* [B][prices_stride >= Tp] $/kWh, interface.get_prices; required by tou_energy_cost */
+    int32_t prices_stride;
+    const double* prev_peak;          /* [B] A, interface.get_prev_peak; NULL = 0 */
+    const double* demand_charge;      /* [B] $/kW, interface.get_demand_charge; NULL = demand_charge_scalar */
+    double demand_charge_scalar;
+    const double* external_signal;    /* [B][ext_stride >= Tp] kW for load_flattening; NULL = zeros */
+    int32_t ext_stride;
+    const double* peak_limit;         /* [B][pl_stride]: pl_stride 1 = scalar per instance, else per period; required iff use_peak_row */
+    int32_t pl_stride;
+} acb_objective;
+
+/* Fills batch->{T, n_sessions, sess_*, min_rates, max_rates ([B*S_max] each), alpha, beta, qd, gamma, ext, peak_w, peak_p0,
+ * peak_limit} (device buffers owned by the caller; B, Tp, S_max, multi_session set by the caller).  flags (device, one
+ * int32, zeroed by the caller) receives bit 0 if an EVSE holds two sessions although multi_session is 0, bit 1 if a
+ * session ends beyond Tp. */
+int acb_pack_sessions(acb_site* site, const acb_sessions* sessions, const acb_objective* objective, const acb_batch* batch,
+                      int32_t* flags, void* stream);
 
 /* lb/ub [B][N][Tp] from the session tables of a batch (only the session fields, B, Tp,
  * S_max, T and n_sessions are read). */

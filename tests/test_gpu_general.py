@@ -98,3 +98,39 @@ def test_config_c5_full_size_properties(require_gpu):
     for b, (iface, S, I) in enumerate(ifaces):
         v = mpc.violations(R[b][:, : insts[b].T], S, I, iface)
         assert v["lb"] <= 0 and v["ub"] <= 0 and v["energy"] <= 1e-4 and v["infrastructure_rel"] <= VIOL_TOL, v
+
+
+@pytest.mark.parametrize("case", ["single_phase_T576", "three_phase_T400"])
+def test_long_horizons_go_through_the_general_path(require_gpu, case):
+    """The reference takes any T = max(arrival_offset + remaining_time) (aco.py:243-245); horizons beyond the on-chip
+    kernel's 288 periods are solved by the general path with rows staged in shared memory (Tp = next multiple of 32)."""
+    from adacharge_b200.generators import session_generator, single_phase_single_constraint, three_phase_balanced_network
+    from adacharge_b200 import engine
+
+    rng = np.random.default_rng(5)
+    if case == "single_phase_T576":
+        n, T = 6, 576
+        infra = single_phase_single_constraint(n, 80)
+        spec = [("quick_charge", 1, {}), ("equal_share", 0.02, {})]
+    else:
+        n, T = 9, 400
+        infra = three_phase_balanced_network(3, 50)
+        spec = [("tou_energy_cost", 1, {}), ("total_energy", 0.3, {}), ("demand_charge", 0.02, {})]
+    arr = rng.integers(0, T // 3, size=n)
+    dep = np.minimum(arr + rng.integers(T // 3, T, size=n), T)
+    dep[0] = T
+    dem = rng.uniform(5, 40, size=n)
+    sessions = session_generator(n, arr.tolist(), dep.tolist(), dem.tolist(), dem.tolist(), [32] * n)
+    iface = ab.TestingInterface({"active_sessions": sessions, "infrastructure_info": infra, "current_time": 0, "period": 5,
+                                 "prices": (0.05 + 0.2 * rng.random(T)).tolist(), "demand_charge": 15.51, "prev_peak": 10.0})
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    assert mpc.horizon(S) == T and engine.padded_horizon(T) == ((T + 31) // 32) * 32
+    obj = [ab.ObjectiveComponent(getattr(ab, nme), c, k) for nme, c, k in spec]
+    aco = ab.AdaptiveChargingOptimization(obj, iface)
+    R = aco.solve(S, I, prev_peak=iface.get_prev_peak())
+    assert R.shape == (n, T)
+    Ro = mpc.solve_mpc(spec, S, I, iface, "SOC", False, None, iface.get_prev_peak())
+    f, fo = (mpc.evaluate_objective(X, spec, I, iface, S, iface.get_prev_peak()) for X in (R, Ro))
+    assert abs(f - fo) <= 1e-4 * abs(fo), (f, fo, aco.last_info)
+    v = mpc.violations(R, S, I, iface)
+    assert v["infrastructure_rel"] <= 1e-5 and v["lb"] <= 0 and v["ub"] <= 0 and v["energy"] <= 1e-4, v

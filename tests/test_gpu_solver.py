@@ -231,36 +231,3 @@ def _cabi_opts(**kw):
     from adacharge_b200 import _cabi
 
     return _cabi.default_options(**kw)
-
-
-@pytest.mark.parametrize("shape", ["c2_288", "c1_128"])
-def test_compact_bounds_kernel_matches_standard(require_gpu, shape):
-    """acb_options.path = 3 (experimental): the on-chip kernel without materialised bounds, two blocks per SM.
-    Same instances through both kernels: both certify 1e-4, so the objectives agree to 2e-4 of the term scale and
-    every schedule respects its bounds, energy caps and the network."""
-    obj_spec = [("tou_energy_cost", 1, {}), ("total_energy", 0.3, {}), ("demand_charge", 1 / 30, {})]
-    obj = _components(obj_spec)
-    insts, ctx = [], []
-    for seed in range(12):
-        d = config_c2(seed + 200, price_noise=0.2) if shape == "c2_288" else config_c1(seed + 200, n=30, T=120)
-        d.setdefault("prices", (0.05 + 0.2 * np.random.default_rng(seed).random(400)).tolist())
-        d.setdefault("demand_charge", 15.51)
-        iface = ab.TestingInterface(d)
-        S, I = iface.active_sessions(), iface.infrastructure_info()
-        aco = ab.AdaptiveChargingOptimization(obj, iface)
-        insts.append(aco.build_instance(S, I, None, iface.get_prev_peak()))
-        ctx.append((iface, S, I))
-    site = aco._site_for(I, insts[0])
-    std = engine.PackedBatch(site, insts).upload().solve(_cabi_opts())
-    cmp_ = engine.PackedBatch(site, insts).upload().solve(_cabi_opts(path=3))
-    assert std.Tp == (288 if shape == "c2_288" else 128)
-    assert (std.status.cpu().numpy() == 0).all() and (cmp_.status.cpu().numpy() == 0).all(), (cmp_.status.cpu().numpy(), cmp_.stats.cpu().numpy()[:, :4])
-    Ra, Rb = std.rates.cpu().numpy().astype(np.float64), cmp_.rates.cpu().numpy().astype(np.float64)
-    for b, (iface, S, I) in enumerate(ctx):
-        T = insts[b].T
-        fa, fb = (mpc.evaluate_objective(R[b][:, :T], obj_spec, I, iface, S, iface.get_prev_peak()) for R in (Ra, Rb))
-        mag = sum(abs(mpc.evaluate_objective(Ra[b][:, :T], [o], I, iface, S, iface.get_prev_peak())) for o in obj_spec)
-        assert abs(fa - fb) <= 2e-4 * max(abs(fa), 0.05 * mag), (b, fa, fb)
-        v = mpc.violations(Rb[b][:, :T], S, I, iface, "SOC", None)
-        assert v["lb"] <= 1e-5 and v["ub"] <= 1e-5 and v["energy"] <= 2e-4 and v["infrastructure_rel"] <= VIOL_TOL, (b, v)
-        assert (Rb[b][:, T:] == 0).all()

@@ -292,8 +292,17 @@ def test_options_struct_matches_header_order():
     body = hdr[hdr.index("typedef struct acb_batch {"):hdr.index("} acb_batch;")]
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = []
-    for decl in re.findall(r"(?:const\s+)?(?:int32_t|float)\s*\*?\s*([^;]+);", body):
+    for decl in re.findall(r"(?:const\s+)?(?:int32_t|float|double)\s*\*?\s*([^;]+);", body):
         names += [x.strip().lstrip("*").split()[-1].lstrip("*") for x in decl.split(",")]
     assert names == [n for n, _ in _cabi.Batch._fields_], (names, [n for n, _ in _cabi.Batch._fields_])
     d = _cabi.default_options()
     assert d.eps_rel == pytest.approx(1e-4) and d.check_every == 25 and d.term_floor == pytest.approx(0.05) and d.rho_curv == pytest.approx(1.0)
+    assert d.rate_tol == pytest.approx(3e-4) and d.polish_min_qd == pytest.approx(5e-4)
+    # the device packer's structs (acb_sessions, acb_objective) against the header as well
+    for cname, ctype in (("acb_sessions", _cabi.Sessions), ("acb_objective", _cabi.Objective)):
+        body = hdr[hdr.index("typedef struct %s {" % cname):hdr.index("} %s;" % cname)]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in re.findall(r"(?:const\s+)?(?:int32_t|float|double)\s*\*?\s*([^;]+);", body):
+            names += [re.sub(r"\[.*\]", "", x.strip().lstrip("*").split()[-1].lstrip("*")) for x in decl.split(",")]
+        assert names == [n for n, _ in ctype._fields_], (cname, names)

@@ -14,6 +14,6 @@ def run(**kw):
     it = pb.iters.cpu().numpy(); st = pb.status.cpu().numpy()
     print(f"{str(kw):70s} {e0.elapsed_time(e1):7.1f} ms  iters mean {it.mean():6.0f} p90 {np.percentile(it,90):6.0f} max {it.max():6d} unsolved {(st!=0).sum()}")
 run()
-for kw in (dict(alpha=1.8), dict(alpha=1.85), dict(alpha=1.9), dict(alpha=1.8, stall_checks=2), dict(alpha=1.85, stall_checks=2), dict(alpha=1.9, stall_checks=2),
-           dict(alpha=1.8, stall_checks=2, kappa=0.5), dict(alpha=1.8, rho0=0.05), dict(alpha=1.8, stall_checks=2, check_every=20)):
+variants = [eval(a) for a in sys.argv[1:]] or [dict(check_every=20), dict(check_every=30), dict(check_every=40), dict(check_every=50), dict(avg_every=10), dict(avg_every=3)]
+for kw in variants:
     run(**kw)
