@@ -182,7 +182,10 @@ class BatchedAdaptiveCharging:
         self.host_stats = torch.empty((self.B, _cabi.ACB_NSTATS), dtype=torch.float32).pin_memory()
         self.h2d_bytes = sum(c.h2d_bytes for c in self.chunks)
         self.d2h_bytes = sum(t.numel() * t.element_size() for t in (self.host_pilots, self.host_status, self.host_iters, self.host_T, self.host_stats))
-        self.kernel_launches_per_call = 0
+        # own kernels per call and chunk: the packer + the solve (three launches when phased: solve, relaunch list, solve;
+        # the general path launches per phase and is not counted here)
+        phased = self.options.phase_iters > 0 and self.options.phase_iters < self.options.max_iter
+        self.kernel_launches_per_call = len(self.chunks) * (1 + (3 if phased else 1))
 
     # ------------------------------------------------------------------------------------------------
     def _stage(self, ch: _Chunk, arrays: Dict[str, np.ndarray]):
@@ -206,8 +209,9 @@ class BatchedAdaptiveCharging:
             else:
                 d[...] = a[ch.lo:ch.hi]
 
-    def enqueue(self, ch: _Chunk, from_device_raw=False):
-        """H2D of the raw arrays (unless they are already on the device), pack, solve, D2H — on the chunk's stream."""
+    def enqueue(self, ch: _Chunk, from_device_raw=False, events=None):
+        """H2D of the raw arrays (unless they are already on the device), pack, solve, D2H — on the chunk's stream.
+        `events`: a list that receives a (start, end) pair of CUDA events around the solve launch(es)."""
         L = _cabi.lib()
         st = C.c_void_p(ch.stream.cuda_stream)
         with torch.cuda.stream(ch.stream):
@@ -216,7 +220,13 @@ class BatchedAdaptiveCharging:
                     ch.dev_raw[k].copy_(t, non_blocking=True)
             ch.flags.zero_()
             _cabi.check(L.acb_pack_sessions(self.site.handle, C.byref(ch.sessions), C.byref(ch.objective), C.byref(ch.batch), engine._ptr(ch.flags), st), "acb_pack_sessions")
+            if events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record(ch.stream)
             _cabi.check(L.acb_solve_batch(self.site.handle, C.byref(ch.batch), C.byref(self.options), st), "acb_solve_batch")
+            if events is not None:
+                ev[1].record(ch.stream)
+                events.append(ev)
             if not from_device_raw:
                 self.host_pilots[ch.lo:ch.hi].copy_(ch.pilots, non_blocking=True)
                 self.host_status[ch.lo:ch.hi].copy_(ch.status, non_blocking=True)
@@ -225,18 +235,47 @@ class BatchedAdaptiveCharging:
                 self.host_stats[ch.lo:ch.hi].copy_(ch.stats, non_blocking=True)
                 ch.flags_host.copy_(ch.flags, non_blocking=True)
 
-    def schedule_async(self, sessions: Dict[str, np.ndarray], prices=None, prev_peak=None, demand_charge=None, external_signal=None, peak_limit=None):
-        """Stage, copy, pack, solve and copy back, chunk by chunk; returns after everything is enqueued.  The current
-        stream waits for all chunks, so a synchronize of the current stream makes ``result()`` valid."""
+    def schedule_async(self, sessions: Dict[str, np.ndarray], prices=None, prev_peak=None, demand_charge=None, external_signal=None, peak_limit=None,
+                       independent=False, start_event=None):
+        """Stage, copy, pack, solve and copy back, chunk by chunk; returns after everything is enqueued.  By default the
+        chunk streams start after the current stream's earlier work and the current stream waits for all chunks, so a
+        synchronize of the current stream makes ``result()`` valid.  ``independent=True`` leaves the current stream out
+        (the chunks start after ``start_event`` if given): calls on different objects then overlap on the device
+        (double buffering); use ``wait()`` / ``join()`` before reading the result."""
+        self.wait()  # the pinned staging and the result buffers of the previous call on this object are reused
         arrays = dict(sessions)
         arrays.update(prices=prices, prev_peak=prev_peak, demand_charge=demand_charge, external_signal=external_signal, peak_limit=peak_limit)
         cur = torch.cuda.current_stream(self.device)
         for ch in self.chunks:
             self._stage(ch, arrays)
-            ch.stream.wait_stream(cur)
+            if start_event is not None:
+                ch.stream.wait_event(start_event)
+            elif not independent:
+                ch.stream.wait_stream(cur)
             self.enqueue(ch)
+        self._finish(cur, independent)
+        return self
+
+    def _finish(self, cur, independent):
+        self._done = []
         for ch in self.chunks:
-            cur.wait_stream(ch.stream)
+            ev = torch.cuda.Event()
+            ev.record(ch.stream)
+            self._done.append(ev)
+            if not independent:
+                cur.wait_stream(ch.stream)
+
+    def wait(self):
+        """Block the host until the last call on this object has delivered its results."""
+        for ev in getattr(self, "_done", ()):
+            ev.synchronize()
+        return self
+
+    def join(self, stream=None):
+        """Make `stream` (default: the current one) wait for the last call on this object."""
+        st = stream or torch.cuda.current_stream(self.device)
+        for ev in getattr(self, "_done", ()):
+            st.wait_event(ev)
         return self
 
     def result(self, check=True) -> BatchResult:
@@ -267,13 +306,15 @@ class BatchedAdaptiveCharging:
         torch.cuda.synchronize(self.device)
         return self
 
-    def solve_resident(self):
+    def solve_resident(self, events=None, independent=False, start_event=None):
         cur = torch.cuda.current_stream(self.device)
         for ch in self.chunks:
-            ch.stream.wait_stream(cur)
-            self.enqueue(ch, from_device_raw=True)
-        for ch in self.chunks:
-            cur.wait_stream(ch.stream)
+            if start_event is not None:
+                ch.stream.wait_event(start_event)
+            elif not independent:
+                ch.stream.wait_stream(cur)
+            self.enqueue(ch, from_device_raw=True, events=events)
+        self._finish(cur, independent)
         return self
 
 

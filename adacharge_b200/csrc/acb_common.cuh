@@ -7,7 +7,7 @@
 #include "../../include/adacharge_b200.h"
 
 #define ACB_VERSION 100
-#define ACB_OPP 8          // outputs per column-pass work item
+#define ACB_OHT 12         // outputs per column-pass thread (one or two threads per period: at most 24 column inputs on chip)
 #define ACB_NRED 16        // floats per warp in the reduction scratch
 #define ACB_MAX_WARPS 32
 #define ACB_FIRST_CHECK 10  // iteration of the first convergence check (then every check_every)

@@ -28,10 +28,10 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
     }
 }
 
-int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
-int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
-int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
-int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
+int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
+int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
+int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
 
 // Between the launches of a phased solve: the parked (still running) instances, ordered by the relative gap of their
 // last convergence check, largest first (a counting sort over 256 logarithmic buckets; one block).  The gap after the
@@ -80,13 +80,13 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     const bool chipQ = (Q == 2 || Q == 4 || Q == 5 || Q == 9);  // horizons the on-chip kernel is instantiated for
     cudaStream_t st = (cudaStream_t)stream;
     const int NIN = d.NG + d.R;
-    const int nch = (NIN <= ACB_OPP) ? 1 : 3;
-    const int nParts = (NIN + ACB_OPP * nch - 1) / (ACB_OPP * nch);
+    const int nParts = (NIN + ACB_OHT - 1) / ACB_OHT;  // column-pass threads per period
     // threads: warps for the EVSE rows plus room for the coupling rows, and one column-pass sweep if possible
     int want = std::max(d.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp));
-    int nthreads = std::min(768, ((want + 31) / 32) * 32);
+    // (registers are allocated in groups of four warps: round up to a multiple of 128 threads, the extra warps take coupling work)
+    int nthreads = std::min(768, ((want + 127) / 128) * 128);
     size_t smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
-    const bool fits = chipQ && d.TPW == 3 && nCT_ <= 32 && nthreads <= 768 && d.nRowWarps * 32 <= nthreads && smem <= 232448;
+    const bool fits = chipQ && d.TPW == 3 && NIN <= 2 * ACB_OHT && nthreads <= 768 && d.nRowWarps * 32 <= nthreads && smem <= 232448;
     if (opt.path == 2 || (!fits && opt.path == 0)) return acb_solve_general(site, batch, opt, st);
     if (!fits) {
         acb_set_error("acb_solve_batch: instance does not fit the on-chip path (Tp in {64, 128, 160, 288}, N <= ~66 EVSEs, <= 32 coupling tasks, " +
@@ -95,10 +95,10 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     }
     const bool multi = batch->multi_session != 0;
     auto launch = [&](const SolvePhase& ph) -> int {
-        if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
-        if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
-        if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
-        return acb_launch_solve_q9(site, batch, &opt, &ph, nthreads, smem, st, multi, nch);
+        if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, &ph, nthreads, smem, st, multi);
+        if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, &ph, nthreads, smem, st, multi);
+        if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, &ph, nthreads, smem, st, multi);
+        return acb_launch_solve_q9(site, batch, &opt, &ph, nthreads, smem, st, multi);
     };
     // scratch from the stream-ordered pool: the schedule of the previous check (rate polish) and the parked state
     int nSM = 148;

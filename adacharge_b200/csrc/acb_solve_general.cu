@@ -331,7 +331,15 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                     else phi = fminf(lbq * rt, ubq * rt);
                     dsum += (double)phi;
                 }
-                if (MODE == 4) B.rates[base + 32 * q] = z;
+                if (MODE == 4) {
+                    B.rates[base + 32 * q] = z;
+                    if (B.pilots) {  // fused project_into_continuous_feasible_pilots, same selects as k_project_continuous
+                        double pv = (double)z;
+                        const double mp = S.max_pilot[row];
+                        pv = (mp < pv) ? mp : pv;
+                        B.pilots[base + 32 * q] = (pv > 0.0) ? pv : 0.0;
+                    }
+                }
                 if (MODE == 5) W.V[base + 32 * q] = z + rescale * (vq - z);
                 if (MODE == 4 && B.out_v1) B.out_v1[base + 32 * q] = vq;
             }

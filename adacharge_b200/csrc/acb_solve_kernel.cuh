@@ -61,7 +61,7 @@ __device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za
 
 // shared-memory layout (in floats), computed identically on host and device
 struct SmemLayout {
-    int LB, UB, PART, VC, VOUT, HG, THC, THA, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
+    int LB, UB, PART, VC, VOUT, GIN, HG, THC, THA, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
         SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
     int OP;  // padded output count of MFT
 };
@@ -69,7 +69,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
     SmemLayout L;
     int o = 0;
     auto take = [&](int n) { int p = o; o += (n + 3) & ~3; return p; };
-    L.OP = ((NG + R + 3 * ACB_OPP - 1) / (3 * ACB_OPP)) * (3 * ACB_OPP);  // multiple of 24: any NCH in {1,3} divides it
+    L.OP = ((NG + R + ACB_OHT - 1) / ACB_OHT) * ACB_OHT;  // one or two column-pass threads per period, ACB_OHT outputs each
     L.LB = take(N * Tp);
     L.UB = take(N * Tp);
     // PART doubles as scratch for Sinv (R*R) and X (R*NG) while the column matrix is rebuilt
@@ -77,6 +77,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
     L.PART = take(NP * Tp > scratch ? NP * Tp : scratch);
     L.VC = take(R * Tp);
     L.VOUT = take(R * Tp);
+    L.GIN = take(R * Tp);  // rho (2 z - v) of the coupling rows: written where v is updated, read by the column pass
     L.HG = take(NG * Tp);
     L.THC = take(Tp);  // per-period restoration factors of the current / averaged candidate
     L.THA = take(Tp);
@@ -143,7 +144,7 @@ __device__ long long g_acb_trace[ACB_TR_NIT * 32 * 8];
 #define ACB_TR(k) do { } while (0)
 #endif
 
-template <int Q, int TPW, bool MULTI, int NCH>
+template <int Q, int TPW, bool MULTI>
 __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L, const SolvePhase P) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     constexpr int Tp = 32 * Q;  // the host pads every batch to an instantiated horizon
     const int N = S.N, R = S.R, NG = S.NG, NP = S.NP;
     float* LB = sm + L.LB; float* UB = sm + L.UB; float* PART = sm + L.PART; float* VC = sm + L.VC;
-    float* VOUT = sm + L.VOUT; float* HG = sm + L.HG; float* THC = sm + L.THC; float* THA = sm + L.THA; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
+    float* VOUT = sm + L.VOUT; float* GIN = sm + L.GIN; float* HG = sm + L.HG; float* THC = sm + L.THC; float* THA = sm + L.THA; float* ALPHA = sm + L.ALPHA; float* BETA = sm + L.BETA;
     float* PLIM = sm + L.PLIM; float* EBAR = sm + L.EBAR; float* MFT = sm + L.MFT; float* CS = sm + L.CS;
     float* SINV = PART; float* XS = PART + R * R;
     int* SESS_A = (int*)(sm + L.SESS_A); int* SESS_B = (int*)(sm + L.SESS_B);
@@ -170,18 +171,18 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     const int rPL = 2 * nDisc + nLin, rU = rPL + S.has_pl;
     const int nCT = nDisc + nLin + S.has_pl + S.has_u;  // coupling tasks
     const float linLo = S.lin_two_sided ? -1.f : -3.0e38f;  // lower end of a linear row as a multiple of its limit
-    // coupling tasks run on the warps that own no EVSE rows (if any); the aggregate-power task,
-    // which carries the peak-level root find, gets a warp of its own when two or more are free
-    unsigned myTasks = 0;  // bit c set <=> this warp runs coupling task c (nCT <= 32 on this path)
+    // coupling rows run on the warps that own no EVSE rows (if any): the disc / linear / peak-limit tasks are cut into
+    // 32-period chunks and dealt round-robin to those warps; the aggregate-power row, which carries the peak-level
+    // root find over the whole horizon, gets the last warp (to itself when two or more warps are free)
+    const int nCT1 = nDisc + nLin + S.has_pl;
+    int cwIdx = -1, nCW = 1;
+    bool doAgg = false;
     {
         const int nFree = nwarps - S.nRowWarps;
-        for (int c = 0; c < nCT; ++c) {
-            int w;
-            if (nFree <= 0) w = nwarps - 1 - (c % nwarps);
-            else if (S.has_u && nFree >= 2) w = (c == nCT - 1) ? nwarps - 1 : S.nRowWarps + (c % (nFree - 1));
-            else w = S.nRowWarps + (c % nFree);
-            if (w == warp) myTasks |= 1u << c;
-        }
+        if (nFree <= 0) { cwIdx = warp; nCW = nwarps; }
+        else if (S.has_u && nFree >= 2) { nCW = nFree - 1; if (warp >= S.nRowWarps && warp < nwarps - 1) cwIdx = warp - S.nRowWarps; }
+        else { nCW = nFree; if (warp >= S.nRowWarps) cwIdx = warp - S.nRowWarps; }
+        doAgg = S.has_u && warp == nwarps - 1;
     }
     float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
     const bool useAvg = opt.restart && VSUM != nullptr;
@@ -610,6 +611,28 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             }
         }
     };
+    // GIN <- rho (2 z(v) - v) for every coupling row from the stored v (start, restart, penalty change)
+    auto write_gin = [&]() {
+        const float pl = SCAL[SC_PLEVEL];
+        for (int t = tid; t < Tp; t += nthreads) {
+            int r = 0;
+            for (int j = 0; j < nDisc; ++j, r += 2) {
+                float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
+                proj_disc(a, bb, LIM[r], za, zb);
+                GIN[r * Tp + t] = rho * (2.f * za - a); GIN[(r + 1) * Tp + t] = rho * (2.f * zb - bb);
+            }
+            for (int j = 0; j < nLin; ++j, ++r) {
+                float v = VC[r * Tp + t], z = clampf(v, (linLo < -1.0e30f) ? linLo : linLo * LIM[r], LIM[r]);
+                GIN[r * Tp + t] = rho * (2.f * z - v);
+            }
+            if (S.has_pl) { float v = VC[r * Tp + t], z = fminf(v, PLIM[t]); GIN[r * Tp + t] = rho * (2.f * z - v); ++r; }
+            if (S.has_u) {
+                float v = VC[r * Tp + t], a = agg_a(v, t);
+                float z = ((pk_w > 0.f) ? fminf(a, pl) : a) / su;
+                GIN[r * Tp + t] = rho * (2.f * z - v);
+            }
+        }
+    };
     // column evaluation of a candidate whose group partial sums are in PART: relative coupling
     // violation, max and quadratic part of the aggregate power; optionally HG <- C' yc (yc in VOUT)
     auto eval_columns = [&](bool with_hy, float* TH, float& viol, float& umax, double& uq, double& plin) {
@@ -668,30 +691,33 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     } else zero_sums();
     build_matrix();
     write_part_q();
+    write_gin();
     __syncthreads();
+    const bool fastRows = !MULTI && SCAL[SC_LBPOS] == 0.f;  // every minimum rate is 0: the hot row pass needs no lower bounds
 
     int it = 0, status = ACB_MAX_ITER;
     bool parked = false;
-    const int nParts = (NIN + ACB_OPP * NCH - 1) / (ACB_OPP * NCH);
+    const int nParts = (NIN + ACB_OHT - 1) / ACB_OHT;
     const int avgEvery = max(1, opt.avg_every);
     for (it = it0 + 1; it <= opt.max_iter; ++it) {
         if (it > P.it_stop) { parked = true; break; }
         const float plevel = SCAL[SC_PLEVEL];
         ACB_TR(0);
         // ------------------------------------------------------------ column pass
-        // work item = (period t, block of 8*NCH outputs); with NIN <= 8*NCH one thread owns a
-        // whole column and nothing is loaded twice
+        // work item = (period t, block of ACB_OHT outputs): one or two threads per period.  Inputs of a period: the NG
+        // group sums of q = 2z - v (summed here from the row warps' partial rows) and the R coupling inputs
+        // rho (2z - v), which the coupling warps left in GIN when they updated v.
         for (int wk = tid; wk < nParts * Tp; wk += nthreads) {
             const int part = wk / Tp, t = wk - part * Tp;
-            const int obase = part * (ACB_OPP * NCH);
-            float out[ACB_OPP * NCH];
+            const int obase = part * ACB_OHT;
+            float out[ACB_OHT];
 #pragma unroll
-            for (int k = 0; k < ACB_OPP * NCH; ++k) out[k] = 0.f;
+            for (int k = 0; k < ACB_OHT; ++k) out[k] = 0.f;
             const float al = ALPHA[t], be = BETA[t];
             auto accum = [&](int c, float in) {
                 const float4* mrow = reinterpret_cast<const float4*>(MFT + c * OP + obase);
 #pragma unroll
-                for (int h = 0; h < 2 * NCH; ++h) {
+                for (int h = 0; h < ACB_OHT / 4; ++h) {
                     const float4 m = mrow[h];
                     out[4 * h + 0] += m.x * in; out[4 * h + 1] += m.y * in; out[4 * h + 2] += m.z * in; out[4 * h + 3] += m.w * in;
                 }
@@ -699,34 +725,16 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             for (int g = 0; g < NG; ++g) {
                 float acc = 0.f;
                 const int p1 = PGOFF[g + 1];
+#pragma unroll 4
                 for (int p = PGOFF[g]; p < p1; ++p) acc += PART[p * Tp + t];
                 accum(g, rho1 * acc - NGRP[g] * (al + KG[g] * be));
             }
-            int r = 0;
-            for (int j = 0; j < nDisc; ++j, r += 2) {
-                float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
-                proj_disc(a, bb, LIM[r], za, zb);
-                accum(NG + r, rho * (2.f * za - a));
-                accum(NG + r + 1, rho * (2.f * zb - bb));
-            }
-            for (int j = 0; j < nLin; ++j, ++r) {
-                float v = VC[r * Tp + t], z = clampf(v, (linLo < -1.0e30f) ? linLo : linLo * LIM[r], LIM[r]);
-                accum(NG + r, rho * (2.f * z - v));
-            }
-            if (S.has_pl) {
-                float v = VC[r * Tp + t], z = fminf(v, PLIM[t]);
-                accum(NG + r, rho * (2.f * z - v));
-                ++r;
-            }
-            if (S.has_u) {
-                float v = VC[r * Tp + t], a = agg_a(v, t);
-                float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
-                accum(NG + r, rho * (2.f * z - v));
-                ++r;
-            }
+            const float* gin = GIN + t;
+#pragma unroll 4
+            for (int r = 0; r < R; ++r) accum(NG + r, gin[r * Tp]);
             const float inv_rho = 1.f / rho;
 #pragma unroll
-            for (int k = 0; k < ACB_OPP * NCH; ++k) {
+            for (int k = 0; k < ACB_OHT; ++k) {
                 int o = obase + k;
                 if (o < NG) HG[o * Tp + t] = out[k] - (al + KG[o] * be);
                 else if (o < NIN) VOUT[(o - NG) * Tp + t] = out[k] * inv_rho;
@@ -799,80 +807,207 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 }
             }
         };
+        // Hot row pass when every minimum rate is 0 and rows hold one session: the warp's TPW rows advance together, so
+        // the three multiplier searches (warp reductions, scalar Newton steps) overlap instead of queueing, and the
+        // evaluation that confirms a Newton step is the pass that also produces z and the partial sums.
+        auto row_pass_fast = [&]() {
+            const bool eq = opt.equality != 0;
+            float mu[TPW], Eb[TPW], lo[TPW], hi[TPW], E[TPW];
+            int nf[TPW], rowk[TPW];
+            bool open[TPW];
+            // pass 1: x, over-relaxed v, and the energy of the row at its warm multiplier
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                const int* sl = SLOT + (warp * TPW + k) * 6;
+                const int row = sl[0];
+                rowk[k] = row; E[k] = 0.f; nf[k] = 0; open[k] = false; mu[k] = 0.f; Eb[k] = 0.f; lo[k] = -1.f; hi[k] = 3.0e38f;
+                if (row < 0) continue;
+                const int g = sl[1], sf = sl[4], scn = sl[5];
+                const float mu0 = scn ? SESS_MU[sf] : 0.f;
+                mu[k] = eq ? mu0 : fmaxf(mu0, 0.f);
+                Eb[k] = scn ? SESS_E[sf] : 0.f;
+                open[k] = scn != 0;
+                if (eq) lo[k] = -3.0e38f;
+                const float* hgp = HG + g * Tp + lane;
+                const float* ubp = UB + row * Tp + lane;
+                float e = 0.f;
+                int n = 0;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float ub = ubp[32 * q], vo = v1[k][q];
+                    const float z = fminf(fmaxf(vo - mu0, 0.f), ub);
+                    const float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
+                    const float vn = vo + alpha * (x - z);
+                    v1[k][q] = vn;
+                    if (doAvg) atomicAdd(VSUM + (size_t)row * Tp + lane + 32 * q, vn);  // result unused -> RED
+                    const float w = vn - mu[k];
+                    e += fminf(fmaxf(w, 0.f), ub);
+                    n += (w > 0.f && w < ub) ? 1 : 0;
+                }
+                E[k] = e; nf[k] = n;
+            }
+            // one safeguarded Newton step per open row (same rule as newton_mu); a row that closes keeps its multiplier
+            auto nstep = [&](int k, int round) {
+                const float rr = E[k] - Eb[k];
+                if (fabsf(rr) <= 2e-6f * (Eb[k] + 1.f) || round >= 15) { open[k] = false; return; }
+                if (!eq && mu[k] <= 0.f && rr < 0.f) { mu[k] = 0.f; open[k] = false; return; }
+                if (rr > 0.f) lo[k] = mu[k]; else hi[k] = mu[k];
+                float mun = (nf[k] > 0) ? mu[k] + rr / (float)nf[k] : (rr > 0.f ? 3.0e38f : -3.0e38f);
+                if (!eq) mun = fmaxf(mun, 0.f);
+                if (!(mun > lo[k] && mun < hi[k])) {
+                    if (hi[k] < 1.0e38f && lo[k] > -1.0e38f) mun = 0.5f * (fmaxf(lo[k], eq ? lo[k] : 0.f) + hi[k]);
+                    else if (rr > 0.f) mun = mu[k] + fmaxf(1.f, 2.f * fabsf(mu[k]));
+                    else mun = mu[k] - fmaxf(1.f, 2.f * fabsf(mu[k]));
+                    if (!eq) mun = fmaxf(mun, 0.f);
+                }
+                mu[k] = mun;
+            };
+            auto reduce_all = [&]() {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < TPW; ++k) E[k] += __shfl_xor_sync(0xffffffffu, E[k], o);
+                }
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) nf[k] = __reduce_add_sync(0xffffffffu, nf[k]);
+            };
+            reduce_all();
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) if (open[k]) nstep(k, 0);
+            // pass 2: z and the partial sums of 2z - v with the current multipliers; rows still open are re-evaluated on
+            // the way and the pass repeats only if one of them has to move its multiplier again
+            for (int round = 1; ; ++round) {
+                float acc[Q];
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    const int row = rowk[k];
+                    if (row < 0) continue;
+                    const int* sl = SLOT + (warp * TPW + k) * 6;
+                    const bool first = sl[3] != 0;
+                    const float* ubp = UB + row * Tp + lane;
+                    float e = 0.f;
+                    int n = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float ub = ubp[32 * q], vn = v1[k][q];
+                        const float w = vn - mu[k];
+                        const float zn = fminf(fmaxf(w, 0.f), ub);
+                        const float val = 2.f * zn - vn;
+                        acc[q] = first ? val : acc[q] + val;
+                        e += zn;
+                        n += (w > 0.f && w < ub) ? 1 : 0;
+                    }
+                    E[k] = e; nf[k] = n;
+                    const bool last = (k == TPW - 1) || rowk[k + 1 < TPW ? k + 1 : k] < 0 || SLOT[(warp * TPW + k + 1) * 6 + 3] != 0;
+                    if (last) {
+                        float* pp = PART + sl[2] * Tp + lane;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) pp[32 * q] = acc[q];
+                    }
+                }
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) any |= open[k];
+                if (!any) break;
+                reduce_all();
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) if (open[k]) nstep(k, round);
+                any = false;
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) any |= open[k];
+                if (!any) break;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    const int* sl = SLOT + (warp * TPW + k) * 6;
+                    if (rowk[k] >= 0 && sl[5]) SESS_MU[sl[4]] = mu[k];
+                }
+            }
+        };
         if (rowWarp) {
-            if (chk) row_pass(std::true_type{}); else row_pass(std::false_type{});
+            if (chk) row_pass(std::true_type{});
+            else if (fastRows) row_pass_fast();
+            else row_pass(std::false_type{});
         }
         // ---------------------------------------------------------- coupling rows
-        // v update; on check iterations VOUT <- y = rho (v - z) and the conjugate terms of D
-        for (unsigned rem = myTasks; rem; rem &= rem - 1) {
-            const int c = __ffs(rem) - 1;
-            if (c < nDisc) {
-                const int r = 2 * c;
-                const float lim = LIM[r];
-                for (int t = lane; t < Tp; t += 32) {
+        // v update and GIN <- rho (2 z(v) - v) for the next column pass; on check iterations VOUT <- y = rho (v - z)
+        // and the conjugate terms of D.  Work item = (task, 32-period chunk), dealt round-robin to the coupling warps.
+        if (cwIdx >= 0) {
+            for (int item = cwIdx; item < nCT1 * Q; item += nCW) {
+                const int c = item / Q, t = (item - c * Q) * 32 + lane;
+                if (c < nDisc) {
+                    const int r = 2 * c;
+                    const float lim = LIM[r];
                     float a = VC[r * Tp + t], bb = VC[(r + 1) * Tp + t], za, zb;
                     proj_disc(a, bb, lim, za, zb);
                     float ka = VOUT[r * Tp + t], kb = VOUT[(r + 1) * Tp + t];
                     float an = a + alpha * (ka - za), bn = bb + alpha * (kb - zb);
                     VC[r * Tp + t] = an; VC[(r + 1) * Tp + t] = bn;
+                    float zan, zbn;
+                    proj_disc(an, bn, lim, zan, zbn);
+                    GIN[r * Tp + t] = rho * (2.f * zan - an); GIN[(r + 1) * Tp + t] = rho * (2.f * zbn - bn);
                     if (doAvg) {
                         float* vs = VSUM + (size_t)(N + r) * Tp + t;
                         atomicAdd(vs, an); atomicAdd(vs + Tp, bn);
                     }
                     if (chk) {
-                        float zan, zbn;
-                        proj_disc(an, bn, lim, zan, zbn);
                         float ya = rho * (an - zan), yb = rho * (bn - zbn);
                         VOUT[r * Tp + t] = ya; VOUT[(r + 1) * Tp + t] = yb;
                         dD -= (double)(lim * sqrtf(ya * ya + yb * yb));  // support function of the disc
                     }
-                }
-            } else if (c < nDisc + nLin + S.has_pl) {
-                const int r = 2 * nDisc + (c - nDisc);
-                const bool isPL = (c == nDisc + nLin);
-                const float lo = isPL ? -3.0e38f : linLo;
-                for (int t = lane; t < Tp; t += 32) {
+                } else {
+                    const int r = 2 * nDisc + (c - nDisc);
+                    const bool isPL = (c == nDisc + nLin);
+                    const float lo = isPL ? -3.0e38f : linLo;
                     float cap = isPL ? PLIM[t] : LIM[r];
                     float capLo = (lo < -1.0e30f) ? lo : lo * cap;
                     float v = VC[r * Tp + t], z = clampf(v, capLo, cap), kx = VOUT[r * Tp + t];
                     float vn = v + alpha * (kx - z);
                     VC[r * Tp + t] = vn;
+                    float zn = clampf(vn, capLo, cap);
+                    GIN[r * Tp + t] = rho * (2.f * zn - vn);
                     if (doAvg) { atomicAdd(VSUM + (size_t)(N + r) * Tp + t, vn); }
                     if (chk) {
-                        float zn = clampf(vn, capLo, cap), y = rho * (vn - zn);
+                        float y = rho * (vn - zn);
                         VOUT[r * Tp + t] = y;
                         if (y != 0.f) dD -= (double)(cap * fabsf(y));  // support function of the half line / interval
                     }
                 }
-            } else {
-                // aggregate-power row: quadratic (load flattening) + peak epigraph
-                const int r = rU;
-                for (int t = lane; t < Tp; t += 32) {
-                    float v = VC[r * Tp + t], a = agg_a(v, t);
-                    float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
-                    float vn = v + alpha * (VOUT[r * Tp + t] - z);
-                    VC[r * Tp + t] = vn;
-                    if (doAvg) { atomicAdd(VSUM + (size_t)(N + r) * Tp + t, vn); }
-                }
-                __syncwarp();
-                const float pl = peak_level(plevel);
-                if (lane == 0) SCAL[SC_PLEVEL] = pl;
+            }
+        }
+        if (doAgg) {
+            // aggregate-power row: quadratic (load flattening) + peak epigraph
+            const int r = rU;
+            for (int t = lane; t < Tp; t += 32) {
+                float v = VC[r * Tp + t], a = agg_a(v, t);
+                float z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+                float vn = v + alpha * (VOUT[r * Tp + t] - z);
+                VC[r * Tp + t] = vn;
+                if (doAvg) { atomicAdd(VSUM + (size_t)(N + r) * Tp + t, vn); }
+            }
+            __syncwarp();
+            const float pl = peak_level(plevel);
+            if (lane == 0) SCAL[SC_PLEVEL] = pl;
+            float zmax = -3.0e38f;
+            double acc = 0.0;
+            for (int t = lane; t < Tp; t += 32) {
+                float vn = VC[r * Tp + t], an = agg_a(vn, t);
+                float zk = (pk_w > 0.f) ? fminf(an, pl) : an;  // kW
+                float zn = zk / su;
+                GIN[r * Tp + t] = rho * (2.f * zn - vn);
                 if (chk) {
                     // Fenchel equality for y in dg(z): -g*(y) = g(z) - <y, z>
-                    float zmax = -3.0e38f;
-                    double acc = 0.0;
-                    for (int t = lane; t < Tp; t += 32) {
-                        float vn = VC[r * Tp + t], an = agg_a(vn, t);
-                        float zk = (pk_w > 0.f) ? fminf(an, pl) : an;  // kW
-                        float zn = zk / su, y = rho * (vn - zn);
-                        VOUT[r * Tp + t] = y;
-                        if (t < Tb) { zmax = fmaxf(zmax, zk); acc += (double)Gamma * (double)(zk + EBAR[t]) * (double)(zk + EBAR[t]); }
-                        acc -= (double)y * (double)zn;
-                    }
-                    zmax = warp_max(zmax);
-                    dD += acc;
-                    if (lane == 0) dD += (double)pk_w * (double)fmaxf(zmax, pk_p0);
+                    float y = rho * (vn - zn);
+                    VOUT[r * Tp + t] = y;
+                    if (t < Tb) { zmax = fmaxf(zmax, zk); acc += (double)Gamma * (double)(zk + EBAR[t]) * (double)(zk + EBAR[t]); }
+                    acc -= (double)y * (double)zn;
                 }
+            }
+            if (chk) {
+                zmax = warp_max(zmax);
+                dD += acc;
+                if (lane == 0) dD += (double)pk_w * (double)fmaxf(zmax, pk_p0);
             }
         }
         if (!chk) {
@@ -1187,6 +1322,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             build_matrix();
         }
         write_part_q();
+        write_gin();
         __syncthreads();
     }
     if (it > opt.max_iter) it = opt.max_iter;
@@ -1257,9 +1393,9 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 
 
 // explicit launch helper used by the per-horizon translation units
-template <int Q, int TPW, bool MULTI, int NCH>
+template <int Q, int TPW, bool MULTI>
 int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_options* opt, const SolvePhase* ph, int nthreads, size_t smem, cudaStream_t st) {
-    auto kern = acb_solve_kernel<Q, TPW, MULTI, NCH>;
+    auto kern = acb_solve_kernel<Q, TPW, MULTI>;
     ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const SiteDev& d = site->d;
     SmemLayout L = make_layout(d.N, d.R, d.NG, d.NP, d.nSlots, 32 * Q, batch->S_max, nthreads / 32);
@@ -1269,9 +1405,7 @@ int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_o
 }
 #define ACB_INSTANTIATE_Q(QQ)                                                                                              \
     int acb_launch_solve_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, const SolvePhase* ph, \
-                               int nthreads, size_t smem, cudaStream_t st, bool multi, int nch) {                          \
-        if (!multi && nch == 1) return acb_launch_solve_t<QQ, 3, false, 1>(site, batch, opt, ph, nthreads, smem, st);       \
-        if (!multi && nch == 3) return acb_launch_solve_t<QQ, 3, false, 3>(site, batch, opt, ph, nthreads, smem, st);       \
-        if (multi && nch == 1) return acb_launch_solve_t<QQ, 3, true, 1>(site, batch, opt, ph, nthreads, smem, st);         \
-        return acb_launch_solve_t<QQ, 3, true, 3>(site, batch, opt, ph, nthreads, smem, st);                                \
+                               int nthreads, size_t smem, cudaStream_t st, bool multi) {                                   \
+        if (!multi) return acb_launch_solve_t<QQ, 3, false>(site, batch, opt, ph, nthreads, smem, st);                      \
+        return acb_launch_solve_t<QQ, 3, true>(site, batch, opt, ph, nthreads, smem, st);                                   \
     }

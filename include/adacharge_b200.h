@@ -140,7 +140,7 @@ typedef struct acb_batch {
     /* results */
     float* rates;                /* [B][N][Tp] */
     double* pilots;              /* optional [B][N][Tp]: max(min(rates, max_pilot), 0) in float64, i.e. the solve's epilogue also does
-                                  * project_into_continuous_feasible_pilots (postprocessing.py:77-94); on-chip path only, NULL = skip */
+                                  * project_into_continuous_feasible_pilots (postprocessing.py:77-94); NULL = skip */
     float* rate_est;             /* optional [B]: estimated distance (A) of the schedule to its limit point when the rate polish ran, else -1 */
     int32_t* status;             /* [B] */
     int32_t* iters;              /* [B] */

@@ -173,7 +173,8 @@ def main():
         iface = shim.TestingInterface(d)
         S, I = iface.active_sessions(), iface.infrastructure_info()
         obj = obj1 if cfg == "c1" else (obj1s if cfg == "c1s" else obj2)
-        R = mpc.solve_mpc(obj, S, I, iface, prev_peak=iface.get_prev_peak())
+        # the unique-optimum cases are compared rate by rate (1e-3 A): tightest tolerances the float64 IPM reaches
+        R = mpc.solve_mpc(obj, S, I, iface, prev_peak=iface.get_prev_peak(), tol_scale=1e-4 if cfg.startswith("c1") else 1.0)
         gold.append(dict(config=cfg, seed=seed, transformer_cap=cap, objective=obj,
                          oracle_objective=mpc.evaluate_objective(R, obj, I, iface, S, iface.get_prev_peak()), rates=R))
         print(cfg, seed, cap, gold[-1]["oracle_objective"])

@@ -76,27 +76,26 @@ def test_oracle_golden_objective_and_feasibility(require_gpu, mpc_golden):
 
 
 def test_unique_optimum_rates_within_1e3(require_gpu, mpc_golden):
-    """quick_charge + c * equal_share is strictly concave, so the optimum is unique and the
-    schedule itself must match the oracle: within 1e-3 A for c = 0.05 when the iteration is
-    run past the point where the float32 gap estimate can certify anything (negative
-    tolerances => the iteration cap ends the run, accepted as 'inaccurate').  For the
-    nearly linear c = 1e-3 the optimal face is so flat that a 1e-4 gap allows ~1 A of play;
-    there only the objective is compared.  DESIGN.md "precision" has the numbers."""
+    """quick_charge + c * equal_share is strictly concave, so the optimum is unique and the schedule itself must match
+    the oracle within 1e-3 A (BASELINE.json north_star) AT THE DEFAULT OPTIONS of the drop-in class, for the strongly
+    concave c = 0.05 and for the nearly linear c = 1e-3 alike: the kernel's rate polish keeps iterating after the gap
+    is certified until the schedule has stopped moving.  The golden schedules come from the oracle at its tightest
+    tolerances (tests/golden/make_golden.py): at the default interior-point tolerances the oracle itself is up to
+    1.7e-2 A away from the optimum on the c = 1e-3 cases."""
     for g in [g for g in mpc_golden if g["config"].startswith("c1")]:
         iface, S, I = _golden_case(g)
         obj = [tuple(o) for o in g["objective"]]
-        strong = g["config"] == "c1s"
-        opts = dict(eps_rel=-1.0, eps_abs=-1.0, max_iter=3000) if strong else dict(eps_rel=1e-6, eps_abs=1e-9, max_iter=12000)
-        aco = ab.AdaptiveChargingOptimization(_components(obj), iface, solver_options=opts)
-        try:
-            R = aco.solve(S, I)
-        except ab.InfeasibilityException:
-            pytest.fail(str(aco.last_info))
+        aco = ab.AdaptiveChargingOptimization(_components(obj), iface)
+        R = aco.solve(S, I)
+        assert aco.last_info["status"] == 0 and aco.last_info["rate_est"] is not None and 0 <= aco.last_info["rate_est"] <= 3e-4, aco.last_info
         err = np.abs(R - np.array(g["rates"])).max()
         f = mpc.evaluate_objective(R, obj, I, iface)
-        assert abs(f - g["oracle_objective"]) <= 2e-6 * abs(g["oracle_objective"]), (f, g["oracle_objective"], aco.last_info)
-        if strong:
-            assert err <= RATE_TOL, (g["config"], g["seed"], err, aco.last_info)
+        assert abs(f - g["oracle_objective"]) <= 1e-6 * abs(g["oracle_objective"]), (f, g["oracle_objective"], aco.last_info)
+        assert err <= RATE_TOL, (g["config"], g["seed"], err, aco.last_info)
+        # without the polish the same solve stops at the certified gap, far from 1e-3 A on the flat objective
+        if g["config"] == "c1":
+            aco2 = ab.AdaptiveChargingOptimization(_components(obj), iface, solver_options=dict(rate_tol=0.0))
+            assert np.abs(aco2.solve(S, I) - np.array(g["rates"])).max() > RATE_TOL
 
 
 def test_bounds_kernel_matches_reference_rule(require_gpu):

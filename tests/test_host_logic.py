@@ -274,7 +274,12 @@ def test_status_mapping_and_inaccurate_exit():
     from adacharge_b200.adaptive_charging_optimization import check_status
 
     check_status(_cabi.ACB_SOLVED, dict(gap=1.0, violation=1.0))
-    check_status(_cabi.ACB_MAX_ITER, dict(gap=5e-3, violation=5e-4))
+    with pytest.warns(RuntimeWarning, match="iteration limit"):
+        check_status(_cabi.ACB_MAX_ITER, dict(gap=5e-3, violation=5e-6))
+    with pytest.raises(ab.InfeasibilityException):  # 5e-4 is above the 1e-5 parity bar ...
+        check_status(_cabi.ACB_MAX_ITER, dict(gap=5e-3, violation=5e-4))
+    with pytest.warns(RuntimeWarning):               # ... unless the caller opts in
+        check_status(_cabi.ACB_MAX_ITER, dict(gap=5e-3, violation=5e-4), violation=1e-3)
     for status, info in ((_cabi.ACB_MAX_ITER, dict(gap=5e-2, violation=0.0)), (_cabi.ACB_MAX_ITER, dict(gap=0.0, violation=1e-2)),
                          (_cabi.ACB_INFEASIBLE, dict(gap=0.0, violation=0.0)), (_cabi.ACB_NUMERICAL, dict(gap=0.0, violation=0.0))):
         with pytest.raises(ab.InfeasibilityException, match="Solve failed with status"):

@@ -2,9 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import bench
+import common
 from adacharge_b200 import _cabi, engine
-site, insts, _ = bench.build_instances(148, 0)
+site, insts, _ = common.build_instances(148, 0)
 pb = engine.PackedBatch(site, insts).upload()
 def t(max_iter=300, **kw):
     opt = _cabi.default_options(max_iter=max_iter, eps_rel=1e-12, eps_abs=0.0, **kw)

@@ -1,8 +1,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch, bench
+import torch, common
 from adacharge_b200 import _cabi, engine
-site, insts, _ = bench.build_instances(148, 0)
+site, insts, _ = common.build_instances(148, 0)
 pb = engine.PackedBatch(site, insts).upload()
 def t(mi):
     opt = _cabi.default_options(max_iter=mi, check_every=100000, restart=0, adapt_rho=0, eps_rel=1e-12, eps_abs=0.0)

@@ -1,10 +1,10 @@
 """DEV: iterations / time to certificate on the bench workload for solver parameter variants."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch, bench
+import numpy as np, torch, common
 from adacharge_b200 import _cabi, engine
 B = 2368
-site, insts, _ = bench.build_instances(B, 0)
+site, insts, _ = common.build_instances(B, 0)
 pb = engine.PackedBatch(site, insts).upload()
 def run(**kw):
     opt = _cabi.default_options(**kw)

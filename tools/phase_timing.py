@@ -2,9 +2,9 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-import bench
+import common
 from adacharge_b200 import _cabi, engine
-site, insts, _ = bench.build_instances(148, 0)
+site, insts, _ = common.build_instances(148, 0)
 pb = engine.PackedBatch(site, insts, want_warm_out=True).upload()
 pb.warm_out["mu"] = torch.zeros((148, 256), dtype=torch.float32, device=pb.rates.device)
 opt = _cabi.default_options(max_iter=300)

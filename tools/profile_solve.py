@@ -2,12 +2,12 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import bench
+import common
 from adacharge_b200 import _cabi, engine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 300
-site, insts, _ = bench.build_instances(B, 0)
+site, insts, _ = common.build_instances(B, 0)
 pb = engine.PackedBatch(site, insts).upload()
 opt = _cabi.default_options(max_iter=iters)
 for _ in range(2):

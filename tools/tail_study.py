@@ -9,11 +9,11 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-import bench
+import common
 from adacharge_b200 import _cabi, engine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-site, insts, _ = bench.build_instances(B, 0)
+site, insts, _ = common.build_instances(B, 0)
 pb = engine.PackedBatch(site, insts).upload()
 
 

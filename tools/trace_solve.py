@@ -14,10 +14,10 @@ import torch
 from adacharge_b200 import _cabi
 
 _cabi.LIB_PATH = os.path.join(ROOT, "tools", "build", "libadacharge_b200_trace.so")
-import bench
+import common
 from adacharge_b200 import engine
 
-site, insts, _ = bench.build_instances(148, 0)
+site, insts, _ = common.build_instances(148, 0)
 pb = engine.PackedBatch(site, insts).upload()
 opt = _cabi.default_options(max_iter=140, eps_rel=-1.0, eps_abs=-1.0)
 for _ in range(2):
