@@ -12,17 +12,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadacharge_b200.so")
 
 ACB_SOC, ACB_LINEAR = 0, 1
-ACB_SOLVED, ACB_MAX_ITER, ACB_INFEASIBLE, ACB_NUMERICAL = 0, 1, 2, 3
+ACB_SOLVED, ACB_MAX_ITER, ACB_INFEASIBLE, ACB_NUMERICAL, ACB_INVALID = 0, 1, 2, 3, 4
 ACB_NSTATS = 8
 EXPORTS = [
     "acb_site_create", "acb_site_destroy", "acb_site_dims", "acb_site_max_horizon", "acb_default_options",
     "acb_solve_batch", "acb_charging_rate_bounds", "acb_project_continuous", "acb_project_discrete",
-    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_pack_sessions", "acb_last_error", "acb_version",
+    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_pack_sessions", "acb_preprocess_sessions", "acb_last_error", "acb_version",
 ]
 ACB_MAX_COMPONENTS = 16
 # acb_objective.kind values (include/adacharge_b200.h)
 OBJ_KIND = {"quick_charge": 0, "equal_share": 1, "tou_energy_cost": 2, "total_energy": 3, "peak": 4, "demand_charge": 5,
-            "load_flattening": 6, "non_completion_penalty": 7}
+            "load_flattening": 6, "non_completion_penalty": 7, "non_completion_penalty_l2": 8}
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -34,7 +34,7 @@ class Options(C.Structure):
         ("eps_abs", C.c_float), ("eps_rel", C.c_float), ("viol_tol", C.c_float), ("rho0", C.c_float),
         ("kappa", C.c_float), ("alpha", C.c_float), ("max_iter", C.c_int32), ("check_every", C.c_int32),
         ("equality", C.c_int32), ("adapt_rho", C.c_int32), ("restart", C.c_int32), ("avg_every", C.c_int32), ("stall_checks", C.c_int32), ("max_rescues", C.c_int32), ("path", C.c_int32), ("stall_exit", C.c_int32), ("dual_refine", C.c_int32), ("term_floor", C.c_float), ("rho_curv", C.c_float),
-        ("rate_tol", C.c_float), ("polish_min_qd", C.c_float), ("phase_iters", C.c_int32),
+        ("rate_tol", C.c_float), ("polish_min_qd", C.c_float), ("newton_rel", C.c_float), ("phase_iters", C.c_int32),
     ]
 
 
@@ -43,11 +43,11 @@ _P = C.c_void_p
 
 class Batch(C.Structure):
     _fields_ = [
-        ("B", C.c_int32), ("Tp", C.c_int32), ("S_max", C.c_int32), ("multi_session", C.c_int32),
+        ("B", C.c_int32), ("Tp", C.c_int32), ("S_max", C.c_int32), ("multi_session", C.c_int32), ("lb_zero", C.c_int32),
         ("T", _P), ("n_sessions", _P), ("sess_row", _P), ("sess_start", _P), ("sess_len", _P),
         ("sess_energy", _P), ("sess_rate_off", _P), ("min_rates", _P), ("max_rates", _P),
         ("alpha", _P), ("beta", _P), ("qd", _P), ("gamma", _P), ("ext", _P), ("peak_w", _P), ("peak_p0", _P),
-        ("peak_limit", _P), ("work", _P),
+        ("peak_limit", _P), ("sess_quad", _P), ("work", _P),
         ("warm_v1", _P), ("warm_vc", _P), ("warm_mu", _P), ("warm_scal", _P),
         ("out_v1", _P), ("out_vc", _P), ("out_mu", _P), ("out_scal", _P),
         ("rates", _P), ("pilots", _P), ("rate_est", _P), ("status", _P), ("iters", _P), ("stats", _P),
@@ -94,6 +94,7 @@ def lib():
     L.acb_reallocate.argtypes = [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P]
     L.acb_constraints_feasible.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]
     L.acb_min_rate_admission.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]
+    L.acb_preprocess_sessions.argtypes = [_P, C.POINTER(Sessions), C.c_int, _P, _P]
     L.acb_pack_sessions.argtypes = [_P, C.POINTER(Sessions), C.POINTER(Objective), C.POINTER(Batch), _P, _P]
     _lib = L
     return L

@@ -362,7 +362,7 @@ class AdaptiveChargingOptimization:
         return rates
 
 
-_STATUS_NAME = {0: "optimal", 1: "iteration_limit", 2: "infeasible", 3: "numerical_error"}
+_STATUS_NAME = {0: "optimal", 1: "iteration_limit", 2: "infeasible", 3: "numerical_error", 4: "invalid_batch_declaration"}
 
 
 def check_status(status: int, info: dict, gap: float = 1e-2, violation: float = 1e-5):

@@ -83,6 +83,8 @@ class _Chunk:
             raw["external_signal"] = ((B, Tp), np.float64)
         if owner.site.use_peak_row:
             raw["peak_limit"] = ((B, Tp), np.float64)
+        if owner.estimate_max_rate:
+            raw["upper_bound"] = ((B, S), np.float64)
         self.host = {k: torch.empty(shape, dtype=torch.from_numpy(np.empty(0, dt)).dtype).pin_memory() for k, (shape, dt) in raw.items()}
         self.dev_raw = {k: torch.empty_like(v, device=dev) for k, v in self.host.items()}
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
@@ -145,7 +147,8 @@ class BatchedAdaptiveCharging:
 
     def __init__(self, objective: List[aco.ObjectiveComponent], infrastructure, period, batch: int, max_sessions: int, horizon: int,
                  constraint_type="SOC", enforce_energy_equality=False, peak_limit=False, multi_session=False, demand_charge=0.0,
-                 per_instance_demand_charge=False, solver_options: Optional[dict] = None, device=None, chunks: int = 4):
+                 per_instance_demand_charge=False, solver_options: Optional[dict] = None, device=None, chunks: int = 4,
+                 enforce_pilot_limit=True, estimate_max_rate=False):
         from .interface import InfrastructureInfo
 
         if isinstance(infrastructure, dict):
@@ -165,6 +168,9 @@ class BatchedAdaptiveCharging:
         self.need_prices = K["tou_energy_cost"] in kinds
         self.need_ext = K["load_flattening"] in kinds
         self.need_dc_array = bool(per_instance_demand_charge)
+        # preprocessing of schedule() (ada.py:141-146) on the device: max_rate <- min(max_rate, max_pilot) and, with
+        # estimate_max_rate, the estimator's per-session upper bounds (passed to schedule() as `upper_bound`)
+        self.enforce_pilot_limit, self.estimate_max_rate = bool(enforce_pilot_limit), bool(estimate_max_rate)
         self.demand_charge_scalar = float(demand_charge)
         opts = dict(solver_options or {})
         if K["equal_share"] not in kinds:
@@ -185,11 +191,13 @@ class BatchedAdaptiveCharging:
         # own kernels per call and chunk: the packer + the solve (three launches when phased: solve, relaunch list, solve;
         # the general path launches per phase and is not counted here)
         phased = self.options.phase_iters > 0 and self.options.phase_iters < self.options.max_iter
-        self.kernel_launches_per_call = len(self.chunks) * (1 + (3 if phased else 1))
+        self.kernel_launches_per_call = len(self.chunks) * (1 + (3 if phased else 1) + int(self.enforce_pilot_limit or self.estimate_max_rate))
 
     # ------------------------------------------------------------------------------------------------
     def _stage(self, ch: _Chunk, arrays: Dict[str, np.ndarray]):
         """host arrays -> the chunk's pinned staging (a plain memcpy per field)."""
+        # every minimum rate 0 (the usual case) is declared to the library: fastest on-chip variant
+        ch.batch.lb_zero = int(not np.any(np.asarray(arrays["min_rate"])[ch.lo:ch.hi] != 0))
         for k, dst in ch.host.items():
             src = arrays.get(k)
             if src is None:
@@ -219,6 +227,9 @@ class BatchedAdaptiveCharging:
                 for k, t in ch.host.items():
                     ch.dev_raw[k].copy_(t, non_blocking=True)
             ch.flags.zero_()
+            if self.enforce_pilot_limit or self.estimate_max_rate:
+                _cabi.check(L.acb_preprocess_sessions(self.site.handle, C.byref(ch.sessions), int(self.enforce_pilot_limit),
+                                                      engine._ptr(ch.dev_raw.get("upper_bound")), st), "acb_preprocess_sessions")
             _cabi.check(L.acb_pack_sessions(self.site.handle, C.byref(ch.sessions), C.byref(ch.objective), C.byref(ch.batch), engine._ptr(ch.flags), st), "acb_pack_sessions")
             if events is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -236,7 +247,7 @@ class BatchedAdaptiveCharging:
                 ch.flags_host.copy_(ch.flags, non_blocking=True)
 
     def schedule_async(self, sessions: Dict[str, np.ndarray], prices=None, prev_peak=None, demand_charge=None, external_signal=None, peak_limit=None,
-                       independent=False, start_event=None):
+                       upper_bound=None, independent=False, start_event=None):
         """Stage, copy, pack, solve and copy back, chunk by chunk; returns after everything is enqueued.  By default the
         chunk streams start after the current stream's earlier work and the current stream waits for all chunks, so a
         synchronize of the current stream makes ``result()`` valid.  ``independent=True`` leaves the current stream out
@@ -244,7 +255,8 @@ class BatchedAdaptiveCharging:
         (double buffering); use ``wait()`` / ``join()`` before reading the result."""
         self.wait()  # the pinned staging and the result buffers of the previous call on this object are reused
         arrays = dict(sessions)
-        arrays.update(prices=prices, prev_peak=prev_peak, demand_charge=demand_charge, external_signal=external_signal, peak_limit=peak_limit)
+        arrays.update(prices=prices, prev_peak=prev_peak, demand_charge=demand_charge, external_signal=external_signal, peak_limit=peak_limit,
+                      upper_bound=upper_bound)
         cur = torch.cuda.current_stream(self.device)
         for ch in self.chunks:
             self._stage(ch, arrays)

@@ -51,6 +51,8 @@ struct SiteDev {
 struct acb_site {
     int device;
     SiteDev d;
+    SiteDev d2;          // same site with 2 EVSE rows per warp (slot tables only differ): the FAST variant's 1024-thread blocks
+    int has_d2;
     std::vector<void*> allocs;
     int constraint_type;
     const int* grp_off_dev;  // [NG+1] offsets of each group's rows in the (group-sorted) slot list

@@ -9,6 +9,7 @@
 // All arithmetic is float64 in the reference's order of operations and rounded to float32 once, which makes the result
 // bit-identical to the host packer (engine.PackedBatch / pack_objective); tests/test_gpu_batched.py checks that.
 // One block per instance; sessions are rank-sorted by (EVSE row, slot) as the solve kernels expect.
+#include <algorithm>
 #include "acb_common.cuh"
 
 __global__ void acb_pack_kernel(SiteDev S, acb_sessions X, acb_objective O, acb_batch B, int32_t* flags) {
@@ -146,6 +147,44 @@ extern "C" int acb_pack_sessions(acb_site* site, const acb_sessions* sessions, c
     const size_t smem = (size_t)sessions->S_max * sizeof(int);
     if (smem > 48 * 1024) { acb_set_error("acb_pack_sessions: S_max too large"); return ACB_E_TOO_LARGE; }
     acb_pack_kernel<<<batch->B, 128, smem, (cudaStream_t)stream>>>(site->d, *sessions, *objective, *batch, flags);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+// ---- batched preprocessing of the raw session tables ----------------------------------------
+// What AdaptiveSchedulingAlgorithm.schedule applies to the sessions before every solve (reference
+// adacharge/adacharge.py:141-146, acnportal's helpers):
+//   enforce_pilot_limit          max_rate <- min(max_rate, max_pilot of the session's EVSE)
+//   apply_upper_bound_estimate   max_rate <- min(max_rate, estimator's upper bound), then max_rate <- min_rate
+//                                where it fell below the minimum rate
+// element-wise over the [B][S_max] tables, in place.
+__global__ void acb_preprocess_kernel(SiteDev S, acb_sessions X, int do_pilot_limit, const double* upper) {
+    const size_t n = (size_t)X.B * X.S_max;
+    double* mx = const_cast<double*>(X.max_rate);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int row = X.station[i];
+        if (row < 0 || row >= S.N) continue;
+        double m = mx[i];
+        if (do_pilot_limit) { const double p = S.max_pilot[row]; m = (p < m) ? p : m; }  // np.minimum
+        if (upper) {
+            const double u = upper[i];
+            m = (u < m) ? u : m;
+            const double lo = X.min_rate[i];
+            if (m < lo) m = lo;  // reconcile: the minimum rate wins
+        }
+        mx[i] = m;
+    }
+}
+
+extern "C" int acb_preprocess_sessions(acb_site* site, const acb_sessions* sessions, int enforce_pilot_limit, const double* upper_bound, void* stream) {
+    if (!site || !sessions || sessions->B <= 0 || sessions->S_max <= 0 || !sessions->station || !sessions->max_rate || !sessions->min_rate) {
+        acb_set_error("acb_preprocess_sessions: bad arguments");
+        return ACB_E_INVALID;
+    }
+    ACB_CUDA(cudaSetDevice(site->device));
+    const size_t n = (size_t)sessions->B * sessions->S_max;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+    acb_preprocess_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(site->d, *sessions, enforce_pilot_limit, upper_bound);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }

@@ -38,6 +38,7 @@ extern "C" void acb_default_options(acb_options* o) {
     o->path = 0;
     o->rate_tol = 3e-4f;
     o->polish_min_qd = 5e-4f;
+    o->newton_rel = 0.25f;
     o->phase_iters = 0;
 }
 
@@ -289,6 +290,32 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
         UP(volt64, volt)
     }
 #undef UP
+    // second slot layout, two EVSE rows per warp, for the FAST on-chip variant (v in shared memory, 1024-thread blocks:
+    // with no per-element state in registers more, smaller warps hide the latencies better)
+    s->has_d2 = 0;
+    if ((N + 1) / 2 <= ACB_MAX_WARPS) {
+        SiteDev& e = s->d2;
+        e = d;
+        e.TPW = 2;
+        e.nRowWarps = (N + 1) / 2;
+        e.nSlots = e.nRowWarps * 2;
+        std::vector<int> s_row(e.nSlots, -1), s_grp(e.nSlots, 0), s_prow(e.nSlots, 0), s_first(e.nSlots, 0), p_off(NG + 1, 0);
+        int np2 = 0;
+        for (int sl = 0; sl < e.nSlots && sl < N; ++sl) {
+            const int i = order[sl], g = grp[i];
+            s_row[sl] = i;
+            s_grp[sl] = g;
+            const bool newp = (sl % 2 == 0) || s_grp[sl - 1] != g;
+            if (newp) { s_first[sl] = 1; s_prow[sl] = np2++; p_off[g + 1]++; }
+            else s_prow[sl] = s_prow[sl - 1];
+        }
+        for (int g = 0; g < NG; ++g) p_off[g + 1] += p_off[g];
+        e.NP = np2;
+        if ((rc = upload(s, s_row, &e.slot_row)) != ACB_OK || (rc = upload(s, s_grp, &e.slot_grp)) != ACB_OK ||
+            (rc = upload(s, s_prow, &e.slot_prow)) != ACB_OK || (rc = upload(s, s_first, &e.slot_first)) != ACB_OK ||
+            (rc = upload(s, p_off, &e.pg_off)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        s->has_d2 = 1;
+    }
     *out = s;
     return ACB_OK;
 }

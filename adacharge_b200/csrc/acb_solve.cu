@@ -28,10 +28,10 @@ __global__ void acb_bounds_kernel(SiteDev S, acb_batch B, float* lb, float* ub) 
     }
 }
 
-int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
-int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
-int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
-int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool);
+int acb_launch_solve_q2(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q4(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q5(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
+int acb_launch_solve_q9(const acb_site*, const acb_batch*, const acb_options*, const SolvePhase*, int, size_t, cudaStream_t, bool, int);
 
 // Between the launches of a phased solve: the parked (still running) instances, ordered by the relative gap of their
 // last convergence check, largest first (a counting sort over 256 logarithmic buckets; one block).  The gap after the
@@ -94,11 +94,20 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
         return ACB_E_TOO_LARGE;
     }
     const bool multi = batch->multi_session != 0;
+    // every minimum rate declared 0: v in shared memory instead of the lower bounds.  opt.path 4 (experimental) runs that
+    // variant with two rows per warp in 1024-thread blocks (measured 3-4 % slower than three rows in 768 threads)
+    int fast = (!multi && batch->lb_zero != 0) ? 1 : 0;
+    if (fast && site->has_d2 && opt.path == 4) {
+        const SiteDev& e = site->d2;
+        const int nt2 = std::min(1024, ((std::max(e.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp)) + 127) / 128) * 128);
+        const size_t sm2 = (size_t)make_layout(e.N, e.R, e.NG, e.NP, e.nSlots, batch->Tp, batch->S_max, nt2 / 32).total * sizeof(float);
+        if (e.nRowWarps * 32 <= nt2 && sm2 <= 232448) { fast = 2; nthreads = nt2; smem = sm2; }
+    }
     auto launch = [&](const SolvePhase& ph) -> int {
-        if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, &ph, nthreads, smem, st, multi);
-        if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, &ph, nthreads, smem, st, multi);
-        if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, &ph, nthreads, smem, st, multi);
-        return acb_launch_solve_q9(site, batch, &opt, &ph, nthreads, smem, st, multi);
+        if (Q == 2) return acb_launch_solve_q2(site, batch, &opt, &ph, nthreads, smem, st, multi, fast);
+        if (Q == 4) return acb_launch_solve_q4(site, batch, &opt, &ph, nthreads, smem, st, multi, fast);
+        if (Q == 5) return acb_launch_solve_q5(site, batch, &opt, &ph, nthreads, smem, st, multi, fast);
+        return acb_launch_solve_q9(site, batch, &opt, &ph, nthreads, smem, st, multi, fast);
     };
     // scratch from the stream-ordered pool: the schedule of the previous check (rate polish) and the parked state
     int nSM = 148;
@@ -109,7 +118,7 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     const size_t nNT = (size_t)B * N * Tp;
     size_t bytes = 256;
     if (wantZ) bytes += nNT * 4;
-    if (phased) bytes += nNT * 4 + ((size_t)B * R1 * Tp + (size_t)B * batch->S_max + (size_t)B * ACB_NSTATE + B + 64) * 4;
+    if (phased) bytes += nNT * 4 + ((size_t)B * R1 * Tp + (size_t)B * 2 * batch->S_max + (size_t)B * ACB_NSTATE + B + 64) * 4 + 1024;
     char* base = nullptr;
     SolvePhase ph{};
     ph.it_stop = opt.max_iter;
@@ -122,7 +131,7 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
         if (phased) {
             ph.st_v1 = (float*)take(nNT);
             ph.st_vc = (float*)take((size_t)B * R1 * Tp);
-            ph.st_mu = (float*)take((size_t)B * batch->S_max);
+            ph.st_mu = (float*)take((size_t)B * 2 * batch->S_max);
             ph.st_scal = (float*)take((size_t)B * ACB_NSTATE);
         }
     }

@@ -154,6 +154,11 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
             double tot = 0.0;
             float um = 0.f;
             for (int w = 0; w < nw; ++w) { tot += redd[w]; um = fmaxf(um, redu[w]); }
+            if (B.sess_quad)
+                for (int s2 = 0; s2 < nS; ++s2) {
+                    const double Eb = (double)B.sess_energy[(size_t)b * B.S_max + s2];
+                    tot += (double)(B.sess_quad[(size_t)b * B.S_max + s2] * cs) * Eb * Eb;
+                }
             W.dacc[(size_t)b * GD_N + GD_PMAX] = tot + (double)(B.peak_w[b] * cs) * (double)fmaxf(um, B.peak_p0[b]);
         }
         // cold start: rho0, raised to the curvature of the aggregate quadratic seen through the scaled aggregate row
@@ -268,8 +273,12 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                 const float Eb = B.sess_energy[(size_t)b * B.S_max + s];
                 const float tol = 2e-6f * (Eb + 1.f);
                 float mu = MU[s];
-                float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
-                if (!opt.equality) mu = fmaxf(mu, 0.f);
+                // quadratic shortfall term cq (Eb - E)^2 (non_completion_penalty, norm 2): see newton_mu in acb_solve_kernel.cuh
+                const float cq = B.sess_quad ? B.sess_quad[(size_t)b * B.S_max + s] * sc[GS_CS] : 0.f;
+                const bool soft = cq > 0.f && !opt.equality, freeMu = opt.equality || soft;
+                const float ikq = soft ? rho1 / (2.f * cq) : 0.f;
+                float lo = freeMu ? -3.0e38f : -1.f, hi = 3.0e38f;
+                if (!freeMu) mu = fmaxf(mu, 0.f);
                 for (int step = 0; step < 16; ++step) {
                     float E = 0.f;
                     int nf = 0;
@@ -284,17 +293,18 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                     }
                     E = wsum(E);
                     nf = __reduce_add_sync(0xffffffffu, nf);
-                    float rr = E - Eb;
+                    float rr = E - Eb - ((soft && mu < 0.f) ? mu * ikq : 0.f);
+                    const float slope = (float)nf + ((soft && mu < 0.f) ? ikq : 0.f);
                     if (fabsf(rr) <= tol) break;
-                    if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
+                    if (!freeMu && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
                     if (rr > 0.f) lo = mu; else hi = mu;
-                    float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
-                    if (!opt.equality) mun = fmaxf(mun, 0.f);
+                    float mun = (slope > 0.f) ? mu + rr / slope : (rr > 0.f ? 3.0e38f : -3.0e38f);
+                    if (!freeMu) mun = fmaxf(mun, 0.f);
                     if (!(mun > lo && mun < hi)) {
-                        if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
+                        if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, freeMu ? lo : 0.f) + hi);
                         else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
                         else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
-                        if (!opt.equality) mun = fmaxf(mun, 0.f);
+                        if (!freeMu) mun = fmaxf(mun, 0.f);
                     }
                     mu = mun;
                 }
@@ -344,7 +354,29 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                 if (MODE == 4 && B.out_v1) B.out_v1[base + 32 * q] = vq;
             }
             if (MODE == 3 && lane == 0)
-                for (int s = sf; s < sf + scn; ++s) dsum -= (double)(rho1 * MU[s]) * (double)B.sess_energy[(size_t)b * B.S_max + s];
+                for (int s = sf; s < sf + scn; ++s) {
+                    const double m = (double)(rho1 * MU[s]);
+                    dsum -= m * (double)B.sess_energy[(size_t)b * B.S_max + s];
+                    const float cq = B.sess_quad ? B.sess_quad[(size_t)b * B.S_max + s] * sc[GS_CS] : 0.f;
+                    if (m < 0.0 && cq > 0.f) dsum -= m * m / (4.0 * (double)cq);  // conjugate of the quadratic shortfall term
+                }
+            if (MODE == 2 && B.sess_quad) {
+                // objective term cq (Eb - E)^2 of the candidate, E = planned amp-periods inside the session window
+                for (int s = sf; s < sf + scn; ++s) {
+                    const float cq = B.sess_quad[(size_t)b * B.S_max + s] * sc[GS_CS];
+                    if (!(cq > 0.f)) continue;
+                    const int a = SA[s], e = a + SL[s];
+                    float Es = 0.f;
+#pragma unroll
+                    for (int q = 0; q < nq; ++q) {
+                        const int t = lane + 32 * q;
+                        if (t >= a && t < e) Es += clampf(rs.V(q) - MU[s], rs.LB(q), rs.UB(q));
+                    }
+                    Es = wsum(Es);
+                    const float Eb = B.sess_energy[(size_t)b * B.S_max + s];
+                    if (lane == 0) dsum += (double)cq * (double)(Eb - Es) * (double)(Eb - Es);
+                }
+            }
         }
     }
     if (MODE <= 2) {

@@ -61,7 +61,7 @@ __device__ __forceinline__ void proj_disc(float a, float b, float lim, float& za
 
 // shared-memory layout (in floats), computed identically on host and device
 struct SmemLayout {
-    int LB, UB, PART, VC, VOUT, GIN, HG, THC, THA, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2,
+    int LB, UB, PART, VC, VOUT, GIN, HG, THC, THA, ALPHA, BETA, PLIM, EBAR, MFT, CS, SESS_A, SESS_B, SESS_E, SESS_MU, SESS_MU2, SESS_NF, SESS_Q, ROWHI,
         SLOT, PGOFF, NGRP, KG, LIM, SCALE, REDF, REDD, SCAL, SCALD, total;
     int OP;  // padded output count of MFT
 };
@@ -76,22 +76,25 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
     const int scratch = R * R + R * NG + 8;
     L.PART = take(NP * Tp > scratch ? NP * Tp : scratch);
     L.VC = take(R * Tp);
-    L.VOUT = take(R * Tp);
     L.GIN = take(R * Tp);  // rho (2 z - v) of the coupling rows: written where v is updated, read by the column pass
-    L.HG = take(NG * Tp);
+    L.HG = take(NG * Tp);  // HG and VOUT are one (NG + R) x Tp output block of the column pass: keep them adjacent
+    L.VOUT = take(R * Tp);
     L.THC = take(Tp);  // per-period restoration factors of the current / averaged candidate
     L.THA = take(Tp);
     L.ALPHA = take(Tp);
     L.BETA = take(Tp);
     L.PLIM = take(Tp);
     L.EBAR = take(Tp);
-    L.MFT = take((NG + R) * L.OP);
+    L.MFT = take((NG + R + 2) * L.OP);  // inputs: NG group sums, R coupling inputs, alpha_t, beta_t
     L.CS = take(R * NG);
     L.SESS_A = take(S_max);
     L.SESS_B = take(S_max);
     L.SESS_E = take(S_max);
     L.SESS_MU = take(S_max);
     L.SESS_MU2 = take(S_max);
+    L.SESS_Q = take(S_max);    // per-session quadratic weight cq (cost-scaled): objective term cq (Ebar_s - sum_window r)^2
+    L.SESS_NF = take(S_max);   // slope estimate (number of free elements) of each session's energy equation, 0 = unknown
+    L.ROWHI = take(nSlots);    // the row's upper bound inside its window when that is one constant, else -1
     L.SLOT = take(nSlots * 6);  // row, grp, prow, first, sess_first, sess_cnt
     L.PGOFF = take(NG + 1);
     L.NGRP = take(NG);
@@ -108,7 +111,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 
 // float scalars
 enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE,
-       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST };
+       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST, SC_UBVAR };
 // double scalars
 enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP, SD_PMAX };
 // per-warp float reduction slots (max-type)
@@ -127,7 +130,7 @@ struct SolvePhase {
     int resume;        // 1: continue from the parked state
     const int* list;   // instance of block i (NULL: i); blocks >= *count exit
     const int* count;
-    float* st_v1;      // parked state: [B][N][Tp], [B][R][Tp], [B][S_max], [B][ACB_NSTATE]
+    float* st_v1;      // parked state: [B][N][Tp], [B][R][Tp], [B][2 S_max] (multipliers, slope estimates), [B][ACB_NSTATE]
     float* st_vc;
     float* st_mu;
     float* st_scal;
@@ -136,16 +139,20 @@ struct SolvePhase {
 
 #ifdef ACB_TRACE
 // development build only (tools/trace_solve.py): per-warp clock64() stamps of block 0 at the phase boundaries
-#define ACB_TR_IT0 101
+#define ACB_TR_IT0 111
 #define ACB_TR_NIT 16
 __device__ long long g_acb_trace[ACB_TR_NIT * 32 * 8];
-#define ACB_TR(k) do { if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT && lane == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + warp) * 8 + (k)] = clock64(); } while (0)
+__device__ __forceinline__ long long acb_clock() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory"); return c; }
+#define ACB_TR(k) do { if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT && lane == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + warp) * 8 + (k)] = acb_clock(); } while (0)
 #else
 #define ACB_TR(k) do { } while (0)
 #endif
 
-template <int Q, int TPW, bool MULTI>
-__global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L, const SolvePhase P) {
+// FAST: the caller declared every minimum rate 0 (acb_batch.lb_zero) and rows hold one session.  The lower-bound
+// array is then not needed and its shared memory holds v instead of registers: the hot loop keeps no per-element state
+// in registers (no spills under the 80-register cap, loop constants stay resident).
+template <int Q, int TPW, bool MULTI, bool FAST>
+__global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L, const SolvePhase P) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -157,6 +164,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     float* SINV = PART; float* XS = PART + R * R;
     int* SESS_A = (int*)(sm + L.SESS_A); int* SESS_B = (int*)(sm + L.SESS_B);
     float* SESS_E = sm + L.SESS_E; float* SESS_MU = sm + L.SESS_MU; float* SESS_MU2 = sm + L.SESS_MU2;
+    float* SESS_NF = sm + L.SESS_NF; float* ROWHI = sm + L.ROWHI; float* SESS_Q = sm + L.SESS_Q;
     int* SLOT = (int*)(sm + L.SLOT); int* PGOFF = (int*)(sm + L.PGOFF);
     float* NGRP = sm + L.NGRP; float* KG = sm + L.KG; float* LIM = sm + L.LIM; float* SCALE = sm + L.SCALE;
     float* REDF = sm + L.REDF; double* REDD = (double*)(sm + L.REDD); float* SCAL = sm + L.SCAL;
@@ -187,8 +195,9 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
     const bool useAvg = opt.restart && VSUM != nullptr;
 
+    float* Vs = LB;  // FAST: v lives where the lower bounds would be
     // bounds of element (row, t)
-    auto lbv = [&](int row, int t) -> float { return LB[row * Tp + t]; };
+    auto lbv = [&](int row, int t) -> float { if constexpr (FAST) return 0.f; else return LB[row * Tp + t]; };
     auto ubv = [&](int row, int t) -> float { return UB[row * Tp + t]; };
     // the lane's Q elements of a row (t = lane + 32 q)
     auto load_bounds = [&](int row, float (&lb)[Q], float (&ub)[Q]) {
@@ -196,13 +205,13 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         const float* ubp = UB + row * Tp + lane;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            lb[q] = lbp[32 * q];
+            if constexpr (FAST) lb[q] = 0.f; else lb[q] = lbp[32 * q];
             ub[q] = ubp[32 * q];
         }
     };
 
     // ------------------------------------------------------------------ prologue
-    for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB and UB are contiguous
+    for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB (FAST: v) and UB are contiguous
     for (int i = tid; i < R * Tp; i += nthreads) {
         VC[i] = B.warm_vc ? B.warm_vc[(size_t)b * R * Tp + i] : 0.f;
         VOUT[i] = 0.f;
@@ -224,7 +233,10 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         SESS_E[i] = ok ? B.sess_energy[k] : 0.f;
         SESS_MU[i] = (ok && B.warm_mu) ? B.warm_mu[k] : 0.f;
         SESS_MU2[i] = 0.f;
+        SESS_NF[i] = 0.f;
+        SESS_Q[i] = (ok && B.sess_quad) ? B.sess_quad[k] : 0.f;  // (scaled by the cost scale below)
     }
+    if (tid == 0) { SCAL[SC_FLAG] = 0.f; SCAL[SC_LBPOS] = 0.f; SCAL[SC_UBVAR] = 0.f; }
     for (int t = tid; t < Tp; t += nthreads) {
         bool ok = t < Tb;
         ALPHA[t] = ok ? B.alpha[(size_t)b * Tp + t] : 0.f;
@@ -241,7 +253,11 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         for (int j = lane; j < len; j += 32) {
             const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
             float lo = B.min_rates[ri], hi = B.max_rates[ri];
-            if (a + j < Tp) { LB[row * Tp + a + j] = lo; UB[row * Tp + a + j] = fmaxf(hi, lo); }
+            if (a + j < Tp) {
+                if constexpr (FAST) { if (lo != 0.f) SCAL[SC_LBPOS] = 1.f; }  // the caller's lb_zero promise is broken: flagged below
+                else LB[row * Tp + a + j] = lo;
+                UB[row * Tp + a + j] = fmaxf(hi, lo);
+            }
         }
     }
     if (tid < S.nSlots) {
@@ -252,13 +268,26 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         SLOT[tid * 6 + 4] = first < 0 ? 0 : first;
         SLOT[tid * 6 + 5] = cnt;
     }
-    if (tid == 0) { SCAL[SC_FLAG] = 0.f; SCAL[SC_LBPOS] = 0.f; }
     for (int t = tid; t < Tp; t += nthreads) { THC[t] = 1.f; THA[t] = 1.f; }
     __syncthreads();
-    {
+    if constexpr (!FAST) {
         bool pos = false;
         for (int i = tid; i < N * Tp; i += nthreads) pos |= (LB[i] != 0.f);
         if (pos) SCAL[SC_LBPOS] = 1.f;  // benign race: every writer stores the same value
+    }
+    // rows whose upper bound is one constant inside the window (the usual case): the hot row pass clips with a
+    // saturating multiply on the FMA pipe instead of min/max pairs on the half-rate ALU pipe
+    if (warp < S.nRowWarps) {
+        for (int k = 0; k < S.TPW; ++k) {
+            const int sl = warp * S.TPW + k, row = SLOT[sl * 6];
+            float m = 0.f;
+            if (row >= 0) for (int t = lane; t < Tp; t += 32) m = fmaxf(m, UB[row * Tp + t]);
+            m = warp_max(m);
+            bool uni = true;
+            if (row >= 0) for (int t = lane; t < Tp; t += 32) { const float u = UB[row * Tp + t]; uni &= (u == 0.f || u == m); }
+            uni = __all_sync(0xffffffffu, uni);
+            if (lane == 0) { ROWHI[sl] = uni ? m : -1.f; if (!uni) SCAL[SC_UBVAR] = 1.f; }
+        }
     }
     // row-level infeasibility: a session whose window cannot hold its energy equality, or whose
     // minimum rates already exceed its energy cap (the reference would get INFEASIBLE from ECOS)
@@ -271,10 +300,11 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
         if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) SCAL[SC_FLAG] = 1.f;
     }
     __syncthreads();
-    if (SCAL[SC_FLAG] != 0.f) {
+    const bool badHint = FAST && SCAL[SC_LBPOS] != 0.f;  // lb_zero was declared but a minimum rate is positive
+    if (SCAL[SC_FLAG] != 0.f || badHint) {
         for (int i = tid; i < N * Tp; i += nthreads) B.rates[(size_t)b * N * Tp + i] = 0.f;
         if (tid == 0) {
-            B.status[b] = ACB_INFEASIBLE;
+            B.status[b] = badHint ? ACB_INVALID : ACB_INFEASIBLE;
             B.iters[b] = 0;
             for (int k = 0; k < ACB_NSTATS; ++k) B.stats[(size_t)b * ACB_NSTATS + k] = 0.f;
         }
@@ -317,12 +347,20 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     __syncthreads();
     const float cs = SCAL[SC_CS];
     for (int t = tid; t < Tp; t += nthreads) { ALPHA[t] *= cs; BETA[t] *= cs; }
+    bool hasQuad = false;  // some session carries a quadratic shortfall term (non_completion_penalty, norm 2)
+    if (B.sess_quad) {
+        for (int i = 0; i < nS; ++i) hasQuad |= SESS_Q[i] > 0.f;
+        __syncthreads();  // everybody has read the unscaled weights
+        for (int i = tid; i < B.S_max; i += nthreads) SESS_Q[i] *= cs;
+    }
     const float qd = B.qd[b] * cs, Gamma = B.gamma[b] * cs, pk_w = B.peak_w[b] * cs, pk_p0 = B.peak_p0[b];
     const float alpha = opt.alpha, kappa = opt.kappa;
     // Feasibility restoration of a candidate: r_t <- theta_t r_t with theta_t = 1 / max(1, worst current/limit at t).
     // With lb = 0, no quadratic term and inequality energy rows the scaled schedule satisfies box, energy caps and
     // every coupling row exactly, and its objective follows from the per-group column sums.
-    const bool canRestore = (SCAL[SC_LBPOS] == 0.f) && (qd == 0.f) && !opt.equality;
+    // (a quadratic weight below 1e-9 of the largest cost coefficient -- the reference's 1e-12 tie-breaker -- changes the
+    // objective of the scaled candidate by less than float32 resolves and does not block the restoration)
+    const bool canRestore = (SCAL[SC_LBPOS] == 0.f) && (qd <= 1e-9f) && !opt.equality && !hasQuad;
     // rate polish (strictly convex objective, unique optimum): besides the certified gap the stop also asks that the
     // schedule has stopped moving -- estimated distance to the fixed point <= rate_tol amperes (see the check path)
     float* ZPREV = P.zprev ? P.zprev + (size_t)b * N * Tp : nullptr;
@@ -376,13 +414,21 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             double tot = 0.0;
             float um = 0.f;
             for (int w = 0; w < nwarps; ++w) { tot += REDD[w * ACB_NRED]; um = fmaxf(um, REDF[w * ACB_NRED]); }
+            if (hasQuad)  // the planned energy stays in [0, Eb] under the cap: (Eb - E)^2 <= Eb^2
+                for (int i = 0; i < nS; ++i) tot += (double)SESS_Q[i] * (double)SESS_E[i] * (double)SESS_E[i];
             SCALD[SD_PMAX] = tot + (double)pk_w * (double)fmaxf(um, pk_p0);
         }
         __syncthreads();
     }
 
     // per-lane state: v for this warp's EVSE rows
-    float v1[TPW][Q];
+    float v1[FAST ? 1 : TPW][FAST ? 1 : Q];
+    auto vget = [&](int k, int q, int row) -> float {
+        if constexpr (FAST) return Vs[row * Tp + lane + 32 * q]; else return v1[k][q];
+    };
+    auto vset = [&](int k, int q, int row, float val) {
+        if constexpr (FAST) Vs[row * Tp + lane + 32 * q] = val; else v1[k][q] = val;
+    };
     const bool rowWarp = warp < S.nRowWarps;
 #pragma unroll
     for (int k = 0; k < TPW; ++k) {
@@ -395,8 +441,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 if (P.resume) v = P.st_v1[((size_t)b * N + row) * Tp + t];
                 else if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
                 else v = clampf(0.f, lbv(row, t), ubv(row, t));
+                vset(k, q, row, v);
             }
-            v1[k][q] = v;
         }
     }
 
@@ -415,12 +461,18 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     // `single`: the row has one session, so outside its window lb = ub = 0 and no mask is needed.
     // `max_evals` = 1 gives one Newton step from the warm start without re-evaluation (used on
     // non-check iterations: the projection is then inexact by an active-set change at most).
+    // `cq` > 0 (inequality rows only): the row also carries the objective term cq (Eb - E)^2 (non_completion_penalty,
+    // norm 2), so this is a prox rather than a projection: the multiplier may go negative, mu = kq (E(mu) - Eb) with
+    // kq = 2 cq / rho1 while the cap is inactive; in residual form E(mu) - Eb - min(mu, 0) / kq = 0, still monotone.
     auto newton_mu = [&](const float (&vv)[Q], const float (&lb)[Q], const float (&ub)[Q], int a, int e, float Eb, float mu,
-                         bool single, int max_evals) -> float {
+                         bool single, int max_evals, float cq = 0.f) -> float {
         const float tol = 2e-6f * (Eb + 1.f);
+        const bool soft = cq > 0.f && !opt.equality;
+        const float ikq = soft ? rho1 / (2.f * cq) : 0.f;
+        const bool freeMu = opt.equality || soft;
         // inequality rows: lo = -1 marks "mu = 0 not evaluated yet" (mu itself stays >= 0)
-        float lo = opt.equality ? -3.0e38f : -1.f, hi = 3.0e38f;
-        if (!opt.equality) mu = fmaxf(mu, 0.f);
+        float lo = freeMu ? -3.0e38f : -1.f, hi = 3.0e38f;
+        if (!freeMu) mu = fmaxf(mu, 0.f);
         for (int step = 0; step < 16; ++step) {
             float E = 0.f;
             int nf = 0;
@@ -444,20 +496,21 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             }
             E = warp_sum(E);
             nf = __reduce_add_sync(0xffffffffu, nf);
-            float rr = E - Eb;
+            float rr = E - Eb - ((soft && mu < 0.f) ? mu * ikq : 0.f);
+            const float slope = (float)nf + ((soft && mu < 0.f) ? ikq : 0.f);
             if (fabsf(rr) <= tol) break;
-            if (!opt.equality && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
+            if (!freeMu && mu <= 0.f && rr < 0.f) { mu = 0.f; break; }
             if (rr > 0.f) lo = mu; else hi = mu;
-            float mun = (nf > 0) ? mu + rr / (float)nf : (rr > 0.f ? 3.0e38f : -3.0e38f);
-            if (!opt.equality) mun = fmaxf(mun, 0.f);
+            float mun = (slope > 0.f) ? mu + rr / slope : (rr > 0.f ? 3.0e38f : -3.0e38f);
+            if (!freeMu) mun = fmaxf(mun, 0.f);
             if (!(mun > lo && mun < hi)) {
-                if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, opt.equality ? lo : 0.f) + hi);
+                if (hi < 1.0e38f && lo > -1.0e38f) mun = 0.5f * (fmaxf(lo, freeMu ? lo : 0.f) + hi);
                 else if (rr > 0.f) mun = mu + fmaxf(1.f, 2.f * fabsf(mu));
                 else mun = mu - fmaxf(1.f, 2.f * fabsf(mu));
-                if (!opt.equality) mun = fmaxf(mun, 0.f);
+                if (!freeMu) mun = fmaxf(mun, 0.f);
             }
             mu = mun;
-            if (step + 1 >= max_evals && nf > 0) break;
+            if (step + 1 >= max_evals && slope > 0.f) break;
         }
         return mu;
     };
@@ -525,30 +578,54 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             XS[i] = acc;
         }
         __syncthreads();
-        for (int i = tid; i < NIN * OP; i += nthreads) {
+        // base element M(c, o) of the (NG+R) x (NG+R) column matrix
+        auto melem = [&](int c, int o) -> float {
+            float m = 0.f;
+            if (o < NG && c < NG) {
+                for (int r = 0; r < R; ++r) m -= CS[r * NG + o] * XS[r * NG + c];
+            } else if (o < NG) {
+                m = dr * XS[(c - NG) * NG + o];
+            } else if (c < NG) {
+                m = XS[(o - NG) * NG + c];
+            } else {
+                int r = o - NG, j = c - NG;
+                m = (r == j ? 1.f : 0.f) - dr * SINV[r * R + j];
+            }
+            return m;
+        };
+        // folded form used by the column pass: inputs are the RAW group sums of q, the coupling inputs GIN and the two
+        // cost coefficients of the period; outputs are HG = Khat'h - c (rows < NG) and Khat x (rows >= NG, the 1/rho
+        // included).  With in_g = rho1 sum_g - n_g (alpha + k_g beta):
+        //   row g       : rho1 M(g, o)
+        //   row NG + r  : M(NG + r, o)
+        //   row alpha   : -sum_g n_g M(g, o) - [o < NG]
+        //   row beta    : -sum_g n_g k_g M(g, o) - [o < NG] k_o
+        for (int i = tid; i < (NIN + 2) * OP; i += nthreads) {
             int c = i / OP, o = i - c * OP;
             float m = 0.f;
             if (o < NIN) {
-                if (o < NG && c < NG) {
-                    for (int r = 0; r < R; ++r) m -= CS[r * NG + o] * XS[r * NG + c];
-                } else if (o < NG) {
-                    m = dr * XS[(c - NG) * NG + o];
-                } else if (c < NG) {
-                    m = XS[(o - NG) * NG + c];
-                } else {
-                    int r = o - NG, j = c - NG;
-                    m = (r == j ? 1.f : 0.f) - dr * SINV[r * R + j];
+                const float so = (o < NG) ? 1.f : 1.f / rho;
+                if (c < NG) m = rho1 * melem(c, o);
+                else if (c < NIN) m = melem(c, o);
+                else {
+                    for (int g = 0; g < NG; ++g) m -= NGRP[g] * (c == NIN ? 1.f : KG[g]) * melem(g, o);
+                    if (o < NG) m -= (c == NIN) ? 1.f : KG[o];
                 }
+                m *= so;
             }
             MFT[i] = m;
         }
         __syncthreads();
     };
     // unconstrained minimiser of the aggregate-power prox (kW) given the stored v of that row
-    auto agg_a = [&](float v, int t) -> float {
-        float rp = rho / (su * su);
-        return (rp * (v * su) - 2.f * Gamma * EBAR[t]) / (rp + 2.f * Gamma);
+    float aggA = 0.f, aggB = 0.f;  // a = aggA v - aggB ext_t; follow rho
+    auto set_agg = [&]() {
+        const float rp = rho / (su * su), den = 1.f / (rp + 2.f * Gamma);
+        aggA = rp * su * den;
+        aggB = 2.f * Gamma * den;
     };
+    set_agg();
+    auto agg_a = [&](float v, int t) -> float { return aggA * v - aggB * EBAR[t]; };
     // peak-epigraph level for the aggregate-power row stored in VC (called by one warp):
     // minimise pk_w*max(p,p0) + cur/2 sum (a_t - p)_+^2 over p
     auto peak_level = [&](float guess) -> float {
@@ -605,8 +682,9 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             for (int q = 0; q < Q; ++q) {
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sf, scn, mu0, t), lbv(row, t), ubv(row, t));
-                float val = 2.f * z - v1[k][q];
+                const float vq = vget(k, q, row);
+                float z = clampf(vq - MU_ELEM(SESS_MU, sf, scn, mu0, t), lbv(row, t), ubv(row, t));
+                float val = 2.f * z - vq;
                 if (first) PART[prow * Tp + t] = val; else PART[prow * Tp + t] += val;
             }
         }
@@ -686,14 +764,18 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
     if (P.resume) {
         // (the prologue filled VC / SESS_MU from the warm-start arrays; the PMAX block above ended with a barrier)
         for (int i = tid; i < R * Tp; i += nthreads) VC[i] = P.st_vc[(size_t)b * R * Tp + i];
-        for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = P.st_mu[(size_t)b * B.S_max + i];
+        for (int i = tid; i < B.S_max; i += nthreads) {
+            SESS_MU[i] = P.st_mu[(size_t)b * 2 * B.S_max + i];
+            SESS_NF[i] = P.st_mu[(size_t)b * 2 * B.S_max + B.S_max + i];
+        }
         __syncthreads();
     } else zero_sums();
     build_matrix();
     write_part_q();
     write_gin();
     __syncthreads();
-    const bool fastRows = !MULTI && SCAL[SC_LBPOS] == 0.f;  // every minimum rate is 0: the hot row pass needs no lower bounds
+    // hot row pass: every minimum rate is 0, one session per row, constant upper bound inside each window
+    const bool fastRows = !MULTI && SCAL[SC_LBPOS] == 0.f && SCAL[SC_UBVAR] == 0.f && !hasQuad;  // (FAST implies the first two)
 
     int it = 0, status = ACB_MAX_ITER;
     bool parked = false;
@@ -713,7 +795,6 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             float out[ACB_OHT];
 #pragma unroll
             for (int k = 0; k < ACB_OHT; ++k) out[k] = 0.f;
-            const float al = ALPHA[t], be = BETA[t];
             auto accum = [&](int c, float in) {
                 const float4* mrow = reinterpret_cast<const float4*>(MFT + c * OP + obase);
 #pragma unroll
@@ -727,18 +808,17 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 const int p1 = PGOFF[g + 1];
 #pragma unroll 4
                 for (int p = PGOFF[g]; p < p1; ++p) acc += PART[p * Tp + t];
-                accum(g, rho1 * acc - NGRP[g] * (al + KG[g] * be));
+                accum(g, acc);
             }
             const float* gin = GIN + t;
 #pragma unroll 4
             for (int r = 0; r < R; ++r) accum(NG + r, gin[r * Tp]);
-            const float inv_rho = 1.f / rho;
+            accum(NIN, ALPHA[t]);
+            accum(NIN + 1, BETA[t]);
+            float* ob = HG + obase * Tp + t;  // (HG, VOUT) output block
 #pragma unroll
-            for (int k = 0; k < ACB_OHT; ++k) {
-                int o = obase + k;
-                if (o < NG) HG[o * Tp + t] = out[k] - (al + KG[o] * be);
-                else if (o < NIN) VOUT[(o - NG) * Tp + t] = out[k] * inv_rho;
-            }
+            for (int k = 0; k < ACB_OHT; ++k)
+                if (obase + k < NIN) ob[k * Tp] = out[k];
         }
         ACB_TR(1);
         __syncthreads();
@@ -764,15 +844,18 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                 load_bounds(row, lb, ub);
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    float vo = v1[k][q];
+                    float vo = vget(k, q, row);
                     float z = clampf(vo - MU_ELEM(SESS_MU, sf, scn, mu0, lane + 32 * q), lb[q], ub[q]);
                     float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
-                    v1[k][q] = vo + alpha * (x - z);
+                    vset(k, q, row, vo + alpha * (x - z));
                     if (CHK) { zo[q] = z; xs[q] = x; rXm = fmaxf(rXm, fabsf(x)); }
                 }
                 // projection onto box ∩ energy rows: one multiplier per session
+                float vrow[Q];
+#pragma unroll
+                for (int q = 0; q < Q; ++q) vrow[q] = vget(k, q, row);
                 for (int s = sf; s < sf + scn; ++s) {
-                    float mu = newton_mu(v1[k], lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], !MULTI, 16);
+                    float mu = newton_mu(vrow, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], !MULTI, 16, SESS_Q[s]);
                     if (lane == 0) SESS_MU[s] = mu;
                     __syncwarp();
                 }
@@ -782,7 +865,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const int t = lane + 32 * q;
-                    float vn = v1[k][q];
+                    float vn = vrow[q];
                     float zn = clampf(vn - MU_ELEM(SESS_MU, sf, scn, mu1, t), lb[q], ub[q]);
                     float val = CHK ? zn : 2.f * zn - vn;
                     if (first) pp[32 * q] = val; else pp[32 * q] += val;
@@ -805,78 +888,95 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                         }
                     }
                 }
+                if (CHK && hasQuad) {
+                    // objective term cq (Eb - E)^2 of each session of the row, E = planned amp-periods inside its window
+                    for (int s = sf; s < sf + scn; ++s) {
+                        if (!(SESS_Q[s] > 0.f)) continue;
+                        float Es = 0.f;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            const int t = lane + 32 * q;
+                            if (MULTI && !(t >= SESS_A[s] && t < SESS_B[s])) continue;
+                            Es += clampf(vrow[q] - MU_ELEM(SESS_MU, sf, scn, mu1, t), lb[q], ub[q]);
+                        }
+                        Es = warp_sum(Es);
+                        if (lane == 0) dPc += (double)SESS_Q[s] * (double)(SESS_E[s] - Es) * (double)(SESS_E[s] - Es);
+                    }
+                }
             }
         };
-        // Hot row pass when every minimum rate is 0 and rows hold one session: the warp's TPW rows advance together, so
-        // the three multiplier searches (warp reductions, scalar Newton steps) overlap instead of queueing, and the
-        // evaluation that confirms a Newton step is the pass that also produces z and the partial sums.
+        // Hot row pass (every minimum rate 0, one session per row, constant upper bound inside each window).  The warp's
+        // TPW rows advance together so that their warp reductions overlap.  Clipping is ub * sat((v - mu) / hi) on the
+        // FMA pipe; x is never formed (v' = c1 v + c2 z + c3 hg).  The multiplier takes ONE Newton step with the slope
+        // remembered from the previous iterations (secant update), and the pass that produces z and the partial sums
+        // also verifies the energy equation; only a row that fails the verification (its active set changed) runs the
+        // exact safeguarded Newton search.
         auto row_pass_fast = [&]() {
+            const float nrel = opt.newton_rel;
             const bool eq = opt.equality != 0;
-            float mu[TPW], Eb[TPW], lo[TPW], hi[TPW], E[TPW];
-            int nf[TPW], rowk[TPW];
-            bool open[TPW];
-            // pass 1: x, over-relaxed v, and the energy of the row at its warm multiplier
+            const float c1 = 1.f - alpha * rho1 * inv_d, c2 = alpha * (2.f * rho1 * inv_d - 1.f), c3 = alpha * inv_d;
+            float mu[TPW], Eb[TPW], E[TPW], E1[TPW], ih[TPW];
+            int rowk[TPW], sfk[TPW];
+            unsigned verify = 0, exact = 0;  // bit k: row k took a step to be verified / needs the exact search
 #pragma unroll
             for (int k = 0; k < TPW; ++k) {
                 const int* sl = SLOT + (warp * TPW + k) * 6;
                 const int row = sl[0];
-                rowk[k] = row; E[k] = 0.f; nf[k] = 0; open[k] = false; mu[k] = 0.f; Eb[k] = 0.f; lo[k] = -1.f; hi[k] = 3.0e38f;
+                rowk[k] = row; E[k] = 0.f; E1[k] = 0.f; mu[k] = 0.f; Eb[k] = 0.f; ih[k] = 0.f; sfk[k] = -1;
                 if (row < 0) continue;
                 const int g = sl[1], sf = sl[4], scn = sl[5];
                 const float mu0 = scn ? SESS_MU[sf] : 0.f;
                 mu[k] = eq ? mu0 : fmaxf(mu0, 0.f);
                 Eb[k] = scn ? SESS_E[sf] : 0.f;
-                open[k] = scn != 0;
-                if (eq) lo[k] = -3.0e38f;
+                sfk[k] = scn ? sf : -1;
+                const float hi_ = ROWHI[warp * TPW + k];
+                ih[k] = hi_ > 0.f ? 1.f / hi_ : 0.f;  // rows without any capacity: sat(0 * w) = 0
                 const float* hgp = HG + g * Tp + lane;
                 const float* ubp = UB + row * Tp + lane;
                 float e = 0.f;
-                int n = 0;
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
-                    const float ub = ubp[32 * q], vo = v1[k][q];
-                    const float z = fminf(fmaxf(vo - mu0, 0.f), ub);
-                    const float x = (rho1 * (2.f * z - vo) + hgp[32 * q]) * inv_d;
-                    const float vn = vo + alpha * (x - z);
-                    v1[k][q] = vn;
-                    if (doAvg) atomicAdd(VSUM + (size_t)row * Tp + lane + 32 * q, vn);  // result unused -> RED
-                    const float w = vn - mu[k];
-                    e += fminf(fmaxf(w, 0.f), ub);
-                    n += (w > 0.f && w < ub) ? 1 : 0;
+                    const float ub = ubp[32 * q], vo = vget(k, q, row);
+                    const float z = ub * __saturatef((vo - mu0) * ih[k]);
+                    const float vn = fmaf(c3, hgp[32 * q], fmaf(c2, z, c1 * vo));
+                    vset(k, q, row, vn);
+                    e = fmaf(ub, __saturatef((vn - mu[k]) * ih[k]), e);
                 }
-                E[k] = e; nf[k] = n;
+                E[k] = e;
             }
-            // one safeguarded Newton step per open row (same rule as newton_mu); a row that closes keeps its multiplier
-            auto nstep = [&](int k, int round) {
+            if (doAvg) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    if (rowk[k] < 0) continue;
+                    float* vs = VSUM + (size_t)rowk[k] * Tp + lane;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) atomicAdd(vs + 32 * q, vget(k, q, rowk[k]));  // result unused -> RED
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) E[k] += __shfl_xor_sync(0xffffffffu, E[k], o);
+            }
+            float mun[TPW];
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                mun[k] = mu[k];
+                if (sfk[k] < 0) continue;
                 const float rr = E[k] - Eb[k];
-                if (fabsf(rr) <= 2e-6f * (Eb[k] + 1.f) || round >= 15) { open[k] = false; return; }
-                if (!eq && mu[k] <= 0.f && rr < 0.f) { mu[k] = 0.f; open[k] = false; return; }
-                if (rr > 0.f) lo[k] = mu[k]; else hi[k] = mu[k];
-                float mun = (nf[k] > 0) ? mu[k] + rr / (float)nf[k] : (rr > 0.f ? 3.0e38f : -3.0e38f);
-                if (!eq) mun = fmaxf(mun, 0.f);
-                if (!(mun > lo[k] && mun < hi[k])) {
-                    if (hi[k] < 1.0e38f && lo[k] > -1.0e38f) mun = 0.5f * (fmaxf(lo[k], eq ? lo[k] : 0.f) + hi[k]);
-                    else if (rr > 0.f) mun = mu[k] + fmaxf(1.f, 2.f * fabsf(mu[k]));
-                    else mun = mu[k] - fmaxf(1.f, 2.f * fabsf(mu[k]));
-                    if (!eq) mun = fmaxf(mun, 0.f);
-                }
-                mu[k] = mun;
-            };
-            auto reduce_all = [&]() {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int k = 0; k < TPW; ++k) E[k] += __shfl_xor_sync(0xffffffffu, E[k], o);
-                }
-#pragma unroll
-                for (int k = 0; k < TPW; ++k) nf[k] = __reduce_add_sync(0xffffffffu, nf[k]);
-            };
-            reduce_all();
-#pragma unroll
-            for (int k = 0; k < TPW; ++k) if (open[k]) nstep(k, 0);
-            // pass 2: z and the partial sums of 2z - v with the current multipliers; rows still open are re-evaluated on
-            // the way and the pass repeats only if one of them has to move its multiplier again
-            for (int round = 1; ; ++round) {
+                if (fabsf(rr) <= 2e-6f * (Eb[k] + 1.f)) continue;            // still exact
+                if (!eq && mu[k] <= 0.f && rr < 0.f) { mun[k] = 0.f; continue; }  // energy cap inactive
+                const float nfe = SESS_NF[sfk[k]];
+                if (nfe > 0.f) {
+                    float m1 = mu[k] + rr / nfe;
+                    if (!eq) m1 = fmaxf(m1, 0.f);
+                    mun[k] = m1;
+                    verify |= 1u << k;
+                } else exact |= 1u << k;
+            }
+            // z and the partial sums of 2z - v with the stepped multipliers (verifying them on the way); the pass is
+            // repeated once, without verification, if some row had to run the exact search
+            for (int round = 0; round < 2; ++round) {
                 float acc[Q];
 #pragma unroll
                 for (int k = 0; k < TPW; ++k) {
@@ -886,18 +986,15 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     const bool first = sl[3] != 0;
                     const float* ubp = UB + row * Tp + lane;
                     float e = 0.f;
-                    int n = 0;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
-                        const float ub = ubp[32 * q], vn = v1[k][q];
-                        const float w = vn - mu[k];
-                        const float zn = fminf(fmaxf(w, 0.f), ub);
-                        const float val = 2.f * zn - vn;
+                        const float vn = vget(k, q, row);
+                        const float zn = ubp[32 * q] * __saturatef((vn - mun[k]) * ih[k]);
+                        const float val = fmaf(2.f, zn, -vn);
                         acc[q] = first ? val : acc[q] + val;
                         e += zn;
-                        n += (w > 0.f && w < ub) ? 1 : 0;
                     }
-                    E[k] = e; nf[k] = n;
+                    E1[k] = e;
                     const bool last = (k == TPW - 1) || rowk[k + 1 < TPW ? k + 1 : k] < 0 || SLOT[(warp * TPW + k + 1) * 6 + 3] != 0;
                     if (last) {
                         float* pp = PART + sl[2] * Tp + lane;
@@ -905,28 +1002,53 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                         for (int q = 0; q < Q; ++q) pp[32 * q] = acc[q];
                     }
                 }
-                bool any = false;
+                if (round == 1 || (verify | exact) == 0) break;
+                if (verify) {
 #pragma unroll
-                for (int k = 0; k < TPW; ++k) any |= open[k];
-                if (!any) break;
-                reduce_all();
+                    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                for (int k = 0; k < TPW; ++k) if (open[k]) nstep(k, round);
-                any = false;
+                        for (int k = 0; k < TPW; ++k) E1[k] += __shfl_xor_sync(0xffffffffu, E1[k], o);
+                    }
 #pragma unroll
-                for (int k = 0; k < TPW; ++k) any |= open[k];
-                if (!any) break;
+                    for (int k = 0; k < TPW; ++k) {
+                        if (!(verify >> k & 1)) continue;
+                        const float rr1 = E1[k] - Eb[k], dmu = mun[k] - mu[k];
+                        // (between checks the projection may be inexact by a fraction of the step it just took: the
+                        // multiplier is warm-started every iteration and the check iterations project exactly)
+                        const bool ok = fabsf(rr1) <= 2e-6f * (Eb[k] + 1.f) + nrel * fabsf(E[k] - Eb[k]) || (!eq && mun[k] <= 0.f && rr1 < 0.f);
+                        // secant slope of the energy equation between the two evaluations = free elements on the way
+                        const float sec = (dmu != 0.f) ? (E[k] - E1[k]) / dmu : 0.f;
+                        if (lane == 0) SESS_NF[sfk[k]] = (ok && sec >= 0.5f) ? sec : 0.f;
+                        if (!ok) exact |= 1u << k;
+                    }
+                }
+                if (!exact) break;
+                // exact search for the rows that need it (first visit, or the active set changed under the step)
+#pragma unroll
+                for (int k = 0; k < TPW; ++k) {
+                    if (!(exact >> k & 1)) continue;
+                    float lb[Q], ub[Q], vrow[Q];
+                    load_bounds(rowk[k], lb, ub);
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) vrow[q] = vget(k, q, rowk[k]);
+                    const float m0 = mu[k];
+                    mun[k] = newton_mu(vrow, lb, ub, 0, Tp, Eb[k], m0, true, 16);
+                    // slope at the solution for the next iterations
+                    int nf = 0;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) { const float w = vrow[q] - mun[k]; nf += (w > 0.f && w < ub[q]) ? 1 : 0; }
+                    nf = __reduce_add_sync(0xffffffffu, nf);
+                    if (lane == 0) SESS_NF[sfk[k]] = (float)nf;
+                }
             }
             if (lane == 0) {
 #pragma unroll
-                for (int k = 0; k < TPW; ++k) {
-                    const int* sl = SLOT + (warp * TPW + k) * 6;
-                    if (rowk[k] >= 0 && sl[5]) SESS_MU[sl[4]] = mu[k];
-                }
+                for (int k = 0; k < TPW; ++k)
+                    if (sfk[k] >= 0) SESS_MU[sfk[k]] = mun[k];
             }
         };
         if (rowWarp) {
-            if (chk) row_pass(std::true_type{});
+            if (chk) row_pass(std::true_type{});  // (a check-iteration variant of the fast pass was measured slower: its exact mode ends in the full search)
             else if (fastRows) row_pass_fast();
             else row_pass(std::false_type{});
         }
@@ -1056,7 +1178,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                         aa[q] = (t < Tp) ? ALPHA[t] + kgc * BETA[t] + HG[g * Tp + t] : 0.f;
                     }
                     for (int s = sf; s < sf + scn; ++s) {
-                        float lam = dual_lambda(aa, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], rho1 * SESS_MU[s], !MULTI);
+                        // (rows with a quadratic shortfall term keep the iterate's multiplier: any value gives a valid bound)
+                        float lam = (SESS_Q[s] > 0.f) ? rho1 * SESS_MU[s] : dual_lambda(aa, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], rho1 * SESS_MU[s], !MULTI);
                         if (lane == 0) SESS_MU2[s] = lam;
                     }
                 } else if (lane == 0) {
@@ -1078,15 +1201,34 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     }
                 }
                 if (lane == 0)
-                    for (int s = sf; s < sf + scn; ++s) dD -= (double)SESS_MU2[s] * (double)SESS_E[s];
+                    for (int s = sf; s < sf + scn; ++s) {
+                        const double m = (double)SESS_MU2[s];
+                        dD -= m * (double)SESS_E[s];
+                        // cq (Eb - E)^2 >= nu (Eb - E) - nu^2 / (4 cq): a negative multiplier m is nu = -m of that bound
+                        if (m < 0.0 && SESS_Q[s] > 0.f) dD -= m * m / (4.0 * (double)SESS_Q[s]);
+                    }
                 __syncwarp();  // SESS_MU2 is reused for the averaged candidate below
                 if (haveAvg) {
                     for (int s = sf; s < sf + scn; ++s) {
-                        float mu = newton_mu(va, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], !MULTI, 16);
+                        float mu = newton_mu(va, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], !MULTI, 16, SESS_Q[s]);
                         if (lane == 0) SESS_MU2[s] = mu;
                         __syncwarp();
                     }
                     const float mu2 = scn ? SESS_MU2[sf] : 0.f;
+                    if (hasQuad) {
+                        for (int s = sf; s < sf + scn; ++s) {
+                            if (!(SESS_Q[s] > 0.f)) continue;
+                            float Es = 0.f;
+#pragma unroll
+                            for (int q = 0; q < Q; ++q) {
+                                const int t = lane + 32 * q;
+                                if (MULTI && !(t >= SESS_A[s] && t < SESS_B[s])) continue;
+                                Es += clampf(va[q] - MU_ELEM(SESS_MU2, sf, scn, mu2, t), lb[q], ub[q]);
+                            }
+                            Es = warp_sum(Es);
+                            if (lane == 0) dPa += (double)SESS_Q[s] * (double)(SESS_E[s] - Es) * (double)(SESS_E[s] - Es);
+                        }
+                    }
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
@@ -1241,7 +1383,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
-                        if (t < Tp) v1[k][q] = VSUM[(size_t)row * Tp + t] / nsum;
+                        if (t < Tp) vset(k, q, row, VSUM[(size_t)row * Tp + t] / nsum);
                     }
                 }
             }
@@ -1271,7 +1413,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 #pragma unroll
                         for (int q = 0; q < Q; ++q) {
                             int t = lane + 32 * q;
-                            if (t < Tp) v1[k][q] = clampf(0.f, lbv(row, t), ubv(row, t));
+                            if (t < Tp) vset(k, q, row, clampf(0.f, lbv(row, t), ubv(row, t)));
                         }
                     }
                 }
@@ -1290,8 +1432,9 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
                         if (t >= Tp) continue;
-                        float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
-                        v1[k][q] = z + f * (v1[k][q] - z);
+                        const float vq = vget(k, q, row);
+                        float z = clampf(vq - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
+                        vset(k, q, row, z + f * (vq - z));
                     }
                 }
             }
@@ -1317,6 +1460,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             }
             __syncthreads();
             rho = rn; rho1 = kappa * rho; dd = 2.f * qd + rho1; inv_d = 1.f / dd;
+            set_agg();
             zero_sums();
             if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_NSUM] = 0.f; }  // the average restarts with the new metric
             build_matrix();
@@ -1334,10 +1478,13 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             const int row = rowWarp ? SLOT[(warp * TPW + k) * 6] : -1;
             if (row < 0) continue;
 #pragma unroll
-            for (int q = 0; q < Q; ++q) P.st_v1[((size_t)b * N + row) * Tp + lane + 32 * q] = v1[k][q];
+            for (int q = 0; q < Q; ++q) P.st_v1[((size_t)b * N + row) * Tp + lane + 32 * q] = vget(k, q, row);
         }
         for (int i = tid; i < R * Tp; i += nthreads) P.st_vc[(size_t)b * R * Tp + i] = VC[i];
-        for (int i = tid; i < B.S_max; i += nthreads) P.st_mu[(size_t)b * B.S_max + i] = SESS_MU[i];
+        for (int i = tid; i < B.S_max; i += nthreads) {
+            P.st_mu[(size_t)b * 2 * B.S_max + i] = SESS_MU[i];
+            P.st_mu[(size_t)b * 2 * B.S_max + B.S_max + i] = SESS_NF[i];
+        }
         float* stp = P.st_scal + (size_t)b * ACB_NSTATE;
         if (tid < 32) stp[tid] = SCAL[tid];
         else if (tid < 64) stp[tid] = sm[L.SCALD + tid - 32];
@@ -1364,7 +1511,8 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
             for (int q = 0; q < Q; ++q) {
                 int t = lane + 32 * q;
                 if (t >= Tp) continue;
-                float z = clampf(v1[k][q] - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
+                const float vq = vget(k, q, row);
+                float z = clampf(vq - MU_ELEM(SESS_MU, sl[4], sl[5], mu0, t), lbv(row, t), ubv(row, t));
                 const float rt = z * THX[t];
                 B.rates[((size_t)b * N + row) * Tp + t] = rt;
                 // fused project_into_continuous_feasible_pilots (postprocessing.py:77-94) + the final max(., 0) of schedule()
@@ -1374,7 +1522,7 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
                     pv = (mp < pv) ? mp : pv;
                     B.pilots[((size_t)b * N + row) * Tp + t] = (pv > 0.0) ? pv : 0.0;
                 }
-                if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = v1[k][q];
+                if (B.out_v1) B.out_v1[((size_t)b * N + row) * Tp + t] = vq;
             }
         }
     }
@@ -1393,11 +1541,11 @@ __global__ void __launch_bounds__(768, 1) acb_solve_kernel(const SiteDev S, cons
 
 
 // explicit launch helper used by the per-horizon translation units
-template <int Q, int TPW, bool MULTI>
+template <int Q, int TPW, bool MULTI, bool FAST>
 int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_options* opt, const SolvePhase* ph, int nthreads, size_t smem, cudaStream_t st) {
-    auto kern = acb_solve_kernel<Q, TPW, MULTI>;
+    auto kern = acb_solve_kernel<Q, TPW, MULTI, FAST>;
     ACB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const SiteDev& d = site->d;
+    const SiteDev& d = (TPW == 2) ? site->d2 : site->d;
     SmemLayout L = make_layout(d.N, d.R, d.NG, d.NP, d.nSlots, 32 * Q, batch->S_max, nthreads / 32);
     kern<<<batch->B, nthreads, smem, st>>>(d, *batch, *opt, L, *ph);
     ACB_CUDA(cudaGetLastError());
@@ -1405,7 +1553,9 @@ int acb_launch_solve_t(const acb_site* site, const acb_batch* batch, const acb_o
 }
 #define ACB_INSTANTIATE_Q(QQ)                                                                                              \
     int acb_launch_solve_q##QQ(const acb_site* site, const acb_batch* batch, const acb_options* opt, const SolvePhase* ph, \
-                               int nthreads, size_t smem, cudaStream_t st, bool multi) {                                   \
-        if (!multi) return acb_launch_solve_t<QQ, 3, false>(site, batch, opt, ph, nthreads, smem, st);                      \
-        return acb_launch_solve_t<QQ, 3, true>(site, batch, opt, ph, nthreads, smem, st);                                   \
+                               int nthreads, size_t smem, cudaStream_t st, bool multi, int fast) {                         \
+        if (multi) return acb_launch_solve_t<QQ, 3, true, false>(site, batch, opt, ph, nthreads, smem, st);                 \
+        if (fast == 2) return acb_launch_solve_t<QQ, 2, false, true>(site, batch, opt, ph, nthreads, smem, st);             \
+        if (fast) return acb_launch_solve_t<QQ, 3, false, true>(site, batch, opt, ph, nthreads, smem, st);                  \
+        return acb_launch_solve_t<QQ, 3, false, false>(site, batch, opt, ph, nthreads, smem, st);                           \
     }

@@ -107,7 +107,20 @@ class Site:
             pass
 
 
-_site_cache: Dict = {}
+# Sites are cached per (infrastructure content, problem shape, device).  The cache is a small LRU: an evicted site is
+# only dropped from the table -- batches that still hold it keep it alive, and Site.__del__ frees the device memory
+# once the last reference is gone -- so a long simulation over changing networks does not accumulate device allocations.
+SITE_CACHE_SIZE = 16
+_site_cache: "OrderedDict" = None  # created lazily (keeps `import adacharge_b200` free of side effects)
+
+
+def _cache():
+    global _site_cache
+    if _site_cache is None:
+        from collections import OrderedDict
+
+        _site_cache = OrderedDict()
+    return _site_cache
 
 
 def _infra_key(infra):
@@ -117,20 +130,53 @@ def _infra_key(infra):
     ap = getattr(infra, "allowable_pilots", None)
     apb = b"" if ap is None or any(a is None for a in ap) else b"|".join(np.asarray(a, dtype=np.float64).tobytes() for a in ap)
     mp = getattr(infra, "max_pilot", None)
+    lim = getattr(infra, "constraint_limits", None)
     return hash((
-        cmb, ph, np.asarray(infra.constraint_limits, dtype=np.float64).tobytes(),
+        cmb, ph, b"" if lim is None else np.asarray(lim, dtype=np.float64).tobytes(),
         np.asarray(infra.voltages, dtype=np.float64).tobytes(), apb,
         b"" if mp is None else np.asarray(mp, dtype=np.float64).tobytes(), tuple(infra.station_ids),
     ))
 
 
+def _cache_put(key, site):
+    c = _cache()
+    c[key] = site
+    c.move_to_end(key)
+    while len(c) > SITE_CACHE_SIZE:
+        c.popitem(last=False)
+    return site
+
+
 def get_site(infra, constraint_type="SOC", use_peak_row=False, use_agg_row=False, device=None) -> Site:
     key = (_infra_key(infra), constraint_type, bool(use_peak_row), bool(use_agg_row), _dev_index(device) if torch.cuda.is_available() else -1)
-    s = _site_cache.get(key)
+    c = _cache()
+    s = c.get(key)
     if s is None:
-        s = Site(infra, constraint_type, use_peak_row, use_agg_row, device)
-        _site_cache[key] = s
+        return _cache_put(key, Site(infra, constraint_type, use_peak_row, use_agg_row, device))
+    c.move_to_end(key)
     return s
+
+
+class _PilotsOnly:
+    """View of an infrastructure without its network rows: what the pilot projections read (postprocessing.py:92, 114)."""
+
+    def __init__(self, infra):
+        self.constraint_matrix, self.constraint_limits, self.phases = None, None, None
+        self.station_ids, self.voltages = infra.station_ids, infra.voltages
+        self.max_pilot, self.allowable_pilots = getattr(infra, "max_pilot", None), getattr(infra, "allowable_pilots", None)
+
+
+def get_post_site(infra, network=True, device=None) -> Site:
+    """Site for the postprocessing kernels: any cached site of this infrastructure carries the float64 constants they
+    need; otherwise a SOC site (network=True) or a pilots-only site (network=False, no phases required) is built."""
+    ik, dv = _infra_key(infra), _dev_index(device) if torch.cuda.is_available() else -1
+    c = _cache()
+    for key, s in reversed(c.items()):
+        if key[0] == ik and key[-1] == dv and (not network or (key[1] == "SOC" and s.M == (0 if infra.constraint_matrix is None else np.asarray(infra.constraint_matrix).shape[0]))):
+            return s
+    if network or infra.phases is not None:
+        return get_site(infra, "SOC", False, False, device)
+    return _cache_put((ik, "PILOTS", False, False, dv), Site(_PilotsOnly(infra), "SOC", False, False, device))
 
 
 # ----------------------------------------------------------------------------- packing
@@ -297,6 +343,8 @@ class PackedBatch:
         # the rate polish needs a strictly convex objective: without a quadratic term the library is told not to
         # allocate its previous-schedule scratch
         self.any_quadratic = bool(np.any(np.asarray(h["qd"]) > 0))
+        # every minimum rate 0 (the usual case): declared to the library, which then runs its fastest on-chip variant
+        self.lb_zero = not bool(np.any(np.asarray(h["min_rates"]) != 0))
         self.warm = None
         self.warm_out = None
         if want_warm_out:
@@ -320,6 +368,7 @@ class PackedBatch:
                 raise ValueError(f"refill: field {k} changed shape or dtype ({dst.shape} {dst.dtype} -> {v.shape} {v.dtype})")
             dst[...] = v
         self.any_quadratic = bool(np.any(np.asarray(h["qd"]) > 0))
+        self.lb_zero = not bool(np.any(np.asarray(h["min_rates"]) != 0))
         return self
 
     def upload(self):
@@ -335,6 +384,7 @@ class PackedBatch:
         s = self.struct
         s.B, s.Tp, s.S_max = self.B, self.Tp, self.S_max
         s.multi_session = int(self.multi_session)
+        s.lb_zero = int(self.lb_zero)
         for name in ("T", "n_sessions", "sess_row", "sess_start", "sess_len", "sess_energy", "sess_rate_off",
                      "min_rates", "max_rates", "alpha", "beta", "qd", "gamma", "ext", "peak_w", "peak_p0", "peak_limit"):
             setattr(s, name, _ptr(self.dev.get(name)))

@@ -6,7 +6,6 @@ Python: they are one-element utilities, the device twins live inside the kernels
 """
 from __future__ import annotations
 
-import bisect
 from typing import List
 
 import numpy as np
@@ -15,42 +14,39 @@ from .interface import Interface, SessionInfo, InfrastructureInfo
 from . import engine
 
 
+def _member(allowable_set, index: int):
+    """allowable_set[index] with the index clipped to the ends of the set."""
+    return allowable_set[min(max(index, 0), len(allowable_set) - 1)]
+
+
 def floor_to_set(x: float, allowable_set: np.ndarray, eps=0.05):
-    """Round x down into allowable_set; within eps of the next value rounds up (pp.py:10-31)."""
-    pos = bisect.bisect_left(allowable_set, x + eps)
-    if pos < len(allowable_set) and x == allowable_set[pos]:
+    """Round x down into allowable_set (a member within eps above x counts as reached); an exact member is returned
+    unchanged; results are clipped to the ends of the set.  Same contract as reference postprocessing.py:10-31
+    (device twin: floor_to_set in csrc/acb_post.cu)."""
+    below = int(np.searchsorted(np.asarray(allowable_set), x + eps, side="left"))  # members [0, below) are < x + eps
+    if below < len(allowable_set) and allowable_set[below] == x:
         return x
-    if pos == 0:
-        return allowable_set[0]
-    if pos == len(allowable_set):
-        return allowable_set[-1]
-    return allowable_set[pos - 1]
+    return _member(allowable_set, below - 1)
 
 
 def ceil_to_set(x: float, allowable_set: np.ndarray, eps=0.05):
-    """Round x up into allowable_set; within eps of the next lower value rounds down (pp.py:34-55)."""
-    pos = bisect.bisect_right(allowable_set, x - eps)
-    if pos > 0 and x == allowable_set[pos - 1]:
+    """Round x up into allowable_set (a member within eps below x counts as reached); reference postprocessing.py:34-55."""
+    upto = int(np.searchsorted(np.asarray(allowable_set), x - eps, side="right"))  # members [0, upto) are <= x - eps
+    if upto > 0 and allowable_set[upto - 1] == x:
         return x
-    if pos == 0:
-        return allowable_set[0]
-    if pos == len(allowable_set):
-        return allowable_set[-1]
-    return allowable_set[pos]
+    return _member(allowable_set, upto)
 
 
 def increment_in_set(x: float, allowable_set: np.ndarray):
-    """Next larger value of allowable_set, clipped to its ends (pp.py:58-74)."""
-    pos = bisect.bisect_right(allowable_set, x)
-    if pos == 0:
-        return allowable_set[0]
-    if pos == len(allowable_set):
-        return allowable_set[-1]
-    return allowable_set[pos]
+    """Smallest member strictly above x, or the largest member if there is none; reference postprocessing.py:58-74."""
+    return _member(allowable_set, int(np.searchsorted(np.asarray(allowable_set), x, side="right")))
 
 
-def _site(infrastructure) -> engine.Site:
-    return engine.get_site(infrastructure, "SOC", False, False)
+def _site(infrastructure, network=True) -> engine.Site:
+    """Device constants for postprocessing.  The projections only read max_pilot / allowable_pilots (network=False:
+    works for infrastructures without phases, like the reference); reallocation and the feasibility check need the
+    SOC rows.  Any site already built for this infrastructure (e.g. by the solve) is reused."""
+    return engine.get_post_site(infrastructure, network)
 
 
 def _back(out, like):
@@ -61,12 +57,12 @@ def _back(out, like):
 
 def project_into_continuous_feasible_pilots(rates: np.ndarray, infrastructure: InfrastructureInfo):
     """Clip every rate into [0, max_pilot of its EVSE]; dtype preserved (pp.py:77-94)."""
-    return _back(engine.project_continuous(_site(infrastructure), rates), rates)
+    return _back(engine.project_continuous(_site(infrastructure, network=False), rates), rates)
 
 
 def project_into_discrete_feasible_pilots(rates: np.ndarray, infrastructure: InfrastructureInfo):
     """floor_to_set(., allowable_pilots[i], eps=0.05) then max(., 0); dtype preserved (pp.py:97-118)."""
-    return _back(engine.project_discrete(_site(infrastructure), rates), rates)
+    return _back(engine.project_discrete(_site(infrastructure, network=False), rates), rates)
 
 
 def _session_arrays(active_sessions, infrastructure, interface):

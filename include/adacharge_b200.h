@@ -49,6 +49,7 @@ extern "C" {
 #define ACB_MAX_ITER 1   /* iteration limit hit; residuals are in stats */
 #define ACB_INFEASIBLE 2 /* primal infeasibility detected */
 #define ACB_NUMERICAL 3  /* non-finite iterate */
+#define ACB_INVALID 4    /* the instance breaks a property the caller declared (acb_batch.lb_zero) */
 
 #define ACB_NSTATS 8 /* stats row: r_prim, r_dual, rel. gap, violation, rho, cost_scale, restarts, 1 if the averaged candidate was returned */
 
@@ -99,6 +100,9 @@ typedef struct acb_options {
                           * the estimated distance of the schedule to its limit point is <= rate_tol amperes (default 3e-4; 0 = off) */
     float polish_min_qd; /* smallest cost-scaled quadratic coefficient for which the rate polish is applied (default 5e-4: the
                           * reference's 1e-12 tie-breaker does not trigger it, a 1e-3 equal_share weight does) */
+    float newton_rel;    /* on-chip hot row pass: between convergence checks a row's energy-row multiplier takes one Newton step per
+                          * iteration and is accepted if the remaining energy mismatch is at most newton_rel times the mismatch
+                          * before the step (else the exact safeguarded search runs); 0 = always exact; check iterations are exact */
     int32_t phase_iters; /* on-chip path, batches larger than one wave of SMs: first launch stops every instance after this many
                           * iterations, parks the unfinished ones and relaunches them longest-expected-first (default 100;
                           * 0 = one launch) */
@@ -110,11 +114,14 @@ void acb_default_options(acb_options* o);
  * Tp (64, 128, 160 or 288, >= every T[b]); session arrays to S_max.  Objective in
  * minimisation form per instance:
  *   sum_it (alpha_t + k_i beta_t) r_it + qd sum r_it^2 + gamma sum_t (u_t + ext_t)^2
- *   + peak_w * max(max_t u_t, peak_p0),           u_t = sum_i k_i r_it  (kW)
+ *   + peak_w * max(max_t u_t, peak_p0) + sum_s sess_quad_s (sess_energy_s - sum_{t in window_s} r_it)^2,   u_t = sum_i k_i r_it  (kW)
  */
 typedef struct acb_batch {
     int32_t B, Tp, S_max;
     int32_t multi_session;       /* 1 if any EVSE has more than one session in some instance of the batch */
+    int32_t lb_zero;             /* 1 = the caller guarantees that every minimum rate of the batch is 0 (the usual case): the on-chip
+                                  * kernel then keeps no lower-bound array and runs its fastest variant; an instance that breaks the
+                                  * promise gets status ACB_INVALID.  0 = no promise */
     const int32_t* T;            /* [B] horizon (reference: aco.py:243-245) */
     const int32_t* n_sessions;   /* [B] */
     const int32_t* sess_row;     /* [B*S_max] EVSE index */
@@ -132,6 +139,8 @@ typedef struct acb_batch {
     const float* peak_w;         /* [B] */
     const float* peak_p0;        /* [B] */
     const float* peak_limit;     /* [B*Tp] or NULL (required iff use_peak_row) */
+    const float* sess_quad;      /* [B*S_max] or NULL: per-session weight cq of the objective term cq (energy_s - sum_window r)^2 in
+                                  * (A*periods)^2 (non_completion_penalty with norm 2: coefficient * (kWh per A*period)^2) */
     /* warm start (all optional, NULL = cold).  Layout: v1 [B][N][Tp], vc [B][R][Tp],
      * mu [B][S_max], scal [B][2] = {rho, peak level}. */
     float* work;                 /* scratch [B][N+R][Tp] for the averaged state; NULL disables restarts */
@@ -162,6 +171,7 @@ int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb_options* o
 #define ACB_OBJ_DEMAND_CHARGE 5
 #define ACB_OBJ_LOAD_FLATTENING 6
 #define ACB_OBJ_NON_COMPLETION_L1 7 /* build-defined (absent from the reference): -sum_s |remaining_demand_s - E_s| */
+#define ACB_OBJ_NON_COMPLETION_L2 8 /* -sum_s (remaining_demand_s - E_s)^2 (kWh^2); needs batch->sess_quad */
 #define ACB_MAX_COMPONENTS 16
 
 typedef struct acb_sessions {      /* [B][S_max] tables, any order within an instance; station < 0 marks an empty slot */
@@ -227,6 +237,12 @@ int acb_constraints_feasible(acb_site* site, const double* rates, int B, int T, 
  * with everything admitted before it, else 0 and that EVSE goes back to 0 A. */
 int acb_min_rate_admission(acb_site* site, int B, int S_max, const int32_t* n_sessions, const int32_t* sess_row,
                            const double* try_rate, int32_t* admitted, void* stream);
+
+/* Batched preprocessing of the raw session tables, in place (reference adacharge/adacharge.py:141-146 -> acnportal's
+ * enforce_pilot_limit and apply_upper_bound_estimate): max_rate <- min(max_rate, max_pilot[EVSE]) if enforce_pilot_limit;
+ * if upper_bound ([B][S_max], device) is given, max_rate <- min(max_rate, upper_bound) and then max_rate <- min_rate where
+ * it fell below the minimum rate. */
+int acb_preprocess_sessions(acb_site* site, const acb_sessions* sessions, int enforce_pilot_limit, const double* upper_bound, void* stream);
 
 const char* acb_last_error(void);
 int acb_version(void);

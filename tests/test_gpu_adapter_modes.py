@@ -88,8 +88,18 @@ def test_offline_algorithm_solves_a_whole_day(require_gpu):
     assert out == {ev.station_id: [alg.internal_schedule[ev.station_id][30]] for ev in now}
 
 
+def _numpy_feasible(rates, infra):
+    """infrastructure_constraints_feasible in plain numpy (reference adacharge/utils.py:5-12): no device code."""
+    ph = np.deg2rad(np.asarray(infra.phases, dtype=float))
+    for j, v in enumerate(np.asarray(infra.constraint_matrix, dtype=float)):
+        a = np.stack([v * np.cos(ph), v * np.sin(ph)])
+        if not np.all(np.linalg.norm(a @ rates, axis=0) <= infra.constraint_limits[j] + 1e-7):
+            return False
+    return True
+
+
 def _reference_min_rate_loop(sessions, infra, override):
-    """The per-session loop as acnportal writes it, one feasibility call per session."""
+    """The per-session loop as acnportal writes it, one feasibility call per session, in pure numpy."""
     from copy import deepcopy
 
     queue = deepcopy(sorted(sessions, key=lambda x: x.arrival))
@@ -98,7 +108,7 @@ def _reference_min_rate_loop(sessions, infra, override):
     for s in queue:
         i = infra.get_station_index(s.station_id)
         rates[i] = min(infra.min_pilot[i], override)
-        ok = bool(ab.infrastructure_constraints_feasible(rates, infra))
+        ok = _numpy_feasible(rates, infra)
         if not ok:
             rates[i] = 0
         flags.append(ok)
@@ -137,3 +147,44 @@ def test_min_rate_admission_matches_the_sequential_loop(require_gpu, cap, overri
     flags = engine.min_rate_admission(site, [rows.shape[1]] * 3, B, np.repeat(tries, 3, 0))
     assert flags[0].tolist() == want and flags[1].tolist() == want
     assert flags[2].sum() > 0
+
+
+def test_batched_device_preprocessing_matches_the_host_helpers(require_gpu):
+    """acb_preprocess_sessions (enforce_pilot_limit + apply_upper_bound_estimate on the raw [B, S] tables, in place)
+    against the per-instance host helpers of the adapter (reference adacharge/adacharge.py:141-146)."""
+    import ctypes as C
+
+    import torch
+
+    from adacharge_b200 import _cabi, engine
+    from adacharge_b200.batched import BatchedAdaptiveCharging, sessions_to_arrays
+    from adacharge_b200.algorithms_shim import apply_upper_bound_estimate
+
+    infra = caltech_acn_infrastructure()
+    infra["max_pilot"] = np.where(np.arange(54) % 3 == 0, 16.0, 32.0)  # some EVSEs with a smaller pilot limit
+    rng = np.random.default_rng(3)
+    ifaces = [ab.TestingInterface(config_c2(90 + i, infra=infra)) for i in range(6)]
+    I = ifaces[0].infrastructure_info()
+    lists = [f.active_sessions() for f in ifaces]
+    for ss in lists:  # a few sessions with a minimum rate, so that the reconcile rule matters
+        for s in ss[::5]:
+            s.min_rates = np.full(s.remaining_time, 8.0)
+    sess = sessions_to_arrays(lists, I, S_max=54)
+    upper = rng.uniform(4.0, 40.0, size=sess["max_rate"].shape)
+
+    class Est:
+        def __init__(self, ss, row): self.m = {s.session_id: row[j] for j, s in enumerate(ss)}
+        def get_maximum_rates(self, sessions): return self.m
+
+    bac = BatchedAdaptiveCharging([ab.ObjectiveComponent(ab.quick_charge)], I, 5, batch=6, max_sessions=54, horizon=288, chunks=1,
+                                  enforce_pilot_limit=True, estimate_max_rate=True)
+    ch = bac.chunks[0]
+    bac.upload_raw(sess, upper_bound=upper)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _cabi.check(_cabi.lib().acb_preprocess_sessions(bac.site.handle, C.byref(ch.sessions), 1, engine._ptr(ch.dev_raw["upper_bound"]), st), "pre")
+    got = ch.dev_raw["max_rate"].cpu().numpy()
+    for b, ss in enumerate(lists):
+        want = apply_upper_bound_estimate(Est(ss, upper[b]), enforce_pilot_limit(ss, I))
+        for j, s in enumerate(want):
+            assert np.all(s.max_rates == got[b, j]), (b, j, s.max_rates[:2], got[b, j])
+    assert (got[sess["station"] < 0] == 0).all()
