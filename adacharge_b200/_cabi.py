@@ -17,7 +17,7 @@ ACB_NSTATS = 8
 EXPORTS = [
     "acb_site_create", "acb_site_destroy", "acb_site_dims", "acb_site_max_horizon", "acb_default_options",
     "acb_solve_batch", "acb_charging_rate_bounds", "acb_project_continuous", "acb_project_discrete",
-    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_pack_sessions", "acb_preprocess_sessions", "acb_last_error", "acb_version",
+    "acb_reallocate", "acb_constraints_feasible", "acb_min_rate_admission", "acb_pack_sessions", "acb_preprocess_sessions", "acb_fleet_sessions", "acb_fleet_apply", "acb_last_error", "acb_version",
 ]
 ACB_MAX_COMPONENTS = 16
 # acb_objective.kind values (include/adacharge_b200.h)
@@ -31,7 +31,7 @@ class NativeLibraryMissing(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [
-        ("eps_abs", C.c_float), ("eps_rel", C.c_float), ("viol_tol", C.c_float), ("rho0", C.c_float),
+        ("eps_abs", C.c_float), ("eps_rel", C.c_float), ("viol_tol", C.c_float), ("viol_abs", C.c_float), ("rho0", C.c_float),
         ("kappa", C.c_float), ("alpha", C.c_float), ("max_iter", C.c_int32), ("check_every", C.c_int32),
         ("equality", C.c_int32), ("adapt_rho", C.c_int32), ("restart", C.c_int32), ("avg_every", C.c_int32), ("stall_checks", C.c_int32), ("max_rescues", C.c_int32), ("path", C.c_int32), ("stall_exit", C.c_int32), ("dual_refine", C.c_int32), ("term_floor", C.c_float), ("rho_curv", C.c_float),
         ("rate_tol", C.c_float), ("polish_min_qd", C.c_float), ("newton_rel", C.c_float), ("phase_iters", C.c_int32),
@@ -48,7 +48,7 @@ class Batch(C.Structure):
         ("sess_energy", _P), ("sess_rate_off", _P), ("min_rates", _P), ("max_rates", _P),
         ("alpha", _P), ("beta", _P), ("qd", _P), ("gamma", _P), ("ext", _P), ("peak_w", _P), ("peak_p0", _P),
         ("peak_limit", _P), ("sess_quad", _P), ("work", _P),
-        ("warm_v1", _P), ("warm_vc", _P), ("warm_mu", _P), ("warm_scal", _P),
+        ("warm_v1", _P), ("warm_vc", _P), ("warm_mu", _P), ("warm_scal", _P), ("warm_shift", C.c_int32), ("warm_had", _P),
         ("out_v1", _P), ("out_vc", _P), ("out_mu", _P), ("out_scal", _P),
         ("rates", _P), ("pilots", _P), ("rate_est", _P), ("status", _P), ("iters", _P), ("stats", _P),
     ]
@@ -64,6 +64,11 @@ class Objective(C.Structure):
                 ("param", C.c_double * ACB_MAX_COMPONENTS), ("period", C.c_double), ("prices", _P), ("prices_stride", C.c_int32),
                 ("prev_peak", _P), ("demand_charge", _P), ("demand_charge_scalar", C.c_double), ("external_signal", _P),
                 ("ext_stride", C.c_int32), ("peak_limit", _P), ("pl_stride", C.c_int32)]
+
+
+class Fleet(C.Structure):
+    _fields_ = [("n_sites", C.c_int32), ("n_ev", C.c_int32), ("days", C.c_int32), ("steps_per_day", C.c_int32), ("ev_station", _P), ("ev_arr", _P),
+                ("ev_dep", _P), ("ev_req", _P), ("ev_max", _P), ("ev_dlv", _P), ("ev_mu", _P), ("day_site_off", _P), ("prev_peak", _P), ("had", _P)]
 
 
 _lib = None
@@ -95,6 +100,8 @@ def lib():
     L.acb_constraints_feasible.argtypes = [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]
     L.acb_min_rate_admission.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]
     L.acb_preprocess_sessions.argtypes = [_P, C.POINTER(Sessions), C.c_int, _P, _P]
+    L.acb_fleet_sessions.argtypes = [_P, C.POINTER(Fleet), C.c_int, C.POINTER(Sessions), _P, _P, _P]
+    L.acb_fleet_apply.argtypes = [_P, C.POINTER(Fleet), C.c_int, C.c_double, C.POINTER(Batch), _P, _P, _P, _P]
     L.acb_pack_sessions.argtypes = [_P, C.POINTER(Sessions), C.POINTER(Objective), C.POINTER(Batch), _P, _P]
     _lib = L
     return L

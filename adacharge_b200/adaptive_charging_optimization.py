@@ -100,7 +100,7 @@ def non_completion_penalty(rates, infrastructure, interface, norm=1, **kwargs):
     -sum_s |remaining_demand_s - E_s(rates)| (kWh) over ``interface.active_sessions()``,
     E_s = energy planned inside the session window.  Under the energy rows
     E_s <= remaining_demand_s this is linear in rates.  ``norm=2`` (sum of squares) is
-    accepted by the numeric function and by the oracle, not yet by the device solver."""
+    is the sum of squares instead (a quadratic in each session's planned energy)."""
     R = np.asarray(rates, dtype=float)
     tot = 0.0
     for s in interface.active_sessions():
@@ -148,9 +148,13 @@ def _spec_load_flattening(infra, interface, T, external_signal=None, **kw):
 
 
 def _spec_ncp(infra, interface, T, norm=1, **kw):
-    if norm != 1:
-        raise NotImplementedError("non_completion_penalty(norm=2) is not implemented on the device path yet")
-    return dict(beta=-np.full(T, interface.period / 60))
+    if norm == 1:
+        return dict(beta=-np.full(T, interface.period / 60))
+    if norm == 2:
+        # -sum_s (remaining_demand_s - E_s)^2: a quadratic in each session's planned energy, handled by the solver as
+        # "soft" energy rows (weight per session: coefficient * (kWh per A*period of its EVSE)^2, see build_instance)
+        return dict(ncp2=1.0)
+    raise ValueError("non_completion_penalty: norm must be 1 or 2")
 
 
 _SPECS = {
@@ -168,7 +172,7 @@ _SPECS = {
 def pack_objective(objective: List[ObjectiveComponent], infrastructure, interface, T, **caller_kwargs) -> dict:
     """build_objective (aco.py:200-218) into packed form; component kwargs override
     caller kwargs (aco.py:203-217)."""
-    out = dict(alpha=np.zeros(T), beta=np.zeros(T), qd=0.0, gamma=0.0, ext=None, peak_w=0.0, peak_p0=0.0)
+    out = dict(alpha=np.zeros(T), beta=np.zeros(T), qd=0.0, gamma=0.0, ext=None, peak_w=0.0, peak_p0=0.0, ncp2=0.0)
     ext_acc = np.zeros(T)
     peaks = []
     for comp in objective:
@@ -193,6 +197,10 @@ def pack_objective(objective: List[ObjectiveComponent], infrastructure, interfac
                 raise ValueError("load_flattening with a negative coefficient is not concave")
             out["gamma"] += g
             ext_acc += g * np.asarray(sp.get("ext", np.zeros(T)), dtype=float)
+        if "ncp2" in sp:
+            if coef * sp["ncp2"] < 0:
+                raise ValueError("non_completion_penalty with a negative coefficient is not concave")
+            out["ncp2"] += coef * sp["ncp2"]
         if "peak_w" in sp:
             w = coef * sp["peak_w"]
             if w < 0:
@@ -306,11 +314,16 @@ class AdaptiveChargingOptimization:
             pl = np.broadcast_to(np.asarray(peak_limit, dtype=float), (T,)).copy() if np.ndim(peak_limit) == 0 else np.asarray(peak_limit, dtype=float)[:T]
             if len(pl) < T:
                 raise ValueError("peak_limit is shorter than the optimisation horizon")
+        sq = None
+        if ob.get("ncp2", 0.0) > 0:
+            volt = np.asarray(infrastructure.voltages, dtype=np.float64)
+            w = volt[np.array(ps["sess_row"], dtype=int)] * self.interface.period / 1e3 / 60  # kWh per A*period
+            sq = ob["ncp2"] * w * w
         return engine.Instance(
             T=T, sess_row=np.array(ps["sess_row"]), sess_start=np.array(ps["sess_start"]), sess_len=np.array(ps["sess_len"]),
             sess_energy=np.array(ps["sess_energy"]), min_rates=ps["min_rates"], max_rates=ps["max_rates"],
             alpha=ob["alpha"], beta=ob["beta"], qd=ob["qd"], gamma=ob["gamma"], ext=ob["ext"],
-            peak_w=ob["peak_w"], peak_p0=ob["peak_p0"], peak_limit=pl, sess_order=ps["order"],
+            peak_w=ob["peak_w"], peak_p0=ob["peak_p0"], peak_limit=pl, sess_order=ps["order"], sess_quad=sq,
         )
 
     def build_problem(self, active_sessions, infrastructure, peak_limit=None, prev_peak: float = 0):

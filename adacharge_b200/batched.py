@@ -43,8 +43,8 @@ def objective_components(objective: Sequence[aco.ObjectiveComponent]):
             raise TypeError(f"objective component {getattr(comp.function, '__name__', comp.function)!r} cannot be packed on the device; "
                             f"built-ins are {sorted(_KIND_OF.values())} (use AdaptiveChargingOptimization for custom components)")
         kw = comp.kwargs or {}
-        if name == "non_completion_penalty" and kw.get("norm", 1) != 1:
-            raise NotImplementedError("non_completion_penalty(norm=2) is not available in the batched device packer")
+        if name == "non_completion_penalty" and kw.get("norm", 1) == 2:
+            name = "non_completion_penalty_l2"
         if name == "load_flattening" and kw.get("external_signal") is not None:
             raise ValueError("pass external_signal to schedule() (one row per instance), not as a component kwarg")
         out.append((_cabi.OBJ_KIND[name], float(comp.coefficient), float(kw.get("baseline_peak", 0.0))))
@@ -97,6 +97,8 @@ class _Chunk:
             d["ext"] = mk((B, Tp), f32)
         if owner.site.use_peak_row:
             d["peak_limit"] = mk((B, Tp), f32)
+        if owner.need_sess_quad:
+            d["sess_quad"] = mk((B, S), f32)
         self.packed = d
         self.rates = mk((B, N, Tp), f32)
         self.pilots = mk((B, N, Tp), torch.float64)
@@ -168,6 +170,7 @@ class BatchedAdaptiveCharging:
         self.need_prices = K["tou_energy_cost"] in kinds
         self.need_ext = K["load_flattening"] in kinds
         self.need_dc_array = bool(per_instance_demand_charge)
+        self.need_sess_quad = K["non_completion_penalty_l2"] in kinds
         # preprocessing of schedule() (ada.py:141-146) on the device: max_rate <- min(max_rate, max_pilot) and, with
         # estimate_max_rate, the estimator's per-session upper bounds (passed to schedule() as `upper_bound`)
         self.enforce_pilot_limit, self.estimate_max_rate = bool(enforce_pilot_limit), bool(estimate_max_rate)

@@ -41,6 +41,7 @@ __global__ void acb_pack_kernel(SiteDev S, acb_sessions X, acb_objective O, acb_
     int32_t* o_off = const_cast<int32_t*>(B.sess_rate_off) + base;
     float* o_min = const_cast<float*>(B.min_rates) + base;
     float* o_max = const_cast<float*>(B.max_rates) + base;
+    float* o_sq = B.sess_quad ? const_cast<float*>(B.sess_quad) + base : nullptr;
     for (int s = tid; s < Sm; s += nt) {
         const int k = key[s];
         if (k == 0x7fffffff) continue;
@@ -57,8 +58,14 @@ __global__ void acb_pack_kernel(SiteDev S, acb_sessions X, acb_objective O, acb_
         o_off[rank] = -(int)(base + rank + 1);
         o_min[rank] = (float)X.min_rate[base + s];
         o_max[rank] = (float)fmin(X.max_rate[base + s], 3.0e38);
+        if (o_sq) {  // non_completion_penalty, norm 2: coefficient * (kWh per A*period)^2 per session
+            double c2 = 0.0;
+            for (int c = 0; c < O.n; ++c)
+                if (O.kind[c] == ACB_OBJ_NON_COMPLETION_L2) c2 += O.coef[c] * 1.0;
+            o_sq[rank] = (float)(c2 * w * w);
+        }
     }
-    for (int s = n + tid; s < Sm; s += nt) { o_row[s] = 0; o_start[s] = 0; o_len[s] = 0; o_en[s] = 0.f; o_off[s] = -(int)(base + s + 1); o_min[s] = 0.f; o_max[s] = 0.f; }
+    for (int s = n + tid; s < Sm; s += nt) { o_row[s] = 0; o_start[s] = 0; o_len[s] = 0; o_en[s] = 0.f; o_off[s] = -(int)(base + s + 1); o_min[s] = 0.f; o_max[s] = 0.f; if (o_sq) o_sq[s] = 0.f; }
     __syncthreads();
     if (tid == 0) {
         const_cast<int32_t*>(B.T)[b] = T;
@@ -136,6 +143,10 @@ extern "C" int acb_pack_sessions(acb_site* site, const acb_sessions* sessions, c
         if (k == ACB_OBJ_TOU_ENERGY_COST && !objective->prices) { acb_set_error("acb_pack_sessions: tou_energy_cost needs prices"); return ACB_E_INVALID; }
         if (k == ACB_OBJ_EQUAL_SHARE || k == ACB_OBJ_LOAD_FLATTENING) {
             if (objective->coef[c] < 0) { acb_set_error("acb_pack_sessions: equal_share / load_flattening with a negative coefficient is not concave"); return ACB_E_INVALID; }
+        }
+        if (k == ACB_OBJ_NON_COMPLETION_L2 && (!batch->sess_quad || objective->coef[c] < 0)) {
+            acb_set_error("acb_pack_sessions: non_completion_penalty (norm 2) needs batch.sess_quad and a non-negative coefficient");
+            return ACB_E_INVALID;
         }
         if ((k == ACB_OBJ_PEAK && objective->coef[c] > 0) || (k == ACB_OBJ_DEMAND_CHARGE && objective->coef[c] < 0)) {
             acb_set_error("acb_pack_sessions: peak / demand_charge with this sign is not concave (cvxpy would raise a DCP error)");

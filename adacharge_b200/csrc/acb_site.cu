@@ -20,6 +20,7 @@ extern "C" void acb_default_options(acb_options* o) {
     o->eps_abs = 1e-5f;
     o->eps_rel = 1e-4f;
     o->viol_tol = 1e-5f;
+    o->viol_abs = 1e-3f;
     o->rho0 = 0.07f;
     o->kappa = 0.7f;
     o->alpha = 1.8f;

@@ -45,8 +45,9 @@ __device__ __forceinline__ void atomic_max_pos(float* addr, float v) {  // v >= 
 }
 
 // per-instance scalars
-enum { GS_RHO = 0, GS_PLEVEL, GS_CS, GS_QD, GS_GAMMA, GS_PKW, GS_PKP0, GS_E1, GS_E2, GS_XMAX, GS_YMAX, GS_VIOL, GS_UMAX, GS_ZUMAX, GS_GAP, GS_RP, GS_RD, GS_N };
-enum { GD_P = 0, GD_D, GD_UQ, GD_DBEST, GD_PMAX, GD_N };
+enum { GS_RHO = 0, GS_PLEVEL, GS_CS, GS_QD, GS_GAMMA, GS_PKW, GS_PKP0, GS_E1, GS_E2, GS_XMAX, GS_YMAX, GS_VIOL, GS_UMAX, GS_ZUMAX, GS_GAP, GS_RP, GS_RD,
+       GS_STALL, GS_NRESCUE, GS_NFEAS, GS_BESTVIOL, GS_VSTALL, GS_N };
+enum { GD_P = 0, GD_D, GD_UQ, GD_DBEST, GD_PMAX, GD_BESTGAP, GD_N };
 
 struct GenWork {
     float *V, *LB, *UB, *VC, *KX, *SG, *SGZ, *HG, *MU, *AL, *BE;  // AL/BE: cost-scaled alpha, beta [B][Tp]
@@ -165,26 +166,34 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
         // (2 Gamma u^2 with u = su * (Khat r)_u): at rho ~ Gamma su^2 the row's prox is balanced; a 1000-EVSE
         // load-flattening instance goes from > 1000 iterations at rho0 to the first check
         const float su0 = D.has_u ? S.row_scale[D.rU] : 0.f;
-        sc[GS_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : fmaxf(opt.rho0, opt.rho_curv * B.gamma[b] * cs * su0 * su0);
-        sc[GS_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
+        const bool hadW0 = !B.warm_had || B.warm_had[b] != 0;
+        sc[GS_RHO] = (B.warm_scal && hadW0 && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2] : fmaxf(opt.rho0, opt.rho_curv * B.gamma[b] * cs * su0 * su0);
+        sc[GS_PLEVEL] = B.warm_scal ? fmaxf(hadW0 ? B.warm_scal[b * 2 + 1] : 0.f, B.peak_p0[b]) : B.peak_p0[b];
         sc[GS_CS] = cs;
         sc[GS_QD] = B.qd[b] * cs; sc[GS_GAMMA] = B.gamma[b] * cs; sc[GS_PKW] = B.peak_w[b] * cs; sc[GS_PKP0] = B.peak_p0[b];
         sc[GS_E1] = sc[GS_E2] = sc[GS_XMAX] = sc[GS_YMAX] = sc[GS_VIOL] = sc[GS_UMAX] = sc[GS_ZUMAX] = sc[GS_GAP] = sc[GS_RP] = sc[GS_RD] = 0.f;
         double* da = W.dacc + (size_t)b * GD_N;
         da[GD_P] = da[GD_D] = da[GD_UQ] = 0.0;
         da[GD_DBEST] = -1.0e300;
+        da[GD_BESTGAP] = 1.0e300;
+        sc[GS_STALL] = 0.f; sc[GS_NRESCUE] = 0.f; sc[GS_NFEAS] = 0.f; sc[GS_BESTVIOL] = 3.0e38f; sc[GS_VSTALL] = 0.f;
         W.status[b] = infeas ? ACB_INFEASIBLE : -1;
         W.iters[b] = 0;
         if (infeas) atomicAdd(W.ndone, 1);
     }
     // state
+    // (warm_shift / warm_had: see the on-chip kernel)
+    const int wsh = B.warm_shift;
+    const bool hadW = !B.warm_had || B.warm_had[b] != 0;
     for (int i = tid; i < D.N * Tp; i += blockDim.x) {
         size_t k = (size_t)b * D.N * Tp + i;
-        W.V[k] = B.warm_v1 ? B.warm_v1[k] : clampf(0.f, W.LB[k], W.UB[k]);
+        const int t = i % Tp;
+        W.V[k] = B.warm_v1 ? ((hadW && t + wsh < Tp) ? B.warm_v1[k + wsh] : 0.f) : clampf(0.f, W.LB[k], W.UB[k]);
     }
     for (int i = tid; i < D.R * Tp; i += blockDim.x) {
         size_t k = (size_t)b * D.R * Tp + i;
-        W.VC[k] = B.warm_vc ? B.warm_vc[k] : 0.f;
+        const int t = i % Tp;
+        W.VC[k] = (B.warm_vc && hadW && t + wsh < Tp) ? B.warm_vc[k + wsh] : 0.f;
         W.KX[k] = 0.f;
     }
 }
@@ -445,6 +454,8 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
     };
     double dconj = 0.0, duq = 0.0;
     float viol = -1.f, umax = 0.f, zumax = 0.f;
+    // (excess allowed on a row of L amperes: min(viol_tol L, viol_abs); see eval_columns of the on-chip kernel)
+    auto vfac = [&](float lim_amps) -> float { return (opt.viol_abs > 0.f) ? fmaxf(1.f, lim_amps * opt.viol_tol / opt.viol_abs) : 1.f; };
     for (int i = tid; i < (Rp - R) * TW; i += blockDim.x) { bv[R * TW + i] = 0.f; y1[R * TW + i] = 0.f; }
     // ---- stage 1: inputs (columns beyond Tp read as zero and are never written back)
     for (int g = warp; g < NG; g += nw) {
@@ -511,7 +522,8 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
 #pragma unroll
             for (int c = 0; c < CPL; ++c) {
                 float ka = bv[(2 * j) * TW + 32 * c + lane], kb = bv[(2 * j + 1) * TW + 32 * c + lane];
-                if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f);
+                if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, (sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f) * vfac(S.lim[2 * j] * S.row_scale[2 * j]));
+                else viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) * S.row_scale[2 * j]);  // limit 0: the current itself, in amperes
             }
         for (int r = 2 * D.nDisc + warp; r < 2 * D.nDisc + D.nLin + D.has_pl; r += nw)
 #pragma unroll
@@ -520,7 +532,8 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
                 float ka = bv[r * TW + 32 * c + lane];
                 float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
                 if (r < 2 * D.nDisc + D.nLin && D.lin_two_sided) ka = fabsf(ka);
-                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, ka / cap - 1.f);
+                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, (ka / cap - 1.f) * vfac(cap * S.row_scale[r]));
+                else if (cap <= 0.f) viol = fmaxf(viol, fmaxf(ka, 0.f) * S.row_scale[r]);
             }
         if (D.has_u && warp == 0)
 #pragma unroll
@@ -704,7 +717,27 @@ __global__ void k_decide(acb_batch B, acb_options opt, GenWork W, GenDims D, int
     else if (Dbest > da[GD_PMAX] + 1e-3 * (fabs(da[GD_PMAX]) + 1.0)) st = ACB_INFEASIBLE;  // dual bound above the box maximum
     else if (gap <= tol && viol <= opt.viol_tol) st = ACB_SOLVED;  // a slightly negative gap is rounding noise and passes
     else if (last) st = ACB_MAX_ITER;
-    else if (opt.adapt_rho) {
+    else if (opt.stall_checks > 0 && sc[GS_NRESCUE] < (float)(opt.max_rescues > 0 ? 1 : 0) &&
+             ((fmax(gap, 0.1 * tol) < 0.9 * da[GD_BESTGAP]) ? (da[GD_BESTGAP] = fmax(gap, 0.1 * tol), sc[GS_STALL] = 0.f, false)
+                                                          : ((sc[GS_STALL] += 1.f) >= (float)opt.stall_checks))) {
+        // stagnation rescue as in the on-chip kernel: the gap has not improved by 10 % over stall_checks checks -> one
+        // stiffer penalty, v and the multipliers rescaled so that y is kept
+        const float rn = fminf(fmaxf(rho * 3.f, 1e-4f), 1e4f);
+        ratio_out = rho / rn;
+        sc[GS_RHO] = rn;
+        sc[GS_NRESCUE] += 1.f;
+        sc[GS_STALL] = 0.f;
+        da[GD_BESTGAP] = 1.0e300;
+    } else if (gap <= tol && opt.stall_checks > 0 && sc[GS_NFEAS] < 3.f &&
+               ((viol < 0.9f * sc[GS_BESTVIOL]) ? (sc[GS_BESTVIOL] = viol, sc[GS_VSTALL] = 0.f, false) : ((sc[GS_VSTALL] += 1.f) >= (float)opt.stall_checks))) {
+        // feasibility rescue: gap certified, violation no longer shrinking -> stiffer penalty (up to three times)
+        const float rn = fminf(fmaxf(rho * 3.f, 1e-4f), 1e4f);
+        ratio_out = rho / rn;
+        sc[GS_RHO] = rn;
+        sc[GS_NFEAS] += 1.f;
+        sc[GS_VSTALL] = 0.f; sc[GS_BESTVIOL] = 3.0e38f; sc[GS_STALL] = 0.f;
+        da[GD_BESTGAP] = 1.0e300;
+    } else if (opt.adapt_rho) {
         float ratio = sqrtf(fmaxf(rp_rel, 1e-12f) / fmaxf(rd_rel, 1e-12f));
         if (ratio > 5.f || ratio < 0.2f) {
             float rn = fminf(fmaxf(rho * ratio, 1e-4f), 1e4f);

@@ -111,7 +111,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 
 // float scalars
 enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE,
-       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST, SC_UBVAR };
+       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST, SC_UBVAR, SC_NFEAS, SC_BESTVIOL, SC_VSTALL };
 // double scalars
 enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP, SD_PMAX };
 // per-warp float reduction slots (max-type)
@@ -212,8 +212,13 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
 
     // ------------------------------------------------------------------ prologue
     for (int i = tid; i < 2 * N * Tp; i += nthreads) LB[i] = 0.f;  // LB (FAST: v) and UB are contiguous
+    // warm start of a closed-loop replay: the previous step's state is read `warm_shift` columns ahead (column t of this
+    // problem was column t + 1 of the previous one), and instances whose site was idle before start cold (warm_had)
+    const int wsh = B.warm_shift;
+    const bool hadW = !B.warm_had || B.warm_had[b] != 0;
     for (int i = tid; i < R * Tp; i += nthreads) {
-        VC[i] = B.warm_vc ? B.warm_vc[(size_t)b * R * Tp + i] : 0.f;
+        const int t = i % Tp;
+        VC[i] = (B.warm_vc && hadW && t + wsh < Tp) ? B.warm_vc[(size_t)b * R * Tp + i + wsh] : 0.f;
         VOUT[i] = 0.f;
     }
     for (int i = tid; i < R * NG; i += nthreads) CS[i] = S.C[i];
@@ -328,9 +333,9 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
         // cold start: rho0, raised to the curvature of the aggregate quadratic seen through the scaled aggregate row
         // (see acb_solve_general.cu: k_setup)
         const float su0 = S.has_u ? S.row_scale[rU] : 0.f;
-        SCAL[SC_RHO] = (B.warm_scal && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2]
-                                                                   : fmaxf(opt.rho0, opt.rho_curv * B.gamma[b] * SCAL[SC_CS] * su0 * su0);
-        SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(B.warm_scal[b * 2 + 1], B.peak_p0[b]) : B.peak_p0[b];
+        SCAL[SC_RHO] = (B.warm_scal && hadW && B.warm_scal[b * 2] > 0.f) ? B.warm_scal[b * 2]
+                                                                           : fmaxf(opt.rho0, opt.rho_curv * B.gamma[b] * SCAL[SC_CS] * su0 * su0);
+        SCAL[SC_PLEVEL] = B.warm_scal ? fmaxf(hadW ? B.warm_scal[b * 2 + 1] : 0.f, B.peak_p0[b]) : B.peak_p0[b];
         SCAL[SC_FLAG] = 0.f;
         SCAL[SC_NSUM] = 0.f;
         SCAL[SC_NREST] = 0.f;
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
         SCAL[SC_NRESCUE] = 0.f;
         SCAL[SC_RHOSTART] = SCAL[SC_RHO];
         SCAL[SC_DZ] = 0.f; SCAL[SC_KAP] = 1.f; SCAL[SC_NDZ] = 0.f; SCAL[SC_RATE_EST] = -1.f;
+        SCAL[SC_NFEAS] = 0.f; SCAL[SC_BESTVIOL] = 3.0e38f; SCAL[SC_VSTALL] = 0.f;
     }
     __syncthreads();
     const float cs = SCAL[SC_CS];
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
             float v = 0.f;
             if (row >= 0) {
                 if (P.resume) v = P.st_v1[((size_t)b * N + row) * Tp + t];
-                else if (B.warm_v1) v = B.warm_v1[((size_t)b * N + row) * Tp + t];
+                else if (B.warm_v1) v = (hadW && t + wsh < Tp) ? B.warm_v1[((size_t)b * N + row) * Tp + t + wsh] : 0.f;
                 else v = clampf(0.f, lbv(row, t), ubv(row, t));
                 vset(k, q, row, v);
             }
@@ -713,6 +719,10 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
     };
     // column evaluation of a candidate whose group partial sums are in PART: relative coupling
     // violation, max and quadratic part of the aggregate power; optionally HG <- C' yc (yc in VOUT)
+    // a row whose limit is 0 (a de-rated line, a curtailment period) has no relative violation: any current above 1e-5 A
+    // counts.  With restoration the whole period is scaled to (numerically) zero; without it the violation is the
+    // current in amperes, measured against viol_tol like the relative ones.
+    auto zero_limit = [&](float amps) -> float { return canRestore ? (amps > 1e-5f ? 1.0e30f : 0.f) : 1.f + amps; };
     auto eval_columns = [&](bool with_hy, float* TH, float& viol, float& umax, double& uq, double& plin) {
         viol = -1.f; umax = -3.0e38f; uq = 0.0; plin = 0.0;
         for (int t = tid; t < Tp; t += nthreads) {
@@ -724,22 +734,31 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
                 pcol += (ALPHA[t] + KG[g] * BETA[t]) * sz;  // linear cost of the period (same coefficient within a group)
             }
             float worst = 0.f;  // worst current / limit of the period
+            float vmax = -1.f;  // worst excess in units of the row's tolerance: relative, tightened to viol_abs amperes on large limits
+            // a row with limit L amperes may exceed it by min(viol_tol L, viol_abs): the relative excess is scaled up where
+            // viol_abs (1e-3 A, the bar of the reference's own tests) is the tighter of the two
+            auto vfac = [&](float lim_amps) -> float { return (opt.viol_abs > 0.f) ? fmaxf(1.f, lim_amps * opt.viol_tol / opt.viol_abs) : 1.f; };
             int r = 0;
             for (int j = 0; j < nDisc; ++j, r += 2) {
                 float ka = 0.f, kb = 0.f;
                 for (int g = 0; g < NG; ++g) { float sz = HG[g * Tp + t]; ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz; }
-                if (LIM[r] > 0.f) worst = fmaxf(worst, sqrtf(ka * ka + kb * kb) / LIM[r]);
+                const float cur = sqrtf(ka * ka + kb * kb);
+                float ratio;
+                if (LIM[r] > 0.f) { ratio = cur / LIM[r]; vmax = fmaxf(vmax, (ratio - 1.f) * vfac(LIM[r] * SCALE[r])); }
+                else { ratio = zero_limit(cur * SCALE[r]); vmax = fmaxf(vmax, ratio - 1.f); }
+                worst = fmaxf(worst, ratio);
             }
             for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
                 float ka = 0.f;
                 for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
                 float cap = (j == nLin) ? PLIM[t] : LIM[r];
                 if (j < nLin && S.lin_two_sided) ka = fabsf(ka);
-                if (cap > 0.f && cap < 1.0e30f) worst = fmaxf(worst, ka / cap);
+                if (cap > 0.f && cap < 1.0e30f) { const float ratio = ka / cap; worst = fmaxf(worst, ratio); vmax = fmaxf(vmax, (ratio - 1.f) * vfac(cap * SCALE[r])); }
+                else if (cap <= 0.f) { const float ratio = zero_limit(fmaxf(ka, 0.f) * SCALE[r]); worst = fmaxf(worst, ratio); vmax = fmaxf(vmax, ratio - 1.f); }
             }
             const float th = (canRestore && worst > 1.f) ? 1.f / (worst * (1.f + 2e-7f)) : 1.f;
             TH[t] = th;
-            viol = fmaxf(viol, worst * th - 1.f);
+            viol = fmaxf(viol, th < 1.f ? worst * th - 1.f : vmax);
             plin += (double)(th * pcol);
             if (S.has_u && t < Tb) {
                 float ka = 0.f;
@@ -1321,14 +1340,18 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
             else if (certC) {
                 // only the rate polish is pending: no restarts, rescues or penalty changes (each would reset its history)
             } else {
-                if (haveAvg && gapA <= 0.5 * SCALD[SD_GAPRESTART] && vA <= fmaxf(vC, opt.viol_tol) + 1e-3f) {
+                // (once the averaged gap is inside the tolerance only the violation is pending: restarting on the noise of
+                // a converged gap would keep resetting the stall counter and block the penalty rescue)
+                if (haveAvg && gapA <= 0.5 * SCALD[SD_GAPRESTART] && SCALD[SD_GAPRESTART] > tolA && vA <= fmaxf(vC, opt.viol_tol) + 1e-3f) {
                     SCALD[SD_GAPRESTART] = gapA;
                     flag = 5.f;
                 }
                 // stagnation rescue: the best gap has not improved by 10 % over `stall_checks` checks ->
                 // change the penalty once to 3x and, if that stalls too, once to 1/3 of the start value
                 {
-                    const double gbest = fmin(gapC, haveAvg ? gapA : gapC);
+                    // (a gap below a tenth of the tolerance has nothing left to gain: its rounding noise must not keep
+                    // resetting the stall counter while only the violation is pending)
+                    const double gbest = fmax(fmin(gapC, haveAvg ? gapA : gapC), 0.1 * tolC);
                     if (gbest < 0.9 * SCALD[SD_BESTGAP]) { SCALD[SD_BESTGAP] = gbest; SCAL[SC_STALL] = 0.f; }
                     else SCAL[SC_STALL] += 1.f;
                     // 1st rescue: a stiffer penalty (x3).  2nd, only for warm-started solves: drop the inherited state and
@@ -1344,6 +1367,18 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
                         SCALD[SD_BESTGAP] = 1.0e300;
                         SCALD[SD_GAPRESTART] = 1.0e300;
                         flag = cold ? 11.f : 10.f;
+                    } else if (flag == 0.f && gapC <= tolC && opt.stall_checks > 0 && SCAL[SC_NFEAS] < 3.f &&
+                               ((vC < 0.9f * SCAL[SC_BESTVIOL]) ? (SCAL[SC_BESTVIOL] = vC, SCAL[SC_VSTALL] = 0.f, false)
+                                                               : ((SCAL[SC_VSTALL] += 1.f) >= (float)opt.stall_checks))) {
+                        // feasibility rescue: the gap is certified but the coupling violation of a candidate that cannot be
+                        // restored by scaling (minimum rates, quadratic terms, equality rows) no longer shrinks: a stiffer
+                        // penalty drives the primal residual down (up to three times)
+                        SCAL[SC_NEWRHO] = fminf(fmaxf(rho * 3.f, 1e-4f), 1e4f);
+                        SCAL[SC_NFEAS] += 1.f;
+                        SCAL[SC_VSTALL] = 0.f; SCAL[SC_BESTVIOL] = 3.0e38f; SCAL[SC_STALL] = 0.f;
+                        SCALD[SD_BESTGAP] = 1.0e300;
+                        SCALD[SD_GAPRESTART] = 1.0e300;
+                        flag = 10.f;
                     } else if (flag == 0.f && opt.stall_exit > 0 && SCAL[SC_STALL] >= (float)opt.stall_exit && !canRescue) {
                         flag = 2.f;  // stalled for good: stop with the best certified gap so far (status ACB_MAX_ITER)
                     }

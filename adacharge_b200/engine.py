@@ -202,6 +202,7 @@ class Instance:
     peak_p0: float = 0.0
     peak_limit: Optional[np.ndarray] = None
     sess_order: Optional[np.ndarray] = None  # packed position -> index in the caller's session list
+    sess_quad: Optional[np.ndarray] = None   # per-session weight of (energy - planned)^2 in (A*periods)^2 (non_completion_penalty, norm 2)
 
 
 def pack_sessions(sessions, infra, period) -> dict:
@@ -300,6 +301,12 @@ class PackedBatch:
                 if inst.ext is not None:
                     a[b, : inst.T] = inst.ext[: inst.T]
             h["ext"] = a
+        if any(i.sess_quad is not None for i in instances):
+            a = np.zeros((B, S_), dtype=f32)
+            for b, inst in enumerate(instances):
+                if inst.sess_quad is not None:
+                    a[b, : len(inst.sess_quad)] = inst.sess_quad
+            h["sess_quad"] = a
         if site.use_peak_row:
             a = np.full((B, Tp_), 3.0e38, dtype=f32)
             for b, inst in enumerate(instances):
@@ -386,7 +393,7 @@ class PackedBatch:
         s.multi_session = int(self.multi_session)
         s.lb_zero = int(self.lb_zero)
         for name in ("T", "n_sessions", "sess_row", "sess_start", "sess_len", "sess_energy", "sess_rate_off",
-                     "min_rates", "max_rates", "alpha", "beta", "qd", "gamma", "ext", "peak_w", "peak_p0", "peak_limit"):
+                     "min_rates", "max_rates", "alpha", "beta", "qd", "gamma", "ext", "peak_w", "peak_p0", "peak_limit", "sess_quad"):
             setattr(s, name, _ptr(self.dev.get(name)))
         w = self.warm or {}
         s.warm_v1, s.warm_vc, s.warm_mu, s.warm_scal = (_ptr(w.get(k)) for k in ("v1", "vc", "mu", "scal"))

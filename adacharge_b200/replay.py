@@ -82,6 +82,8 @@ class SiteReplay:
             infra.get("allowable_pilots"), infra.get("is_continuous"))
         self.site: Optional[engine.Site] = None
         self._warm = None  # (device tensors, per-instance {session_id: mu}, site index of each batch row)
+        self.keep_problems = False  # tests: record (t, site, sessions, prev_peak, schedule, status) of every solved step
+        self.problems: List[tuple] = []
 
     # ------------------------------------------------------------------ one control step
     def _active(self, s: int, t: int) -> List[SessionInfo]:
@@ -118,6 +120,10 @@ class SiteReplay:
         first = pilots[:, :, 0].cpu().numpy()
         it, st = pb.iters.cpu().numpy(), pb.status.cpu().numpy()
         self.last_stats = pb.stats.cpu().numpy()  # rows: r_prim, r_dual, gap, violation, rho, cost scale, restarts, averaged
+        if self.keep_problems:
+            R = pb.rates.cpu().numpy().astype(np.float64)
+            for b, s in enumerate(rows):
+                self.problems.append((t, s, self._active(s, t), float(self.prev_peak[s]), R[b][:, : insts[b].T].copy(), int(st[b]), int(it[b])))
         stats.iters.append(it)
         stats.status.append(st)
         # apply the first-period pilots (the simulator side)

@@ -253,3 +253,105 @@ class FleetReplay:
                     device_ms=float(sum(s.device_ms)), host_ms=float(sum(s.host_ms)),
                     iters_mean=float(np.average(s.iters_mean, weights=np.maximum(s.active_sites, 1e-9))) if n else 0.0,
                     iters_max=float(max(s.iters_max, default=0)))
+
+
+class DeviceFleetReplay(FleetReplay):
+    """FleetReplay with the simulator side of the control step on the device as well: the EV table,
+    the energy delivered, the previous peaks and the per-EV warm-start multipliers stay in device arrays; a step is four
+    launches on one stream -- active sessions (acb_fleet_sessions), packing (acb_pack_sessions), the warm-started solve
+    whose prologue reads the previous state one column ahead (acb_batch.warm_shift) and whose epilogue projects the
+    pilots, and the simulator update (acb_fleet_apply) -- with no host synchronisation between steps.  Same schedules,
+    bit for bit, as FleetReplay (tests/test_gpu_replay.py)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        import ctypes as C
+
+        from .batched import BatchedAdaptiveCharging
+
+        dev = torch.device("cuda", engine._dev_index(self.device))
+        opts = {**REPLAY_SOLVER_DEFAULTS, **(kw.get("solver_options") or {})}
+        self._bac = BatchedAdaptiveCharging(self.objective, self.info, self.period, batch=self.n_sites, max_sessions=self.N, horizon=self.Tp,
+                                            demand_charge=self.demand_charge, solver_options=opts, device=self.device, chunks=1,
+                                            enforce_pilot_limit=False)
+        if self._bac.Tp != self.Tp:
+            raise ValueError(f"Tp = {self.Tp} is not a padded horizon of the solve path")
+        self.site = self._bac.site
+        ch = self._bac.chunks[0]
+        self._ch = ch
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(dev)  # noqa: E731
+        n_ev = len(self.ev_req)
+        self._d = dict(
+            station=up(self.ev_station, np.int32), arr=up(self.ev_arr, np.int32), dep=up(self.ev_dep, np.int32), req=up(self.ev_req, np.float64),
+            mx=up(self.ev_max, np.float64), dlv=torch.zeros(n_ev, dtype=torch.float64, device=dev), mu=torch.zeros(n_ev, dtype=torch.float32, device=dev),
+            prev_peak=torch.zeros(self.n_sites, dtype=torch.float64, device=dev), had=torch.zeros(self.n_sites, dtype=torch.int32, device=dev),
+            prices=up(np.concatenate([self.prices, np.zeros(self.Tp)]), np.float64),
+            sess_ev=torch.full((self.n_sites, self.N), -1, dtype=torch.int32, device=dev),
+            warm_mu=torch.zeros((self.n_sites, self.N), dtype=torch.float32, device=dev),
+            first=torch.zeros((self.n_sites, self.N), dtype=torch.float64, device=dev), stats=torch.zeros(3, dtype=torch.float64, device=dev),
+        )
+        # first EV of every (day, site): the table is sorted by (day, site, station)
+        key = (self.ev_arr // self.steps_per_day) * self.n_sites + self.ev_site
+        off = np.searchsorted(key, np.arange(self.days * self.n_sites + 1)).astype(np.int32)
+        self._d["off"] = torch.from_numpy(off).to(dev)
+        f = _cabi.Fleet()
+        f.n_sites, f.n_ev, f.days, f.steps_per_day = self.n_sites, n_ev, self.days, self.steps_per_day
+        p = engine._ptr
+        d = self._d
+        f.ev_station, f.ev_arr, f.ev_dep, f.ev_req, f.ev_max = p(d["station"]), p(d["arr"]), p(d["dep"]), p(d["req"]), p(d["mx"])
+        f.ev_dlv, f.ev_mu, f.day_site_off, f.prev_peak, f.had = p(d["dlv"]), p(d["mu"]), p(d["off"]), p(d["prev_peak"]), p(d["had"])
+        self._fleet = f
+        # two sets of warm-state buffers: a step reads the previous step's and writes its own
+        R = max(self.site.R, 1)
+        mk = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)  # noqa: E731
+        self._state = [dict(v1=mk(self.n_sites, self.N, self.Tp), vc=mk(self.n_sites, R, self.Tp), mu=mk(self.n_sites, self.N), scal=mk(self.n_sites, 2))
+                       for _ in range(2)]
+        self._k = 0
+        b = ch.batch
+        b.lb_zero, b.multi_session = 1, 0
+        b.warm_shift = 1
+        b.warm_had = p(d["had"])
+        b.warm_mu = p(d["warm_mu"])
+        o = ch.objective
+        o.prev_peak = p(d["prev_peak"])
+        o.prices_stride = 0  # one price vector for the whole fleet, read from the current period on
+        self._started = False
+        self._C = C
+
+    def step(self, t: int, want_first: bool = True):
+        C, L, ch, d, p = self._C, _cabi.lib(), self._ch, self._d, engine._ptr
+        st = C.c_void_p(torch.cuda.current_stream(self._bac.device).cuda_stream)
+        b, o = ch.batch, ch.objective
+        cur, prev = self._state[self._k], self._state[1 - self._k]
+        if self.warm_start and self._started:
+            b.warm_v1, b.warm_vc, b.warm_scal, b.warm_mu = p(prev["v1"]), p(prev["vc"]), p(prev["scal"]), p(d["warm_mu"])
+        else:
+            b.warm_v1 = b.warm_vc = b.warm_scal = b.warm_mu = None
+        b.out_v1, b.out_vc, b.out_mu, b.out_scal = p(cur["v1"]), p(cur["vc"]), p(cur["mu"]), p(cur["scal"])
+        o.prices = C.c_void_p(d["prices"].data_ptr() + 8 * t) if self._bac.need_prices else None
+        _cabi.check(L.acb_fleet_sessions(self.site.handle, C.byref(self._fleet), t, C.byref(ch.sessions), p(d["sess_ev"]), p(d["warm_mu"]), st), "acb_fleet_sessions")
+        _cabi.check(L.acb_pack_sessions(self.site.handle, C.byref(ch.sessions), C.byref(o), C.byref(b), p(ch.flags), st), "acb_pack_sessions")
+        _cabi.check(L.acb_solve_batch(self.site.handle, C.byref(b), C.byref(self._bac.options), st), "acb_solve_batch")
+        _cabi.check(L.acb_fleet_apply(self.site.handle, C.byref(self._fleet), t, float(self.period), C.byref(b), p(d["sess_ev"]),
+                                      p(d["first"]) if want_first else None, p(d["stats"]), st), "acb_fleet_apply")
+        self._k = 1 - self._k
+        self._started = True
+        return d["first"].cpu().numpy() if want_first else None
+
+    def run(self, t0: int = 0, t1: Optional[int] = None) -> FleetStats:
+        for t in range(t0, self.steps if t1 is None else t1):
+            self.step(t, want_first=False)
+        torch.cuda.synchronize(self._bac.device)
+        if int(self._ch.flags.cpu()[0]) != 0:
+            raise ValueError("the device packer flagged the fleet's sessions (two sessions on one EVSE, or a session beyond the padded horizon)")
+        self.ev_dlv = self._d["dlv"].cpu().numpy()
+        self.prev_peak = self._d["prev_peak"].cpu().numpy()
+        req = np.bincount(self.ev_site, weights=self.ev_req, minlength=self.n_sites)
+        dlv = np.bincount(self.ev_site, weights=self.ev_dlv, minlength=self.n_sites)
+        self.stats.delivered_frac = dlv / np.maximum(req, 1e-9)
+        self.stats.peak_kw = self.prev_peak * self.volt[0] / 1000
+        return self.stats
+
+    def summary(self) -> Dict[str, float]:
+        s = self._d["stats"].cpu().numpy()
+        return dict(site_steps=float(s[0]), unsolved=float(s[2]), iters_mean=float(s[1] / max(s[0], 1.0)))

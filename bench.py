@@ -367,7 +367,9 @@ def main():
                                        demand_charge=W["demand_charge"], chunks=chunks)
 
     # ---- value: resident raw inputs -> pack + solve (+ fused projection); two instances on their own streams alternate
-    res_a, res_b = make(1).upload_raw(W["sessions"], **kw), make(1).upload_raw(W["sessions"], **kw)
+    res_a = make(1).upload_raw(W["sessions"], **kw)
+    # (the general path synchronises with the host at every convergence check: two objects would only take turns)
+    res_b = make(1).upload_raw(W["sessions"], **kw) if args.config != "c5" else res_a
     solve_ev = []
 
     for k in range(warm):
@@ -395,9 +397,10 @@ def main():
     ch = res_a.chunks[0]
     status = ch.status.cpu().numpy()
     iters = ch.iters.cpu().numpy().astype(np.float64)
-    del res_b
+    res_b = None
     # ---- e2e: host arrays -> host pilots through the public batched call, double-buffered
-    e2e_a, e2e_b = make(4), make(4)
+    e2e_a = make(4 if args.config != "c5" else 1)
+    e2e_b = make(4) if args.config != "c5" else e2e_a
     for k in range(2):
         (e2e_a if k % 2 == 0 else e2e_b).schedule_async(W["sessions"], **kw)
     barrier()
@@ -450,7 +453,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
                          "kernel": "acb_solve_general (k_rows/k_cols)" if general else "acb_solve_kernel", "algorithmic_bytes_per_iteration": b_iter,
-                         "kernel_ms_per_launch": kern_ms, "kernel_share_of_step": None if kern_ms is None else min(1.0, kern_ms / (2 * launch_ms)) if steps > 1 else kern_ms / launch_ms,
+                         "kernel_ms_per_launch": kern_ms,
+                         "kernel_share_of_step": None if kern_ms is None else min(1.0, kern_ms / ((2 if args.config != "c5" and steps > 1 else 1) * launch_ms)),
                          "note": "effective bandwidth: state is on-chip resident, DRAM sees load/store only (SURVEY.md 8(d)); per-GPU figure"
                                  if not general else "state streamed through HBM/L2 every iteration; per-GPU figure"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(e2e_a.h2d_bytes) * world,
@@ -475,21 +479,22 @@ def main():
 
 
 def run_c4(args, world, rank, local, dev, barrier):
-    """BASELINE configs[3]: closed-loop replay, sites sharded over the ranks; a step = one control step of every site."""
+    """BASELINE configs[3]: closed-loop replay, sites sharded over the ranks; a step = one control step of every site
+    (active sessions -> pack -> warm-started solve -> pilots -> simulator update, all on the device, no host sync)."""
     import torch
     import torch.distributed as dist
 
-    import adacharge_b200 as ab
     from adacharge_b200 import sharding
     from adacharge_b200.generators import caltech_acn_infrastructure
-    from adacharge_b200.replay_fast import FleetReplay
+    from adacharge_b200.replay_fast import DeviceFleetReplay
 
     rng = sharding.shard_range(args.batch, rank, world)
-    rp = FleetReplay(caltech_acn_infrastructure(), objective_components(BENCH_OBJECTIVE), n_sites=len(rng), steps_per_day=288, days=1,
-                     seed0=1000, Tp=CONFIGS["c4"]["horizon"], site_offset=rng.start)
-    t_start = 96  # 8 am: the fleet is filling up
+    rp = DeviceFleetReplay(caltech_acn_infrastructure(), objective_components(BENCH_OBJECTIVE), n_sites=len(rng), steps_per_day=288, days=1,
+                           seed0=1000, Tp=CONFIGS["c4"]["horizon"], site_offset=rng.start)
+    t_start = 96  # 8 am: the fleet is filling up (the busiest part of the day for the solver)
     warm = max(args.warmup, 3)
     rp.run(t_start, t_start + warm)
+    s0 = rp.summary()
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -497,17 +502,18 @@ def run_c4(args, world, rank, local, dev, barrier):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    n0 = len(rp.stats.device_ms)
-    rp.run(t_start + warm, t_start + warm + args.steps)
+    for t in range(t_start + warm, t_start + warm + args.steps):
+        rp.step(t, want_first=False)
     e1.record()
+    t_enq = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
-    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    ms = e0.elapsed_time(e1)
     barrier()
     clk = clocks.stop() if rank == 0 else None
     ms = sharding.max_over_ranks(ms, dev)
-    st = rp.stats
-    summ = torch.tensor([float(sum(st.active_sites[n0:])), float(sum(st.unsolved[n0:])), float(sum(st.device_ms[n0:])), float(sum(st.host_ms[n0:])),
-                         float(np.sum(np.array(st.iters_mean[n0:]) * np.array(st.active_sites[n0:])))], dtype=torch.float64, device=dev)
+    s1 = rp.summary()
+    summ = torch.tensor([s1["site_steps"] - s0["site_steps"], s1["unsolved"] - s0["unsolved"],
+                         s1["iters_mean"] * s1["site_steps"] - s0["iters_mean"] * s0["site_steps"], t_enq], dtype=torch.float64, device=dev)
     tot = torch.stack(sharding.gather_summaries(summ)).cpu().numpy()
     if rank == 0:
         solves = tot[:, 0].sum()
@@ -515,12 +521,13 @@ def run_c4(args, world, rank, local, dev, barrier):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(args, world),
-            "timed_region": "closed loop: simulator step + pack + warm-started solve + projection + first-period pilots back, wall clock over the steps",
-            "solved": int(solves - tot[:, 1].sum()), "instances": int(solves), "iters_mean": float(tot[:, 4].sum() / max(solves, 1)),
-            "device_ms_per_step_max_rank": float(tot[:, 2].max() / args.steps), "host_ms_per_step_max_rank": float(tot[:, 3].max() / args.steps),
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "ms_per_step": ms / args.steps,
-                    "call": "FleetReplay.step (closed loop is end to end by construction)"},
-            "gpu_launches": int(args.steps * 3), "clocks": clk,
+            "timed_region": "closed loop on the device: acb_fleet_sessions + acb_pack_sessions + warm-started acb_solve_batch (fused pilot projection) + "
+                            "acb_fleet_apply per control step, CUDA events around all steps, no host synchronisation in between",
+            "solved": int(solves - tot[:, 1].sum()), "instances": int(solves), "iters_mean": float(tot[:, 2].sum() / max(solves, 1)),
+            "host_enqueue_ms_per_step_max_rank": float(tot[:, 3].max() / args.steps),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": ms / args.steps,
+                    "call": "DeviceFleetReplay.step (the closed loop is end to end by construction: the EV state lives on the device)"},
+            "gpu_launches": int(args.steps * 4), "clocks": clk,
         }
         print(json.dumps(line))
     if world > 1:

@@ -76,6 +76,9 @@ typedef struct acb_options {
                            P is the objective of the returned schedule and D a Lagrangian lower bound; negative
                            tolerances never pass: the solve runs its whole iteration budget (status ACB_MAX_ITER) */
     float viol_tol;     /* max relative infrastructure / peak violation of the returned schedule */
+    float viol_abs;     /* ... and at most this many amperes over any limit (default 1e-3 A, the bar of the reference's own tests,
+                           tests/test_adaptive_charging_optimization.py:82; it is the tighter one for limits above 100 A); 0 = off.
+                           stats[3] reports the excess in units of the tighter tolerance (<= viol_tol means both hold) */
     float rho0;         /* initial penalty */
     float kappa;        /* identity-block penalty = kappa * rho */
     float alpha;        /* over-relaxation in (0, 2) */
@@ -145,6 +148,9 @@ typedef struct acb_batch {
      * mu [B][S_max], scal [B][2] = {rho, peak level}. */
     float* work;                 /* scratch [B][N+R][Tp] for the averaged state; NULL disables restarts */
     const float* warm_v1; const float* warm_vc; const float* warm_mu; const float* warm_scal;
+    int32_t warm_shift;          /* closed-loop replay: warm_v1 / warm_vc are read this many columns ahead (1 = the previous control
+                                  * step's state: its column t + 1 is this problem's column t), zero beyond the horizon */
+    const int32_t* warm_had;     /* optional [B]: 0 = this instance starts cold although warm arrays are given (site idle before) */
     float* out_v1; float* out_vc; float* out_mu; float* out_scal;
     /* results */
     float* rates;                /* [B][N][Tp] */
@@ -243,6 +249,37 @@ int acb_min_rate_admission(acb_site* site, int B, int S_max, const int32_t* n_se
  * if upper_bound ([B][S_max], device) is given, max_rate <- min(max_rate, upper_bound) and then max_rate <- min_rate where
  * it fell below the minimum rate. */
 int acb_preprocess_sessions(acb_site* site, const acb_sessions* sessions, int enforce_pilot_limit, const double* upper_bound, void* stream);
+
+/* ---- closed-loop replay on the device (the simulator side of a control step for a fleet of sites) ----
+ * The loop acnportal's Simulator drives around AdaptiveSchedulingAlgorithm.schedule (adacharge/adacharge.py:18-39 active
+ * sessions in, :135-193 pilots out; tests/test_integration.py:115-118), as two kernels around acb_pack_sessions +
+ * acb_solve_batch.  All pointers device.  The EV table is sorted by (day, site, station); day_site_off[(day, site)] is
+ * the first EV of that site-day (length days * n_sites + 1). */
+typedef struct acb_fleet {
+    int32_t n_sites, n_ev, days, steps_per_day;
+    const int32_t* ev_station;   /* [n_ev] EVSE index */
+    const int32_t* ev_arr;       /* [n_ev] arrival period (absolute) */
+    const int32_t* ev_dep;       /* [n_ev] departure period (absolute) */
+    const double* ev_req;        /* [n_ev] requested energy, kWh */
+    const double* ev_max;        /* [n_ev] maximum rate, A */
+    double* ev_dlv;              /* [n_ev] state: energy delivered so far, kWh */
+    float* ev_mu;                /* [n_ev] state: energy-row multiplier of the EV's last solve (warm start) */
+    const int32_t* day_site_off; /* [days * n_sites + 1] */
+    double* prev_peak;           /* [n_sites] state: largest aggregate first-period current so far, A (interface.get_prev_peak) */
+    int32_t* had;                /* [n_sites] state: 1 if the site had sessions in the previous step */
+} acb_fleet;
+
+/* Step t: the active sessions of every site (plugged in, energy still owed) into the raw tables acb_pack_sessions takes
+ * (arrival_offset 0, remaining_time = departure - t, remaining_demand = requested - delivered), plus the EV behind each
+ * slot (sess_ev [n_sites][S_max], -1 = empty) and its warm-start multiplier (warm_mu [n_sites][S_max]). */
+int acb_fleet_sessions(acb_site* site, const acb_fleet* fleet, int t, const acb_sessions* sessions, int32_t* sess_ev, float* warm_mu,
+                       void* stream);
+/* After the solve of step t: the first-period pilots (batch->pilots) charge every plugged-in EV (delivered energy capped at
+ * the request), prev_peak and had are updated, the session multipliers (batch->out_mu) go back to their EVs.  first_pilots
+ * (optional [n_sites][N]) receives the applied pilots; stats (optional, 3 doubles) accumulates site-steps solved, iterations,
+ * uncertified solves. */
+int acb_fleet_apply(acb_site* site, const acb_fleet* fleet, int t, double period, const acb_batch* batch, const int32_t* sess_ev,
+                    double* first_pilots, double* stats, void* stream);
 
 const char* acb_last_error(void);
 int acb_version(void);

@@ -135,3 +135,27 @@ def test_every_padded_horizon_gives_the_same_schedule(require_gpu, Tp):
     pg = engine.PackedBatch(site, [inst], Tp=Tp).upload().solve(_cabi.default_options(path=2, eps_rel=2e-5))
     assert int(pg.status[0]) == 0
     assert np.abs(pg.rates[0, :, : inst.T].cpu().numpy() - ref).max() <= 5e-3
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_zero_limit_row_is_enforced(require_gpu, path):
+    """A constraint row with limit 0 (a de-rated line): the reference would enforce it; the EVSEs behind it must get no
+    current while the others charge (the relative violation measure has no meaning for such a row)."""
+    import adacharge_b200 as ab
+    from adacharge_b200.generators import config_c2, caltech_acn_infrastructure
+    from oracle import mpc
+
+    infra = caltech_acn_infrastructure()
+    infra["constraint_limits"] = np.array(infra["constraint_limits"], dtype=float)
+    infra["constraint_limits"][-1] = 0.0  # second pod
+    iface = ab.TestingInterface(config_c2(12, infra=infra))
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    spec = [("tou_energy_cost", 1, {}), ("total_energy", 0.3, {}), ("demand_charge", 1 / 30, {})]
+    aco = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(getattr(ab, n), c, k) for n, c, k in spec], iface, solver_options=dict(path=path))
+    R = aco.solve(S, I, prev_peak=iface.get_prev_peak())
+    pod = np.abs(np.asarray(I.constraint_matrix)[-1]) > 0
+    assert pod.any() and R[pod].max() <= 1e-4, R[pod].max()
+    assert R[~pod].sum() > 100
+    Ro = mpc.solve_mpc(spec, S, I, iface, "SOC", False, None, iface.get_prev_peak())
+    f, fo = (mpc.evaluate_objective(X, spec, I, iface, S, iface.get_prev_peak()) for X in (R, Ro))
+    assert abs(f - fo) <= 1e-4 * abs(fo), (f, fo, aco.last_info)
