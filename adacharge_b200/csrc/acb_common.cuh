@@ -7,6 +7,9 @@
 #include "../../include/adacharge_b200.h"
 
 #define ACB_VERSION 100
+#ifndef ACB_FAST_THREADS
+#define ACB_FAST_THREADS 640  // block size cap of the FAST variant (v in shared memory): 20 warps -> 96 registers per thread, no spills in the hot loop
+#endif
 #define ACB_OHT 12         // outputs per column-pass thread (one or two threads per period: at most 24 column inputs on chip)
 #define ACB_NRED 16        // floats per warp in the reduction scratch
 #define ACB_MAX_WARPS 32

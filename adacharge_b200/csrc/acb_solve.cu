@@ -97,6 +97,15 @@ extern "C" int acb_solve_batch(acb_site* site, const acb_batch* batch, const acb
     // every minimum rate declared 0: v in shared memory instead of the lower bounds.  opt.path 4 (experimental) runs that
     // variant with two rows per warp in 1024-thread blocks (measured 3-4 % slower than three rows in 768 threads)
     int fast = (!multi && batch->lb_zero != 0) ? 1 : 0;
+    if (fast == 1 && opt.path != 4) {
+        // FAST, three rows per warp: cap the block at ACB_FAST_THREADS (more registers per thread); the coupling items that
+        // the fewer spare warps cannot carry ride on the row warps
+        const int ntf = std::min(nthreads, std::max(ACB_FAST_THREADS, ((d.nRowWarps * 32 + 64 + 127) / 128) * 128));
+        if (ntf <= ACB_FAST_THREADS && d.nRowWarps * 32 + 32 <= ntf) {
+            nthreads = ntf;
+            smem = acb_solve_smem_bytes(d, batch->Tp, batch->S_max, nthreads / 32);
+        } else fast = 0;  // more than 19 row warps: the register-state kernel with its 768-thread bound
+    }
     if (fast && site->has_d2 && opt.path == 4) {
         const SiteDev& e = site->d2;
         const int nt2 = std::min(1024, ((std::max(e.nRowWarps * 32 + nCT * 16, std::min(1024, nParts * batch->Tp)) + 127) / 128) * 128);

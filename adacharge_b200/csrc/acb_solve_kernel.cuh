@@ -152,7 +152,7 @@ __device__ __forceinline__ long long acb_clock() { long long c; asm volatile("mo
 // array is then not needed and its shared memory holds v instead of registers: the hot loop keeps no per-element state
 // in registers (no spills under the 80-register cap, loop constants stay resident).
 template <int Q, int TPW, bool MULTI, bool FAST>
-__global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L, const SolvePhase P) {
+__global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 768), 1) acb_solve_kernel(const SiteDev S, const acb_batch B, const acb_options opt, const SmemLayout L, const SolvePhase P) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -192,6 +192,9 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
         else { nCW = nFree; if (warp >= S.nRowWarps) cwIdx = warp - S.nRowWarps; }
         doAgg = S.has_u && warp == nwarps - 1;
     }
+    // balance: a coupling warp carries about 16 chunk items; what exceeds that rides on the row warps (blocks with few
+    // spare warps: the FAST variant runs 640 threads for 96 registers per thread)
+    const int rowShare = (nwarps > S.nRowWarps) ? max(0, (nCT1 * Q - 16 * nCW + S.nRowWarps - 1) / S.nRowWarps) : 0;
     float* VSUM = B.work ? B.work + (size_t)b * (N + R) * Tp : nullptr;  // running sum of v (rows, then coupling rows)
     const bool useAvg = opt.restart && VSUM != nullptr;
 
@@ -1074,8 +1077,8 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
         // ---------------------------------------------------------- coupling rows
         // v update and GIN <- rho (2 z(v) - v) for the next column pass; on check iterations VOUT <- y = rho (v - z)
         // and the conjugate terms of D.  Work item = (task, 32-period chunk), dealt round-robin to the coupling warps.
-        if (cwIdx >= 0) {
-            for (int item = cwIdx; item < nCT1 * Q; item += nCW) {
+        auto couple_item = [&](int item) {
+            {
                 const int c = item / Q, t = (item - c * Q) * 32 + lane;
                 if (c < nDisc) {
                     const int r = 2 * c;
@@ -1116,6 +1119,14 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : 768, 1) acb_solve_kernel(con
                     }
                 }
             }
+        };
+        // the first rowShare * nRowWarps items ride on the row warps (after their own rows), the rest is dealt
+        // round-robin to the coupling warps
+        if (rowWarp) {
+            for (int j = 0; j < rowShare; ++j) couple_item(warp * rowShare + j);
+        }
+        if (cwIdx >= 0) {
+            for (int item = rowShare * S.nRowWarps + cwIdx; item < nCT1 * Q; item += nCW) couple_item(item);
         }
         if (doAgg) {
             // aggregate-power row: quadratic (load flattening) + peak epigraph

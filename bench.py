@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--groups", type=int, default=4, help="c4: independent groups of sites per GPU, each on its own stream")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = CONFIGS[args.config]["batch"]
@@ -489,31 +490,54 @@ def run_c4(args, world, rank, local, dev, barrier):
     from adacharge_b200.replay_fast import DeviceFleetReplay
 
     rng = sharding.shard_range(args.batch, rank, world)
-    rp = DeviceFleetReplay(caltech_acn_infrastructure(), objective_components(BENCH_OBJECTIVE), n_sites=len(rng), steps_per_day=288, days=1,
-                           seed0=1000, Tp=CONFIGS["c4"]["horizon"], site_offset=rng.start)
+    # Sites are independent closed loops: the rank's sites are cut into groups that advance on their own streams, so
+    # that a group's step does not wait for the slowest site of another group (each group is in lockstep internally)
+    n_groups = max(1, min(args.groups, len(rng) // 64))
+    cuts = [rng.start + round(k * len(rng) / n_groups) for k in range(n_groups + 1)]
+    infra = caltech_acn_infrastructure()
+    rps = [DeviceFleetReplay(infra, objective_components(BENCH_OBJECTIVE), n_sites=b - a, steps_per_day=288, days=1,
+                             seed0=1000, Tp=CONFIGS["c4"]["horizon"], site_offset=a) for a, b in zip(cuts[:-1], cuts[1:])]
+    streams = [torch.cuda.Stream(device=dev) for _ in rps]
     t_start = 96  # 8 am: the fleet is filling up (the busiest part of the day for the solver)
     warm = max(args.warmup, 3)
-    rp.run(t_start, t_start + warm)
-    s0 = rp.summary()
+
+    def run_steps(t0, t1):
+        for t in range(t0, t1):
+            for rp, st in zip(rps, streams):
+                with torch.cuda.stream(st):
+                    rp.step(t, want_first=False)
+
+    def summary():
+        ss = [rp.summary() for rp in rps]
+        return dict(site_steps=sum(x["site_steps"] for x in ss), unsolved=sum(x["unsolved"] for x in ss),
+                    iters=sum(x["iters_mean"] * x["site_steps"] for x in ss))
+
+    run_steps(t_start, t_start + warm)
+    torch.cuda.synchronize()
+    s0 = summary()
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
     t0 = time.perf_counter()
-    e0.record()
-    for t in range(t_start + warm, t_start + warm + args.steps):
-        rp.step(t, want_first=False)
-    e1.record()
+    e0.record(cur)
+    for st in streams:
+        st.wait_event(e0)
+    run_steps(t_start + warm, t_start + warm + args.steps)
+    for st in streams:
+        cur.wait_stream(st)
+    e1.record(cur)
     t_enq = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     barrier()
     clk = clocks.stop() if rank == 0 else None
     ms = sharding.max_over_ranks(ms, dev)
-    s1 = rp.summary()
-    summ = torch.tensor([s1["site_steps"] - s0["site_steps"], s1["unsolved"] - s0["unsolved"],
-                         s1["iters_mean"] * s1["site_steps"] - s0["iters_mean"] * s0["site_steps"], t_enq], dtype=torch.float64, device=dev)
+    s1 = summary()
+    summ = torch.tensor([s1["site_steps"] - s0["site_steps"], s1["unsolved"] - s0["unsolved"], s1["iters"] - s0["iters"], t_enq],
+                        dtype=torch.float64, device=dev)
     tot = torch.stack(sharding.gather_summaries(summ)).cpu().numpy()
     if rank == 0:
         solves = tot[:, 0].sum()
@@ -527,7 +551,7 @@ def run_c4(args, world, rank, local, dev, barrier):
             "host_enqueue_ms_per_step_max_rank": float(tot[:, 3].max() / args.steps),
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": ms / args.steps,
                     "call": "DeviceFleetReplay.step (the closed loop is end to end by construction: the EV state lives on the device)"},
-            "gpu_launches": int(args.steps * 4), "clocks": clk,
+            "gpu_launches": int(args.steps * 4 * n_groups), "site_groups_per_gpu": n_groups, "clocks": clk,
         }
         print(json.dumps(line))
     if world > 1:

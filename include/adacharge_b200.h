@@ -20,6 +20,12 @@
  *   acb_reallocate              index_based_reallocation / diff_based_reallocation
  *                                                                 postprocessing.py:121-258
  *   acb_constraints_feasible    infrastructure_constraints_feasible       utils.py:5-12
+ *   acb_pack_sessions           the host work before the solver: horizon, energy rows, build_objective
+ *                                                                 ...optimization.py:114-122, 200-218, 243-245, 363-408
+ *   acb_preprocess_sessions / acb_min_rate_admission
+ *                               acnportal preprocessing called at      adacharge/adacharge.py:141-150
+ *   acb_fleet_sessions / acb_fleet_apply
+ *                               the simulator side of a closed-loop step  adacharge/adacharge.py:18-39, 135-193
  *
  * Conventions: plain C, no exceptions; every function returns 0 on success or a
  * negative ACB_E_* code (acb_last_error() gives text).  Unless a parameter is marked
