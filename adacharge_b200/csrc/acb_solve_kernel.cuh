@@ -845,7 +845,11 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         ACB_TR(1);
         __syncthreads();
         ACB_TR(2);
+#ifdef ACB_NOCHECK  // experiment: compile the check path out of the loop (the caller never lets a check iteration happen)
+        constexpr bool chk = false;
+#else
         const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter) || (it == ACB_FIRST_CHECK);  // easy / warm-started instances stop early
+#endif
         const bool doAvg = useAvg && (it % avgEvery == 0);
         const bool avgFirst = SCAL[SC_NSUM] == 0.f;
         float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f, rDz = 0.f;
@@ -1169,6 +1173,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
             if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;  // next read is after the next barrier
             continue;
         }
+#ifndef ACB_NOCHECK
 
         // ============================================================= check path
         __syncthreads();  // PART = group sums of z, VOUT = y
@@ -1514,6 +1519,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         write_part_q();
         write_gin();
         __syncthreads();
+#endif
     }
     if (it > opt.max_iter) it = opt.max_iter;
     if (parked) {

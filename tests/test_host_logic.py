@@ -304,10 +304,70 @@ def test_options_struct_matches_header_order():
     assert d.eps_rel == pytest.approx(1e-4) and d.check_every == 25 and d.term_floor == pytest.approx(0.05) and d.rho_curv == pytest.approx(1.0)
     assert d.rate_tol == pytest.approx(3e-4) and d.polish_min_qd == pytest.approx(5e-4)
     # the device packer's structs (acb_sessions, acb_objective) against the header as well
-    for cname, ctype in (("acb_sessions", _cabi.Sessions), ("acb_objective", _cabi.Objective)):
+    for cname, ctype in (("acb_sessions", _cabi.Sessions), ("acb_objective", _cabi.Objective), ("acb_fleet", _cabi.Fleet)):
         body = hdr[hdr.index("typedef struct %s {" % cname):hdr.index("} %s;" % cname)]
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
         for decl in re.findall(r"(?:const\s+)?(?:int32_t|float|double)\s*\*?\s*([^;]+);", body):
             names += [re.sub(r"\[.*\]", "", x.strip().lstrip("*").split()[-1].lstrip("*")) for x in decl.split(",")]
         assert names == [n for n, _ in ctype._fields_], (cname, names)
+
+
+def test_padded_horizon_and_long_horizons():
+    """Horizons up to 288 use the on-chip kernel's instantiations, longer ones the next multiple of 32 (general path);
+    the reference puts no limit on T (aco.py:243-245), this library's is 3616 periods."""
+    from adacharge_b200 import engine
+
+    assert [engine.padded_horizon(t) for t in (1, 64, 65, 128, 129, 160, 161, 288)] == [64, 64, 128, 128, 160, 160, 288, 288]
+    assert engine.padded_horizon(289) == 320 and engine.padded_horizon(2016) == 2016 and engine.padded_horizon(3600) == 3616
+    with pytest.raises(ValueError, match="longest supported horizon"):
+        engine.padded_horizon(3617)
+
+
+def test_quadratic_non_completion_penalty_packs_per_session_weights():
+    """non_completion_penalty(norm=2) -> one weight per session: coefficient * (kWh per A*period of its EVSE)^2, in the
+    packed (row-sorted) session order; the numeric twin and the oracle evaluate the same value."""
+    d = config_c2(4)
+    iface = ab.TestingInterface(d)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    spec = [("tou_energy_cost", 1.0, {}), ("non_completion_penalty", 2.5, {"norm": 2})]
+    aco = ab.AdaptiveChargingOptimization([ab.ObjectiveComponent(getattr(ab, n), c, k) for n, c, k in spec], iface)
+    inst = aco.build_instance(S, I)
+    w = np.asarray(I.voltages)[inst.sess_row] * iface.period / 1e3 / 60
+    np.testing.assert_allclose(inst.sess_quad, 2.5 * w * w)
+    rng = np.random.default_rng(0)
+    R = rng.uniform(0, 8, size=(I.num_stations, mpc.horizon(S)))
+    val = sum(c * getattr(ab, n)(R, I, iface, **k) for n, c, k in spec)
+    assert val == pytest.approx(mpc.evaluate_objective(R, spec, I, iface, S), rel=1e-12)
+    with pytest.raises(ValueError, match="not concave"):
+        ab.pack_objective([ab.ObjectiveComponent(ab.non_completion_penalty, -1.0, {"norm": 2})], I, iface, 10)
+
+
+def test_batched_objective_components_validation():
+    from adacharge_b200.batched import objective_components
+
+    comps = objective_components([ab.ObjectiveComponent(ab.quick_charge, 2.0), ab.ObjectiveComponent(ab.demand_charge, 0.5, {"baseline_peak": 7.0}),
+                                  ab.ObjectiveComponent(ab.non_completion_penalty, 1.0, {"norm": 2})])
+    assert comps == [(_cabi.OBJ_KIND["quick_charge"], 2.0, 0.0), (_cabi.OBJ_KIND["demand_charge"], 0.5, 7.0), (_cabi.OBJ_KIND["non_completion_penalty_l2"], 1.0, 0.0)]
+    with pytest.raises(TypeError, match="cannot be packed on the device"):
+        objective_components([ab.ObjectiveComponent(lambda rates, infra, iface, **kw: 0.0)])
+    with pytest.raises(NotImplementedError, match="different baselines"):
+        objective_components([ab.ObjectiveComponent(ab.demand_charge, 1.0, {"baseline_peak": 3.0}), ab.ObjectiveComponent(ab.peak, -1.0, {"baseline_peak": 4.0})])
+
+
+def test_set_rounding_helpers_keep_the_reference_contract():
+    """floor_to_set / ceil_to_set / increment_in_set (reference postprocessing.py:10-74), incl. the documented corner:
+    a member exactly eps above x is NOT reached by floor_to_set."""
+    from oracle import postprocessing as opp
+
+    s = [0, 5, 10]
+    assert ab.floor_to_set(4.95, s) == 0 and ab.floor_to_set(4.96, s) == 5 and ab.floor_to_set(5, s) == 5 and ab.floor_to_set(-1, s) == 0 and ab.floor_to_set(11, s) == 10
+    assert ab.ceil_to_set(5.04, s) == 5 and ab.ceil_to_set(5.06, s) == 10 and ab.ceil_to_set(20, s) == 10 and ab.ceil_to_set(-3, s) == 0
+    assert ab.increment_in_set(5, s) == 10 and ab.increment_in_set(4.9, s) == 5 and ab.increment_in_set(10, s) == 10 and ab.increment_in_set(-1, s) == 0
+    rng = np.random.default_rng(1)
+    sets = [np.array([0.0, 6.0, 8.0, 16.0, 32.0]), np.arange(0, 33, 1.0), np.array([8.0])]
+    for a in sets:
+        for x in np.concatenate([rng.uniform(-2, 36, 200), a, a + 0.05, a - 0.05]):
+            assert ab.floor_to_set(x, a) == opp.floor_to_set(x, a)
+            assert ab.ceil_to_set(x, a) == opp.ceil_to_set(x, a)
+            assert ab.increment_in_set(x, a) == opp.increment_in_set(x, a)

@@ -2,6 +2,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, common
 from adacharge_b200 import _cabi, engine
+if len(sys.argv) > 2:  # e.g. `nocheck`: tools/build/libadacharge_b200_nocheck.so (make -C adacharge_b200/csrc nocheck)
+    _cabi.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "build", f"libadacharge_b200_{sys.argv[2]}.so")
 site, insts, _ = common.build_instances(148, 0)
 pb = engine.PackedBatch(site, insts).upload()
 def t(mi):

@@ -1,8 +1,9 @@
 """BASELINE config 4 at scale: closed-loop warm-started replay of many Caltech-shaped sites.
-  python tools/replay_c4.py [n_sites] [t0] [t1] [days] [Tp] [host|device]   (one GPU; default: simulator step on the device)
-  torchrun --nproc-per-node N tools/replay_c4.py ...                   (sites sharded over ranks)
-Prints one JSON line: control steps per second for the whole fleet, site-steps per second,
-the host/device split and the iteration statistics."""
+  python tools/replay_c4.py [n_sites] [t0] [t1] [days] [Tp] [host|device] [groups]   (one GPU; default: device simulator, 8 groups)
+  torchrun --nproc-per-node N tools/replay_c4.py ...                                  (sites sharded over ranks)
+Sites are independent closed loops: with the device simulator a rank's sites are cut into `groups` fleets that advance on
+their own streams (each in lockstep internally), so one fleet's step does not wait for the slowest site of another.
+Prints one JSON line: control steps per second for the whole fleet, site-steps per second, iteration statistics."""
 import json
 import os
 import sys
@@ -23,6 +24,7 @@ t1 = int(sys.argv[3]) if len(sys.argv) > 3 else 288
 days = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 Tp = int(sys.argv[5]) if len(sys.argv) > 5 else 160
 on_device = (sys.argv[6] if len(sys.argv) > 6 else "device") == "device"
+groups = int(sys.argv[7]) if len(sys.argv) > 7 else 8
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -32,44 +34,57 @@ if world > 1:
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
 _r = sharding.shard_range(n_sites, rank, world)
-lo, hi = _r.start, _r.stop
 obj = [ab.ObjectiveComponent(ab.tou_energy_cost), ab.ObjectiveComponent(ab.total_energy, 0.3), ab.ObjectiveComponent(ab.demand_charge, 1 / 30)]
-rp = (DeviceFleetReplay if on_device else FleetReplay)(caltech_acn_infrastructure(), obj, n_sites=hi - lo, steps_per_day=288, days=days, seed0=1000, Tp=Tp, site_offset=lo,
-                 solver_options=json.loads(os.environ.get("ACB_REPLAY_OPTS", "{}")))
-rp.run(t0, min(t0 + 3, t1))  # warm-up steps (library load, allocator), not timed
+opts = json.loads(os.environ.get("ACB_REPLAY_OPTS", "{}"))
+infra = caltech_acn_infrastructure()
+if on_device:
+    g = max(1, min(groups, len(_r) // 8))
+    cuts = [_r.start + round(k * len(_r) / g) for k in range(g + 1)]
+    rps = [DeviceFleetReplay(infra, obj, n_sites=b - a, steps_per_day=288, days=days, seed0=1000, Tp=Tp, site_offset=a, solver_options=opts)
+           for a, b in zip(cuts[:-1], cuts[1:])]
+else:
+    rps = [FleetReplay(infra, obj, n_sites=len(_r), steps_per_day=288, days=days, seed0=1000, Tp=Tp, site_offset=_r.start, solver_options=opts)]
+streams = [torch.cuda.Stream() for _ in rps]
+
+
+def run(a, b):
+    for t in range(a, b):
+        for rp, st in zip(rps, streams):
+            with torch.cuda.stream(st):
+                rp.step(t, want_first=False) if on_device else rp.step(t)
+
+
+def summary():
+    ss = [rp.summary() for rp in rps]
+    return dict(site_steps=sum(x["site_steps"] for x in ss), unsolved=sum(x["unsolved"] for x in ss), iters=sum(x["iters_mean"] * x["site_steps"] for x in ss))
+
+
+run(t0, min(t0 + 3, t1))  # warm-up steps (library load, allocator), not timed
+torch.cuda.synchronize()
+s0 = summary()
 if world > 1:
     torch.distributed.barrier()
 torch.cuda.synchronize()
 w0 = time.perf_counter()
-n_before = len(rp.stats.device_ms)
-s_before = rp.summary()
-stats = rp.run(t0 + 3, t1)
+run(t0 + 3, t1)
 torch.cuda.synchronize()
 wall = time.perf_counter() - w0
-s = rp.summary()
-if on_device:
-    timed = dict(steps=t1 - t0 - 3, device_ms=wall * 1e3, host_ms=0.0, site_steps=s["site_steps"] - s_before["site_steps"])
-    s = dict(s, unsolved=s["unsolved"] - s_before["unsolved"], iters_max=float("nan"))
-else:
-    timed = dict(steps=len(stats.device_ms) - n_before, device_ms=sum(stats.device_ms[n_before:]), host_ms=sum(stats.host_ms[n_before:]),
-                 site_steps=sum(stats.active_sites[n_before:]))
+s1 = summary()
+for rp in rps:
+    rp.run(0, 0)  # (device replay: reads the EV state back; no steps)
+frac = float(np.sum([np.sum(rp.stats.delivered_frac) for rp in rps])) if all(rp.stats.delivered_frac is not None for rp in rps) else float("nan")
+vals = torch.tensor([s1["site_steps"] - s0["site_steps"], s1["unsolved"] - s0["unsolved"], s1["iters"] - s0["iters"], frac], device="cuda", dtype=torch.float64)
+wt = torch.tensor([wall], device="cuda", dtype=torch.float64)
 if world > 1:
-    t = torch.tensor([wall, timed["device_ms"], timed["host_ms"]], device="cuda", dtype=torch.float64)
-    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    c = torch.tensor([timed["site_steps"], s["unsolved"], float(np.sum(stats.delivered_frac)), s["iters_max"]], device="cuda", dtype=torch.float64)
-    mx = c[3:].clone()
-    torch.distributed.all_reduce(c, op=torch.distributed.ReduceOp.SUM)
-    torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)
-    wall, dms, hms = t.tolist()
-    site_steps, unsolved, full = c[:3].tolist()
-    it_max = mx.item()
-else:
-    dms, hms, site_steps, unsolved, full, it_max = timed["device_ms"], timed["host_ms"], timed["site_steps"], s["unsolved"], float(np.sum(stats.delivered_frac)), s["iters_max"]
+    torch.distributed.all_reduce(vals, op=torch.distributed.ReduceOp.SUM)
+    torch.distributed.all_reduce(wt, op=torch.distributed.ReduceOp.MAX)
+site_steps, unsolved, iters, full = vals.tolist()
+wall = wt.item()
 if rank == 0:
-    print(json.dumps(dict(workload="C4 replay", simulator="device" if on_device else "host", n_sites=n_sites, n_gpus=world, steps=timed["steps"], Tp=Tp, days=days,
-                          control_steps_per_s=round(timed["steps"] / wall, 2), site_steps_per_s=round(site_steps / wall, 1),
-                          wall_s=round(wall, 2), device_ms_per_step=round(dms / max(timed["steps"], 1), 2),
-                          host_ms_per_step=round(hms / max(timed["steps"], 1), 2), iters_mean_rank0=round(s["iters_mean"], 1),
-                          iters_max=it_max, unsolved=unsolved, mean_delivered_fraction=round(full / n_sites, 4))))
+    steps = t1 - t0 - 3
+    print(json.dumps(dict(workload="C4 replay", simulator="device" if on_device else "host", groups_per_gpu=len(rps), n_sites=n_sites, n_gpus=world,
+                          steps=steps, Tp=Tp, days=days, control_steps_per_s=round(steps / wall, 2), site_steps_per_s=round(site_steps / wall, 1),
+                          wall_s=round(wall, 2), ms_per_step=round(wall * 1e3 / max(steps, 1), 3), iters_mean=round(iters / max(site_steps, 1), 1),
+                          unsolved=unsolved, mean_delivered_fraction=round(full / n_sites, 4))))
 if world > 1:
     torch.distributed.destroy_process_group()
