@@ -12,9 +12,10 @@ What differs (documented, unavoidable without cvxpy):
 * objective functions are *numeric*: called with a numpy rates matrix they return the
   value the reference's cvxpy expression would have; the solver recognises the
   built-in ones by identity and packs them into the device objective.  A user
-  component must carry a ``kernel_spec(infrastructure, interface, T, **kwargs)``
-  attribute returning the same dict as the built-ins (see ``_SPECS``); anything else
-  is rejected loudly.
+  component either carries a ``kernel_spec(infrastructure, interface, T, **kwargs)``
+  attribute returning the same dict as the built-ins (see ``_SPECS``), or is a numeric
+  callable with the built-ins' signature, whose linear / quadratic form is recovered
+  by probing (``tracer.py``); anything that does not fit is rejected loudly.
 * ``build_problem`` and the static constraint builders return packed descriptors
   (numpy), not cvxpy objects.
 """
@@ -26,7 +27,7 @@ from typing import List, Optional, Union
 import numpy as np
 
 from .interface import Interface, SessionInfo, InfrastructureInfo
-from . import engine, _cabi
+from . import engine, _cabi, tracer
 
 
 class InfeasibilityException(Exception):
@@ -180,10 +181,14 @@ def pack_objective(objective: List[ObjectiveComponent], infrastructure, interfac
         kw.update(comp.kwargs or {})
         spec_fn = _SPECS.get(fn) or getattr(fn, "kernel_spec", None)
         if spec_fn is None:
-            raise TypeError(
-                f"objective component {getattr(fn, '__name__', fn)!r} has no device kernel spec; built-ins are "
-                f"{sorted(f.__name__ for f in _SPECS)}; custom components must define `kernel_spec`."
-            )
+            if not callable(fn):
+                raise TypeError(
+                    f"objective component {getattr(fn, '__name__', fn)!r} is not callable; built-ins are "
+                    f"{sorted(f.__name__ for f in _SPECS)}; custom components are numeric callables or define `kernel_spec`."
+                )
+            # a user's numeric callable: recover its linear / quadratic form by probing (tracer.py); a component that is
+            # not of that form raises tracer.NotTraceable (a TypeError)
+            spec_fn = tracer.traced_spec(fn)
         sp = spec_fn(infrastructure, interface, T, **kw)
         if "alpha" in sp:
             out["alpha"] += coef * np.asarray(sp["alpha"], dtype=float)

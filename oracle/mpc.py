@@ -120,6 +120,9 @@ def objective_terms(objective, infra, interface, T, sessions=None, prev_peak=0):
             if coef < 0:
                 raise ValueError("non_completion_penalty with negative coefficient is not concave")
             out["ncp"].append((coef, int(kw.get("norm", 1))))
+        elif fn == "linear":  # test hook, not a reference component: f = sum(weights * R), weights (N, >=T); the form a
+            # user-written linear ObjectiveComponent.function (aco.py:200-218) canonicalises to
+            lin -= coef * np.asarray(kw["weights"], dtype=float)[:, :T]
         else:
             raise ValueError(f"unknown objective component {fn}")
     if out["diag_q"] < 0:
