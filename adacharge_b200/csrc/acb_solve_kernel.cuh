@@ -1073,15 +1073,13 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     if (sfk[k] >= 0) SESS_MU[sfk[k]] = mun[k];
             }
         };
-        if (rowWarp) {
-            if (chk) row_pass(std::true_type{});  // (a check-iteration variant of the fast pass was measured slower: its exact mode ends in the full search)
-            else if (fastRows) row_pass_fast();
-            else row_pass(std::false_type{});
-        }
         // ---------------------------------------------------------- coupling rows
         // v update and GIN <- rho (2 z(v) - v) for the next column pass; on check iterations VOUT <- y = rho (v - z)
         // and the conjugate terms of D.  Work item = (task, 32-period chunk), dealt round-robin to the coupling warps.
-        auto couple_item = [&](int item) {
+        // (templated on the check flag like the row pass: the accumulators of the dual bound must not be live, i.e. spilled,
+        // across the hot iterations)
+        auto couple_item = [&](int item, auto chk_tag) {
+            constexpr bool CHK = decltype(chk_tag)::value;
             {
                 const int c = item / Q, t = (item - c * Q) * 32 + lane;
                 if (c < nDisc) {
@@ -1099,7 +1097,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                         float* vs = VSUM + (size_t)(N + r) * Tp + t;
                         atomicAdd(vs, an); atomicAdd(vs + Tp, bn);
                     }
-                    if (chk) {
+                    if (CHK) {
                         float ya = rho * (an - zan), yb = rho * (bn - zbn);
                         VOUT[r * Tp + t] = ya; VOUT[(r + 1) * Tp + t] = yb;
                         dD -= (double)(lim * sqrtf(ya * ya + yb * yb));  // support function of the disc
@@ -1116,7 +1114,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     float zn = clampf(vn, capLo, cap);
                     GIN[r * Tp + t] = rho * (2.f * zn - vn);
                     if (doAvg) { atomicAdd(VSUM + (size_t)(N + r) * Tp + t, vn); }
-                    if (chk) {
+                    if (CHK) {
                         float y = rho * (vn - zn);
                         VOUT[r * Tp + t] = y;
                         if (y != 0.f) dD -= (double)(cap * fabsf(y));  // support function of the half line / interval
@@ -1126,11 +1124,13 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         };
         // the first rowShare * nRowWarps items ride on the row warps (after their own rows), the rest is dealt
         // round-robin to the coupling warps
+        auto couple_all = [&](auto chk_tag) {
+        constexpr bool CHK = decltype(chk_tag)::value;
         if (rowWarp) {
-            for (int j = 0; j < rowShare; ++j) couple_item(warp * rowShare + j);
+            for (int j = 0; j < rowShare; ++j) couple_item(warp * rowShare + j, chk_tag);
         }
         if (cwIdx >= 0) {
-            for (int item = rowShare * S.nRowWarps + cwIdx; item < nCT1 * Q; item += nCW) couple_item(item);
+            for (int item = rowShare * S.nRowWarps + cwIdx; item < nCT1 * Q; item += nCW) couple_item(item, chk_tag);
         }
         if (doAgg) {
             // aggregate-power row: quadratic (load flattening) + peak epigraph
@@ -1152,7 +1152,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                 float zk = (pk_w > 0.f) ? fminf(an, pl) : an;  // kW
                 float zn = zk / su;
                 GIN[r * Tp + t] = rho * (2.f * zn - vn);
-                if (chk) {
+                if (CHK) {
                     // Fenchel equality for y in dg(z): -g*(y) = g(z) - <y, z>
                     float y = rho * (vn - zn);
                     VOUT[r * Tp + t] = y;
@@ -1160,13 +1160,19 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     acc -= (double)y * (double)zn;
                 }
             }
-            if (chk) {
+            if (CHK) {
                 zmax = warp_max(zmax);
                 dD += acc;
                 if (lane == 0) dD += (double)pk_w * (double)fmaxf(zmax, pk_p0);
             }
         }
+        };
         if (!chk) {
+            if (rowWarp) {
+                if (fastRows) row_pass_fast();
+                else row_pass(std::false_type{});
+            }
+            couple_all(std::false_type{});
             ACB_TR(3);
             __syncthreads();
             ACB_TR(4);
@@ -1176,11 +1182,16 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
 #ifndef ACB_NOCHECK
 
         // ============================================================= check path
+        // (a check-iteration variant of the fast pass was measured slower: its exact mode ends in the full search)
+        if (rowWarp) row_pass(std::true_type{});
+        couple_all(std::true_type{});
+        ACB_TR(3);
         __syncthreads();  // PART = group sums of z, VOUT = y
         if (doAvg && tid == 0) SCAL[SC_NSUM] = avgFirst ? 1.f : SCAL[SC_NSUM] + 1.f;
         float violC, umaxC; double uqC, plC;
         eval_columns(true, THC, violC, umaxC, uqC, plC);  // HG <- C'y afterwards
         __syncthreads();
+        ACB_TR(4);
         // Lagrangian inner minimum over the box and energy-row terms; averaged candidate
         const float nsum = SCAL[SC_NSUM];
         const bool haveAvg = useAvg && nsum >= 2.f;
@@ -1276,9 +1287,11 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                 }
             }
         }
+        ACB_TR(5);
         __syncthreads();  // PART = group sums of the averaged candidate
         float violA = 3.0e38f, umaxA = -3.0e38f; double uqA = 0.0, plA = 0.0;
         if (haveAvg) eval_columns(false, THA, violA, umaxA, uqA, plA);
+        ACB_TR(6);
         // block reductions
         rE1 = warp_max(rE1); rE2 = warp_max(rE2); rXm = warp_max(rXm); rZm = warp_max(rZm); rYm = warp_max(rYm); rNan = warp_max(rNan); rDz = warp_max(rDz);
         violC = warp_max(violC); umaxC = warp_max(umaxC);
@@ -1519,6 +1532,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         write_part_q();
         write_gin();
         __syncthreads();
+        ACB_TR(7);
 #endif
     }
     if (it > opt.max_iter) it = opt.max_iter;

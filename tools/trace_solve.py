@@ -29,6 +29,7 @@ buf = (C.c_longlong * (NIT * NW * 8))()
 n = L.acb_trace_fetch(buf, NIT * NW * 8)
 a = np.frombuffer(buf, dtype=np.int64).reshape(NIT, NW, 8).astype(np.float64)
 nw = int((a[0, :, 0] > 0).sum())
+full = a[:, :nw, :]
 a = a[:, :nw, :5]
 MHZ = 1965.0
 it0 = a[:, :, 0].min(axis=1, keepdims=True)
@@ -49,3 +50,13 @@ for name, sel in (("plain iterations", [i for i in range(NIT) if (IT0 + i) % 5 !
     print(f" max  {col[sel].max(axis=1).mean():8.2f} {'':8s} {row[sel].max(axis=1).mean():8.2f}")
     print(f"phase ends (us after iteration start): column done {rel[sel, :, 1].max(axis=1).mean():.2f}, barrier1 released {rel[sel, :, 2].min(axis=1).mean():.2f}, "
           f"row done {rel[sel, :, 3].max(axis=1).mean():.2f}, barrier2 released {rel[sel, :, 4].min(axis=1).mean():.2f}")
+
+# the check iteration (it = 125): stamps 3..7 = row pass done, current candidate evaluated (eval_columns + barrier), Lagrangian
+# bound + averaged candidate rows done, averaged candidate evaluated, end of the check path (decision, restart, rebuilt inputs)
+ic = 125 - IT0
+c = full[ic]
+t0 = c[:, 0].min()
+names = ["loop top", "column pass", "barrier 1", "general row pass", "eval current + barrier", "Lagrangian + averaged rows", "eval averaged", "decision + rebuild"]
+print("--- check iteration 125: per-phase end, max over warps [us after iteration start] and the phase's longest warp [us]")
+for k in range(1, 8):
+    print(f"{names[k]:28s} end {((c[:, k].max() - t0) / MHZ):7.2f}   longest {((c[:, k] - c[:, k - 1]).max() / MHZ):7.2f}   mean {((c[:, k] - c[:, k - 1]).mean() / MHZ):7.2f}")
