@@ -216,11 +216,15 @@ def pack_objective(objective: List[ObjectiveComponent], infrastructure, interfac
     if out["gamma"] > 0:
         out["ext"] = ext_acc / out["gamma"]
     if peaks:
-        p0s = {round(p, 12) for _, p in peaks}
-        if len(p0s) > 1:
-            raise NotImplementedError("peak terms with different baselines are not supported on the device path")
-        out["peak_w"] = sum(w for w, _ in peaks)
-        out["peak_p0"] = peaks[0][1]
+        merged = {}
+        for w, p in peaks:
+            merged[round(p, 12)] = merged.get(round(p, 12), 0.0) + w
+        out["peak_w"] = sum(merged.values())
+        out["peak_p0"] = max(merged)
+        if len(merged) > 1:
+            # sum_j w_j max(m, p_j) is piecewise linear in the peak m; the device objective holds one piece at a time and
+            # AdaptiveChargingOptimization.solve() walks the pieces from the top (see _solve_peak_pieces)
+            out["peak_terms"] = sorted(merged.items())
     return out
 
 
@@ -329,6 +333,7 @@ class AdaptiveChargingOptimization:
             sess_energy=np.array(ps["sess_energy"]), min_rates=ps["min_rates"], max_rates=ps["max_rates"],
             alpha=ob["alpha"], beta=ob["beta"], qd=ob["qd"], gamma=ob["gamma"], ext=ob["ext"],
             peak_w=ob["peak_w"], peak_p0=ob["peak_p0"], peak_limit=pl, sess_order=ps["order"], sess_quad=sq,
+            peak_terms=ob.get("peak_terms"),
         )
 
     def build_problem(self, active_sessions, infrastructure, peak_limit=None, prev_peak: float = 0):
@@ -358,6 +363,36 @@ class AdaptiveChargingOptimization:
         opts.setdefault("eps_rel", 2e-5)
         return _cabi.default_options(equality=int(bool(self.enforce_energy_equality)), **opts)
 
+    def _solve_peak_pieces(self, inst: engine.Instance, infrastructure) -> engine.PackedBatch:
+        """Peak / demand-charge components with different baselines (each component takes its own ``baseline_peak``,
+        aco.py:387-400): phi(m) = sum_j w_j max(m, p_j), p_1 < ... < p_K, is convex piecewise linear in the peak m, equal
+        to (w_1 + .. + w_k) m + const on [p_k, p_k+1].  Piece k is the single-term problem (weight w_1 + .. + w_k,
+        baseline p_k) with the peak capped at p_k+1; walking down from the top piece, the first solve whose peak lies
+        above its own baseline is an optimum of the whole problem (phi is below every piece's own single-term
+        objective, and equal to it on the piece).  The cap is the reference's peak constraint (sum of amperes,
+        aco.py:181-198), so it needs one voltage across the site."""
+        volt = np.asarray(infrastructure.voltages, dtype=float)
+        if np.ptp(volt) > 1e-9 * volt.max():
+            raise NotImplementedError("peak terms with different baselines need a single EVSE voltage on the device path")
+        kw_per_a = volt[0] / 1e3
+        terms = inst.peak_terms
+        base_limit = inst.peak_limit
+        pb = None
+        for k in range(len(terms) - 1, -1, -1):
+            inst.peak_p0 = terms[k][0]
+            inst.peak_w = sum(w for _, w in terms[: k + 1])
+            if k + 1 < len(terms):
+                cap = np.full(inst.T, terms[k + 1][0] / kw_per_a)
+                inst.peak_limit = cap if base_limit is None else np.minimum(cap, base_limit)
+            site = self._site_for(infrastructure, inst)
+            pb = engine.PackedBatch(site, [inst]).upload().solve(self._options(inst))
+            if k == 0 or int(pb.status[0].item()) not in (_cabi.ACB_SOLVED, _cabi.ACB_MAX_ITER):
+                break
+            m = float(pb.rates[0, :, : inst.T].sum(dim=0).max().item()) * kw_per_a
+            if m > terms[k][0] * (1 + 1e-6) + 1e-9:
+                break
+        return pb
+
     def solve(self, active_sessions: List[SessionInfo], infrastructure: InfrastructureInfo,
               peak_limit: Union[float, List[float], np.ndarray] = None, prev_peak=0, verbose: bool = False):
         """Returns an (N, T) float64 array of charging rates, rows ordered like
@@ -365,8 +400,11 @@ class AdaptiveChargingOptimization:
         if len(active_sessions) == 0:
             return np.zeros((infrastructure.num_stations, 1))  # aco.py:310-311
         inst = self.build_instance(active_sessions, infrastructure, peak_limit, prev_peak)
-        site = self._site_for(infrastructure, inst)
-        pb = engine.PackedBatch(site, [inst]).upload().solve(self._options(inst))
+        if getattr(inst, "peak_terms", None):
+            pb = self._solve_peak_pieces(inst, infrastructure)
+        else:
+            site = self._site_for(infrastructure, inst)
+            pb = engine.PackedBatch(site, [inst]).upload().solve(self._options(inst))
         rates = pb.rates[0, :, : inst.T].to("cpu", non_blocking=False).numpy().astype(np.float64)
         status = int(pb.status[0].item())
         stats = pb.stats[0].cpu().numpy()

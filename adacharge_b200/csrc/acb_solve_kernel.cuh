@@ -139,13 +139,20 @@ struct SolvePhase {
 
 #ifdef ACB_TRACE
 // development build only (tools/trace_solve.py): per-warp clock64() stamps of block 0 at the phase boundaries
+#ifndef ACB_TR_IT0
 #define ACB_TR_IT0 111
+#endif
 #define ACB_TR_NIT 16
-__device__ long long g_acb_trace[ACB_TR_NIT * 32 * 8];
+#define ACB_TR_SLOTS 16
+__device__ long long g_acb_trace[ACB_TR_NIT * 32 * ACB_TR_SLOTS];
 __device__ __forceinline__ long long acb_clock() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) :: "memory"); return c; }
-#define ACB_TR(k) do { if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT && lane == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + warp) * 8 + (k)] = acb_clock(); } while (0)
+#define ACB_TR(k) do { if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT && lane == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + warp) * ACB_TR_SLOTS + (k)] = acb_clock(); } while (0)
+// (stamp that waits for a value: the float operand orders the clock read after the instructions producing it)
+__device__ __forceinline__ long long acb_clock_after(float v) { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) : "f"(v) : "memory"); return c; }
+#define ACB_TRV(k, v) do { if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT) { long long c_ = acb_clock_after(v); if (lane == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + warp) * ACB_TR_SLOTS + (k)] = c_; } } while (0)
 #else
 #define ACB_TR(k) do { } while (0)
+#define ACB_TRV(k, v) do { } while (0)
 #endif
 
 // FAST: the caller declared every minimum rate 0 (acb_batch.lb_zero) and rows hold one session.  The lower-bound
@@ -726,23 +733,29 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
     // counts.  With restoration the whole period is scaled to (numerically) zero; without it the violation is the
     // current in amperes, measured against viol_tol like the relative ones.
     auto zero_limit = [&](float amps) -> float { return canRestore ? (amps > 1e-5f ? 1.0e30f : 0.f) : 1.f + amps; };
+    // Two adjacent lanes share a period: the group sums, the coupling rows and the C'y outputs are dealt to them by parity
+    // (the pass is a chain of dependent shared-memory loads; one thread per period left 9 of the block's warps to do it).
     auto eval_columns = [&](bool with_hy, float* TH, float& viol, float& umax, double& uq, double& plin) {
         viol = -1.f; umax = -3.0e38f; uq = 0.0; plin = 0.0;
-        for (int t = tid; t < Tp; t += nthreads) {
+        const int h = tid & 1, half = nthreads >> 1;
+        // a row with limit L amperes may exceed it by min(viol_tol L, viol_abs): the relative excess is scaled up where
+        // viol_abs (1e-3 A, the bar of the reference's own tests) is the tighter of the two
+        auto vfac = [&](float lim_amps) -> float { return (opt.viol_abs > 0.f) ? fmaxf(1.f, lim_amps * opt.viol_tol / opt.viol_abs) : 1.f; };
+        for (int base = 0; base < Tp; base += half) {
+            const int t = base + (tid >> 1);
+            if (t >= Tp) continue;  // (whole warps: Tp and half are multiples of 16)
             float pcol = 0.f;
-            for (int g = 0; g < NG; ++g) {
+            for (int g = h; g < NG; g += 2) {
                 float sz = 0.f;
                 for (int p = PGOFF[g]; p < PGOFF[g + 1]; ++p) sz += PART[p * Tp + t];
                 HG[g * Tp + t] = sz;
                 pcol += (ALPHA[t] + KG[g] * BETA[t]) * sz;  // linear cost of the period (same coefficient within a group)
             }
+            __syncwarp();  // the partner's group sums
             float worst = 0.f;  // worst current / limit of the period
             float vmax = -1.f;  // worst excess in units of the row's tolerance: relative, tightened to viol_abs amperes on large limits
-            // a row with limit L amperes may exceed it by min(viol_tol L, viol_abs): the relative excess is scaled up where
-            // viol_abs (1e-3 A, the bar of the reference's own tests) is the tighter of the two
-            auto vfac = [&](float lim_amps) -> float { return (opt.viol_abs > 0.f) ? fmaxf(1.f, lim_amps * opt.viol_tol / opt.viol_abs) : 1.f; };
-            int r = 0;
-            for (int j = 0; j < nDisc; ++j, r += 2) {
+            for (int j = h; j < nDisc; j += 2) {
+                const int r = 2 * j;
                 float ka = 0.f, kb = 0.f;
                 for (int g = 0; g < NG; ++g) { float sz = HG[g * Tp + t]; ka += CS[r * NG + g] * sz; kb += CS[(r + 1) * NG + g] * sz; }
                 const float cur = sqrtf(ka * ka + kb * kb);
@@ -751,7 +764,8 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                 else { ratio = zero_limit(cur * SCALE[r]); vmax = fmaxf(vmax, ratio - 1.f); }
                 worst = fmaxf(worst, ratio);
             }
-            for (int j = 0; j < nLin + S.has_pl; ++j, ++r) {
+            for (int j = h; j < nLin + S.has_pl; j += 2) {
+                const int r = 2 * nDisc + j;
                 float ka = 0.f;
                 for (int g = 0; g < NG; ++g) ka += CS[r * NG + g] * HG[g * Tp + t];
                 float cap = (j == nLin) ? PLIM[t] : LIM[r];
@@ -759,23 +773,27 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                 if (cap > 0.f && cap < 1.0e30f) { const float ratio = ka / cap; worst = fmaxf(worst, ratio); vmax = fmaxf(vmax, (ratio - 1.f) * vfac(cap * SCALE[r])); }
                 else if (cap <= 0.f) { const float ratio = zero_limit(fmaxf(ka, 0.f) * SCALE[r]); worst = fmaxf(worst, ratio); vmax = fmaxf(vmax, ratio - 1.f); }
             }
+            worst = fmaxf(worst, __shfl_xor_sync(0xffffffffu, worst, 1));
+            vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
             const float th = (canRestore && worst > 1.f) ? 1.f / (worst * (1.f + 2e-7f)) : 1.f;
-            TH[t] = th;
+            if (h == 0) TH[t] = th;
             viol = fmaxf(viol, th < 1.f ? worst * th - 1.f : vmax);
-            plin += (double)(th * pcol);
-            if (S.has_u && t < Tb) {
+            plin += (double)(th * pcol);  // (each lane its own groups: the block sum adds them)
+            if (S.has_u && t < Tb && h == 1) {
                 float ka = 0.f;
                 for (int g = 0; g < NG; ++g) ka += CS[rU * NG + g] * HG[g * Tp + t];
                 float u = ka * su * th;
                 umax = fmaxf(umax, u);
                 uq += (double)(u + EBAR[t]) * (double)(u + EBAR[t]);
             }
-            if (with_hy)
-                for (int g = 0; g < NG; ++g) {
+            if (with_hy) {
+                __syncwarp();  // both lanes are done with the group sums
+                for (int g = h; g < NG; g += 2) {
                     float acc = 0.f;
                     for (int rr = 0; rr < R; ++rr) acc += CS[rr * NG + g] * VOUT[rr * Tp + t];
                     HG[g * Tp + t] = acc;
                 }
+            }
         }
     };
 
@@ -1215,6 +1233,9 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     ub[q] = in ? ubv(row, t) : 0.f;
                     va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] / nsum : 0.f;
                 }
+#ifdef ACB_TRACE
+                if (k == 0) { float sv_ = 0.f; for (int q = 0; q < Q; ++q) sv_ += va[q]; ACB_TRV(12, sv_); }
+#endif
                 // energy-row multipliers of the dual bound: the iterate's (rho1 * mu_s), or the maximiser given y
                 if (refineDual) {
                     float aa[Q];
@@ -1254,11 +1275,13 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                         if (m < 0.0 && SESS_Q[s] > 0.f) dD -= m * m / (4.0 * (double)SESS_Q[s]);
                     }
                 __syncwarp();  // SESS_MU2 is reused for the averaged candidate below
+                if (k == 0) ACB_TRV(13, (float)dD);
                 if (haveAvg) {
                     for (int s = sf; s < sf + scn; ++s) {
                         float mu = newton_mu(va, lb, ub, SESS_A[s], SESS_B[s], SESS_E[s], SESS_MU[s], !MULTI, 16, SESS_Q[s]);
                         if (lane == 0) SESS_MU2[s] = mu;
                         __syncwarp();
+                        if (k == 0) ACB_TRV(14, mu);
                     }
                     const float mu2 = scn ? SESS_MU2[sf] : 0.f;
                     if (hasQuad) {
@@ -1306,6 +1329,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
             rd[RD_PC] = dPc; rd[RD_PA] = dPa; rd[RD_D] = dD; rd[RD_UQC] = uqC; rd[RD_UQA] = uqA; rd[RD_PLC] = plC; rd[RD_PLA] = plA;
         }
         __syncthreads();
+        ACB_TR(7);
         if (tid == 0) {
             float e1 = 0, e2 = 0, xm = 0, zm = 0, ym = 0, nn = 0, vC = -1.f, vA = -1.f, uC = -3.0e38f, uA = -3.0e38f, dz = 0.f;
             double Pc = 0, Pa = 0, D = 0, qC = 0, qA = 0, lC = 0, lA = 0;
@@ -1429,7 +1453,11 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
             SCAL[SC_VIOL] = useA ? vA : vC;
         }
         __syncthreads();
+        ACB_TR(8);
         const float flag = SCAL[SC_FLAG];
+#ifdef ACB_TRACE
+        if (b == 0 && it >= ACB_TR_IT0 && it < ACB_TR_IT0 + ACB_TR_NIT && tid == 0) g_acb_trace[((it - ACB_TR_IT0) * 32 + 31) * ACB_TR_SLOTS + 15] = (long long)flag;
+#endif
         if (flag == 1.f) { status = ACB_SOLVED; break; }
         if (flag == 3.f) { status = ACB_NUMERICAL; break; }
         if (flag == 6.f) { status = ACB_INFEASIBLE; break; }
@@ -1447,18 +1475,19 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         int t = lane + 32 * q;
-                        if (t < Tp) vset(k, q, row, VSUM[(size_t)row * Tp + t] / nsum);
+                        if (t < Tp) { float* vs = VSUM + (size_t)row * Tp + t; vset(k, q, row, *vs / nsum); *vs = 0.f; }
                     }
                 }
             }
+            // (the running sums restart from zero: every element is zeroed by the thread that just read it; rows without
+            // a session never receive a contribution)
             for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = SESS_MU2[i];
-            for (int i = tid; i < R * Tp; i += nthreads) VC[i] = VSUM[(size_t)N * Tp + i] / nsum;
+            for (int i = tid; i < R * Tp; i += nthreads) { float* vs = VSUM + (size_t)N * Tp + i; VC[i] = *vs / nsum; *vs = 0.f; }
             __syncthreads();
             if (S.has_u && warp == nwarps - 1) {
                 float pl = peak_level(SCAL[SC_PLEVEL]);
                 if (lane == 0) SCAL[SC_PLEVEL] = pl;
             }
-            zero_sums();
             if (tid == 0) { SCAL[SC_NSUM] = 0.f; SCAL[SC_NREST] += 1.f; }
             __syncthreads();
             if (flag == 4.f) { status = ACB_SOLVED; if (tid == 0) SCAL[SC_USEDAVG] = 1.f; break; }
@@ -1529,10 +1558,12 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
             if (tid == 0) { SCAL[SC_RHO] = rho; SCAL[SC_NSUM] = 0.f; }  // the average restarts with the new metric
             build_matrix();
         }
+        ACB_TR(9);
         write_part_q();
-        write_gin();
+        ACB_TR(10);
+        if (toAvg || flag >= 10.f) write_gin();  // (otherwise the coupling pass of this iteration left GIN current)
         __syncthreads();
-        ACB_TR(7);
+        ACB_TR(11);
 #endif
     }
     if (it > opt.max_iter) it = opt.max_iter;

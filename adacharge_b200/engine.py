@@ -203,6 +203,7 @@ class Instance:
     peak_limit: Optional[np.ndarray] = None
     sess_order: Optional[np.ndarray] = None  # packed position -> index in the caller's session list
     sess_quad: Optional[np.ndarray] = None   # per-session weight of (energy - planned)^2 in (A*periods)^2 (non_completion_penalty, norm 2)
+    peak_terms: Optional[list] = None        # [(baseline kW, weight)] ascending when peak components differ in baseline (host walks the pieces)
 
 
 def pack_sessions(sessions, infra, period) -> dict:

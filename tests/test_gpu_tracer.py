@@ -62,3 +62,26 @@ def test_traced_components_solve_like_their_builtin_twins(require_gpu, seed):
     assert abs(f - fo) <= 1e-4 * abs(fo) + 1e-7, (f, fo, aco.last_info)
     v = mpc.violations(R, S, I, iface)
     assert v["infrastructure_rel"] <= 1e-5 and v["lb"] <= 0 and v["ub"] <= 0 and v["energy"] <= 1e-4, v
+
+
+@pytest.mark.parametrize("scale", [0.3, 0.75, 1.5], ids=["optimum_above_both", "optimum_between", "optimum_below_both"])
+def test_peak_terms_with_different_baselines(require_gpu, scale):
+    """Two demand-charge components with their own baseline_peak (aco.py:387-400): the sum of two epigraphs with
+    different kinks.  The device objective holds one linear piece of it at a time; solve() walks the pieces.  The
+    baselines are set relative to the peak of the plain (single baseline 0) optimum so that the three cases are hit."""
+    iface = _iface(5, n=12, T=60)
+    S, I = iface.active_sessions(), iface.infrastructure_info()
+    base = [("tou_energy_cost", 1, {}), ("total_energy", 0.4, {}), ("equal_share", 1e-5, {})]
+    R0 = mpc.solve_mpc(base + [("demand_charge", 0.05, {})], S, I, iface, "SOC", False, None, 0.0)
+    k = np.asarray(I.voltages) / 1e3
+    m0 = (k @ R0).max()
+    p1, p2 = 0.8 * scale * m0, 1.3 * scale * m0
+    spec = base + [("demand_charge", 0.03, {"baseline_peak": p1}), ("demand_charge", 0.04, {"baseline_peak": p2})]
+    obj = [ab.ObjectiveComponent(getattr(ab, n), c, kw) for n, c, kw in spec]
+    aco = ab.AdaptiveChargingOptimization(obj, iface)
+    R = aco.solve(S, I)
+    Ro = mpc.solve_mpc(spec, S, I, iface, "SOC", False, None, 0.0)
+    f, fo = (mpc.evaluate_objective(X, spec, I, iface, S, 0.0) for X in (R, Ro))
+    assert abs(f - fo) <= 1e-4 * abs(fo) + 1e-7, (f, fo, (k @ R).max(), (k @ Ro).max(), p1, p2, aco.last_info)
+    v = mpc.violations(R, S, I, iface)
+    assert v["infrastructure_rel"] <= 1e-5 and v["lb"] <= 0 and v["ub"] <= 0 and v["energy"] <= 1e-4, v

@@ -401,6 +401,18 @@ def test_quadratic_non_completion_penalty_packs_per_session_weights():
         ab.pack_objective([ab.ObjectiveComponent(ab.non_completion_penalty, -1.0, {"norm": 2})], I, iface, 10)
 
 
+def test_peak_terms_with_different_baselines_are_kept_as_pieces():
+    iface = ab.TestingInterface(config_c2(0))
+    I = iface.infrastructure_info()
+    ob = ab.pack_objective([ab.ObjectiveComponent(ab.demand_charge, 0.5, {"baseline_peak": 30.0}), ab.ObjectiveComponent(ab.peak, -2.0, {"baseline_peak": 20.0}),
+                            ab.ObjectiveComponent(ab.demand_charge, 0.25, {"baseline_peak": 30.0})], I, iface, 10)
+    dc = iface.get_demand_charge()
+    assert ob["peak_terms"] == [(20.0, pytest.approx(2.0)), (30.0, pytest.approx(0.75 * dc))]   # (the site's previous peak is 17.1 kW)
+    assert ob["peak_w"] == pytest.approx(2.0 + 0.75 * dc) and ob["peak_p0"] == 30.0   # the top piece
+    one = ab.pack_objective([ab.ObjectiveComponent(ab.demand_charge, 0.5, {"baseline_peak": 30.0}), ab.ObjectiveComponent(ab.peak, -2.0, {"baseline_peak": 30.0})], I, iface, 10)
+    assert "peak_terms" not in one and one["peak_p0"] == 30.0
+
+
 def test_batched_objective_components_validation():
     from adacharge_b200.batched import objective_components
 
