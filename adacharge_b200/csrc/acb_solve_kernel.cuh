@@ -1213,6 +1213,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         // Lagrangian inner minimum over the box and energy-row terms; averaged candidate
         const float nsum = SCAL[SC_NSUM];
         const bool haveAvg = useAvg && nsum >= 2.f;
+        const float inv_nsum = 1.f / fmaxf(nsum, 1.f);
         const bool refineDual = opt.dual_refine > 1 || (opt.dual_refine == 1 && SCAL[SC_STALL] >= 1.f);
         double dPa = 0.0;
         if (rowWarp) {
@@ -1231,8 +1232,11 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     bool in = t < Tp;
                     lb[q] = in ? lbv(row, t) : 0.f;
                     ub[q] = in ? ubv(row, t) : 0.f;
-                    va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] / nsum : 0.f;
+                    va[q] = (in && haveAvg) ? VSUM[(size_t)row * Tp + t] : 0.f;  // (all loads in flight together: a division
+                    // per load would wait for each in turn)
                 }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) va[q] *= inv_nsum;
 #ifdef ACB_TRACE
                 if (k == 0) { float sv_ = 0.f; for (int q = 0; q < Q; ++q) sv_ += va[q]; ACB_TRV(12, sv_); }
 #endif
@@ -1472,17 +1476,18 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     const int* sl = SLOT + (warp * TPW + k) * 6;
                     int row = sl[0];
                     if (row < 0) continue;
+                    float* vs = VSUM + (size_t)row * Tp + lane;
+                    float sv[Q];
 #pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        int t = lane + 32 * q;
-                        if (t < Tp) { float* vs = VSUM + (size_t)row * Tp + t; vset(k, q, row, *vs / nsum); *vs = 0.f; }
-                    }
+                    for (int q = 0; q < Q; ++q) sv[q] = vs[32 * q];
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) { vset(k, q, row, sv[q] * inv_nsum); vs[32 * q] = 0.f; }
                 }
             }
             // (the running sums restart from zero: every element is zeroed by the thread that just read it; rows without
             // a session never receive a contribution)
             for (int i = tid; i < B.S_max; i += nthreads) SESS_MU[i] = SESS_MU2[i];
-            for (int i = tid; i < R * Tp; i += nthreads) { float* vs = VSUM + (size_t)N * Tp + i; VC[i] = *vs / nsum; *vs = 0.f; }
+            for (int i = tid; i < R * Tp; i += nthreads) { float* vs = VSUM + (size_t)N * Tp + i; VC[i] = *vs * inv_nsum; *vs = 0.f; }
             __syncthreads();
             if (S.has_u && warp == nwarps - 1) {
                 float pl = peak_level(SCAL[SC_PLEVEL]);
