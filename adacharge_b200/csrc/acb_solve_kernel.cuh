@@ -111,7 +111,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int R, int NG, int NP, 
 
 // float scalars
 enum { SC_RHO = 0, SC_PLEVEL, SC_FLAG, SC_NEWRHO, SC_CS, SC_RP, SC_RD, SC_GAP, SC_VIOL, SC_NSUM, SC_NREST, SC_USEDAVG, SC_LBPOS, SC_STALL, SC_NRESCUE,
-       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST, SC_UBVAR, SC_NFEAS, SC_BESTVIOL, SC_VSTALL };
+       SC_RHOSTART, SC_DZ, SC_KAP, SC_NDZ, SC_RATE_EST, SC_UBVAR, SC_NFEAS, SC_BESTVIOL, SC_VSTALL, SC_RATEM, SC_RATECNT, SC_NRATEOK };
 // double scalars
 enum { SD_DBEST = 0, SD_GAPRESTART, SD_BESTGAP, SD_PMAX };
 // per-warp float reduction slots (max-type)
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         SCAL[SC_STALL] = 0.f;
         SCAL[SC_NRESCUE] = 0.f;
         SCAL[SC_RHOSTART] = SCAL[SC_RHO];
-        SCAL[SC_DZ] = 0.f; SCAL[SC_KAP] = 1.f; SCAL[SC_NDZ] = 0.f; SCAL[SC_RATE_EST] = -1.f;
+        SCAL[SC_DZ] = 0.f; SCAL[SC_KAP] = 1.f; SCAL[SC_RATEM] = 1.f; SCAL[SC_RATECNT] = 0.f; SCAL[SC_NRATEOK] = 0.f; SCAL[SC_NDZ] = 0.f; SCAL[SC_RATE_EST] = -1.f;
         SCAL[SC_NFEAS] = 0.f; SCAL[SC_BESTVIOL] = 3.0e38f; SCAL[SC_VSTALL] = 0.f;
     }
     __syncthreads();
@@ -869,6 +869,9 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
         const bool chk = (it % opt.check_every == 0) || (it == opt.max_iter) || (it == ACB_FIRST_CHECK);  // easy / warm-started instances stop early
 #endif
         const bool doAvg = useAvg && (it % avgEvery == 0);
+        // rate polish: this check measures the movement of the schedule (every check, or every fourth once the iteration
+        // has turned out to contract slowly; see the check path)
+        const bool rateTick = polish && chk && SCAL[SC_RATECNT] + 1.f >= SCAL[SC_RATEM];
         const bool avgFirst = SCAL[SC_NSUM] == 0.f;
         float rE1 = 0.f, rE2 = 0.f, rXm = 0.f, rZm = 0.f, rYm = 0.f, rNan = 0.f, rDz = 0.f;
         double dPc = 0.0, dD = 0.0;  // primal (linear + diagonal part) of the current candidate; dual pieces
@@ -925,7 +928,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                         rZm = fmaxf(rZm, fabsf(zn));
                         rYm = fmaxf(rYm, fabsf(rho1 * (vn - zn)));
                         if (!(fabsf(vn) < 1.0e30f)) rNan = 1.f;
-                        if (polish) {  // movement of the schedule since the previous check
+                        if (rateTick) {  // movement of the schedule since the previous measurement
                             float* zp = ZPREV + (size_t)row * Tp + t;
                             rDz = fmaxf(rDz, fabsf(zn - *zp));
                             *zp = zn;
@@ -1371,21 +1374,51 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
             float flag = 0.f;
             // a (slightly) negative gap is rounding noise around a converged pair and passes; negative tolerances
             // therefore mean "never stop on the gap" (run the whole iteration budget)
-            // rate polish: with a linearly converging iteration the movement dz over one check period and the ratio
-            // kap of two consecutive movements give the remaining distance dz kap / (1 - kap); the larger of the last
-            // two ratios is used, and the estimate only counts from the third check after a (re)start
+            // rate polish: with a linearly converging iteration the movement dz between two measurements and the ratio
+            // kap of two consecutive movements give the remaining distance dz kap / (1 - kap).  The extrapolation is only
+            // trusted while the contraction per measurement is strong (ratios <= 0.5: factor <= 1).  On nearly flat
+            // objectives the schedule contracts by ~0.9 per check period, the movement per period at 1e-3 A from the
+            // optimum (~1e-4 A) is as large as the float32 noise of the iteration, and single ratios are meaningless:
+            // the measurements then switch to every FOURTH check (contraction ~0.7, four times the signal).  There the
+            // stop is est <= rate_tol with the ratio capped at 0.9, or a movement below rate_tol at two consecutive
+            // measurements: the float32 floor of the schedule on such objectives is 1e-4 .. 5e-4 A, where the ratios carry
+            // no information any more (the maximum over 15 k elements is biased upwards by the noise, so the movement is
+            // not underestimated; polish_min_qd keeps flatter objectives, which contract slower than ~0.7 per hundred
+            // iterations, out of the polish).
             bool okRate = true;
             if (polish) {
-                const float dzp = SCAL[SC_DZ], nd = SCAL[SC_NDZ];
-                const float kap = (nd >= 1.f && dzp > 0.f) ? fminf(dz / dzp, 0.98f) : 0.98f;
-                const float ku = fmaxf(kap, SCAL[SC_KAP]);
-                const float est = (nd >= 2.f) ? dz * ku / (1.f - ku) : 3.0e38f;
-                SCAL[SC_RATE_EST] = est;
-                SCAL[SC_KAP] = (nd >= 1.f) ? kap : 0.f;
-                SCAL[SC_DZ] = dz;
-                SCAL[SC_NDZ] = nd + 1.f;
-                // (a movement at the float32 noise floor of the rates counts as converged whatever the ratio says)
-                okRate = est <= opt.rate_tol || (nd >= 2.f && dz <= 1e-5f);
+                okRate = false;
+                if (rateTick) {
+                    const float dzp = SCAL[SC_DZ], nd = SCAL[SC_NDZ], m = SCAL[SC_RATEM];
+                    const float kap = (nd >= 1.f && dzp > 0.f) ? dz / dzp : 1.f;
+                    const float kprev = (nd >= 2.f) ? SCAL[SC_KAP] : (m > 1.f ? 0.f : 1.f);
+                    const float ku = fminf(fmaxf(kap, kprev), m > 1.f ? 0.9f : 0.98f);
+                    float est = 3.0e38f, nok = 0.f;
+                    bool slow = false;
+                    if (m <= 1.f) {
+                        if (nd >= 2.f) {
+                            est = dz * ku / (1.f - ku);
+                            // (a movement at the float32 noise floor of the rates counts as converged whatever the ratio says)
+                            okRate = (ku <= 0.5f && est <= opt.rate_tol) || dz <= 1e-5f;
+                            slow = !okRate && ku > 0.5f;
+                        }
+                    } else if (nd >= 1.f) {
+                        est = dz * ku / (1.f - ku);
+                        nok = (dz <= opt.rate_tol) ? SCAL[SC_NRATEOK] + 1.f : 0.f;
+                        okRate = est <= opt.rate_tol || nok >= 2.f;
+                        if (okRate && est > opt.rate_tol) est = dz;  // at the floor: nothing below the movement itself is resolved
+                    }
+                    SCAL[SC_RATE_EST] = est;
+                    SCAL[SC_NRATEOK] = nok;
+                    if (slow) {  // start over on the long baseline (the snapshot was just refreshed)
+                        SCAL[SC_RATEM] = 4.f; SCAL[SC_NDZ] = 0.f; SCAL[SC_DZ] = 0.f; SCAL[SC_KAP] = 0.f;
+                    } else {
+                        SCAL[SC_KAP] = (nd >= 1.f) ? kap : 0.f;
+                        SCAL[SC_DZ] = dz;
+                        SCAL[SC_NDZ] = nd + 1.f;
+                    }
+                    SCAL[SC_RATECNT] = 0.f;
+                } else SCAL[SC_RATECNT] += 1.f;
             }
             const bool certC = gapC <= tolC && vC <= opt.viol_tol;  // gap and violation certified; the polish may still be running
             const bool okC = certC && okRate;
@@ -1449,7 +1482,7 @@ __global__ void __launch_bounds__(TPW == 2 ? 1024 : (FAST ? ACB_FAST_THREADS : 7
                     }
                 }
             }
-            if (flag == 5.f || flag >= 10.f) SCAL[SC_NDZ] = 0.f;  // the iterate jumps: the movement history starts over
+            if (flag == 5.f || flag >= 10.f) { SCAL[SC_NDZ] = 0.f; SCAL[SC_NRATEOK] = 0.f; }  // the iterate jumps: the movement history starts over
             SCAL[SC_FLAG] = flag;
             SCAL[SC_RP] = rp_rel; SCAL[SC_RD] = rd_rel;
             const bool useA = (flag == 4.f);

@@ -36,5 +36,5 @@ for g in gold:
         err, info = run(g, **o)
         print(f"  {name:42s} max|dR| {err if err is None else format(err, '.2e')} A  iters {info['iters']:6d} status {info['status']} gap {info['gap']:.1e} rate_est {info.get('rate_est')}")
     for mi in (100, 200, 400, 800, 1600, 3200, 6400, 12800):
-        err, info = run(g, eps_rel=-1.0, eps_abs=-1.0, max_iter=mi, rate_tol=0.0)
-        print(f"  fixed {mi:6d} iterations: max|dR| {err:.2e} A  gap {info['gap']:.1e}")
+        err, info = run(g, eps_rel=-1.0, eps_abs=-1.0, max_iter=mi, rate_tol=0.0, accept_inaccurate=dict(gap=1e9, violation=1e9))
+        print(f"  fixed {mi:6d} iterations: max|dR| {err if err is None else format(err, '.2e')} A  gap {info['gap']:.1e}")
