@@ -38,6 +38,9 @@ struct SiteDev {
     const float* Up;        // [R*Rp] U with rows padded to Rp = roundup(R, 4) (general path, float4 loads)
     const float* Ut;        // [R*Rp] U' padded the same way
     int Rp;
+    const float* Cp;        // [R*NGp] C with rows padded to NGp = roundup(NG, 4) (general path: k-major operand of hg = C'h)
+    const float* Ct;        // [NG*Rp] C' padded the same way (k-major operand of b = C sa)
+    int NGp;
     const float* lam;       // [R] eigenvalues
     const float* row_scale; // [R]
     const float* lim;       // [R] limit / row_scale (disc rows: both entries; 0 for pl/u rows)

@@ -284,6 +284,13 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
             for (int b2 = 0; b2 < R; ++b2) { up[(size_t)a * Rp + b2] = Uf[(size_t)a * R + b2]; ut[(size_t)a * Rp + b2] = Uf[(size_t)b2 * R + a]; }
         if ((rc = upload(s, up, &d.Up)) != ACB_OK) { acb_site_destroy(s); return rc; }
         if ((rc = upload(s, ut, &d.Ut)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        const int NGp = (NG + 3) & ~3;
+        d.NGp = NGp;
+        std::vector<float> cp((size_t)std::max(R, 1) * NGp, 0.f), ct((size_t)NG * std::max(Rp, 4), 0.f);
+        for (int a = 0; a < R; ++a)
+            for (int g = 0; g < NG; ++g) { cp[(size_t)a * NGp + g] = Cf[(size_t)a * NG + g]; ct[(size_t)g * Rp + a] = Cf[(size_t)a * NG + g]; }
+        if ((rc = upload(s, cp, &d.Cp)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        if ((rc = upload(s, ct, &d.Ct)) != ACB_OK) { acb_site_destroy(s); return rc; }
     }
     UP(acos_, a_cos) UP(asin_, a_sin) UP(lim64, limits) UP(mp, max_pilot) UP(aoff, allow_off) UP(avals, allow_vals)
     {

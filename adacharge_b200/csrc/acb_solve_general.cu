@@ -232,7 +232,7 @@ struct RowStore<0> {
 };
 
 template <int Q, int MODE>
-__global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
+__global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
     const int g = blockIdx.x, b = blockIdx.y;
     if (W.status[b] >= 0 && MODE != 4) return;
     constexpr bool DYN = (Q == 0);
@@ -258,20 +258,71 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
     const float rescale = (MODE == 5) ? sc[GS_E1] : 1.f;
     if (MODE == 5 && rescale == 1.f) return;
     RowStore<Q> rs(DYN ? dsm + (size_t)warp * 4 * Tp : nullptr, Tp, lane);
-    for (int k = grp_off[g] + warp; k < grp_off[g + 1]; k += nw) {
+    const int* SO = B.sess_rate_off + (size_t)b * B.S_max;
+    // the group's row of the column pass (K'h - c), the same for every EVSE of the group
+    const float* HGg = W.HG + ((size_t)b * D.NG + g) * Tp;
+    float hgq[Q > 0 ? Q : 1];
+    if constexpr (!DYN) {
+        if (MODE == 0 || MODE == 3) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) hgq[q] = HGg[lane + 32 * q];
+        }
+    }
+    auto hg_at = [&](int q) -> float { if constexpr (DYN) return HGg[lane + 32 * q]; else return hgq[q]; };
+    // register path: the next row's v is requested before the current row's multiplier search starts
+    const int kend = grp_off[g + 1];
+    float vnx[Q > 0 ? Q : 1];
+    if constexpr (!DYN) {
+        const int k0 = grp_off[g] + warp;
+        if (k0 < kend) {
+            const size_t bn = ((size_t)b * D.N + S.slot_row[k0]) * Tp + lane;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) vnx[q] = W.V[bn + 32 * q];
+        }
+    }
+    for (int k = grp_off[g] + warp; k < kend; k += nw) {
         const int row = S.slot_row[k];
         const size_t base = ((size_t)b * D.N + row) * Tp + lane;
         const int sf = W.row_first[(size_t)b * D.N + row], scn = W.row_cnt[(size_t)b * D.N + row];
+        if constexpr (DYN) {
+            for (int q = 0; q < nq; ++q) rs.V(q) = W.V[base + 32 * q];
+        } else {
 #pragma unroll
-        for (int q = 0; q < nq; ++q) { rs.V(q) = W.V[base + 32 * q]; rs.LB(q) = W.LB[base + 32 * q]; rs.UB(q) = W.UB[base + 32 * q]; }
+            for (int q = 0; q < Q; ++q) rs.V(q) = vnx[q];
+            if (k + nw < kend) {
+                const size_t bn = ((size_t)b * D.N + S.slot_row[k + nw]) * Tp + lane;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) vnx[q] = W.V[bn + 32 * q];
+            }
+        }
+        // rate bounds straight from the session table (charging_rate_bounds, aco.py:61-79; same rule as k_bounds_general):
+        // a constant (min, max) pair per session costs two warp-uniform loads instead of two streamed rows
+#pragma unroll
+        for (int q = 0; q < nq; ++q) { rs.LB(q) = 0.f; rs.UB(q) = 0.f; }
+        for (int s = sf; s < sf + scn; ++s) {
+            const int a = SA[s], len = SL[s], off = SO[s];
+#pragma unroll
+            for (int q = 0; q < nq; ++q) {
+                const int j = lane + 32 * q - a;
+                if (j >= 0 && j < len) {
+                    const int ri = off >= 0 ? off + j : -(off + 1);
+                    const float lo = B.min_rates[ri];
+                    rs.LB(q) = lo; rs.UB(q) = fmaxf(B.max_rates[ri], lo);
+                }
+            }
+        }
         if (MODE == 0) {
             float zo[Q > 0 ? Q : 1];  // previous z for the dual residual (register path only; long horizons report r_dual = 0)
+            // one session on the row (the usual case): the bounds are zero outside its window, so clamp(v - mu, lb, ub) is
+            // already 0 there and neither the multiplier lookup nor the window tests are needed
+            const bool one = (scn == 1);
+            float mu1 = one ? MU[sf] : 0.f;
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
                 const int t = lane + 32 * q;
                 const float vq = rs.V(q);
-                float z = clampf(vq - mu_at(MU, SA, SL, sf, scn, t), rs.LB(q), rs.UB(q));
-                float x = (rho1 * (2.f * z - vq) + W.HG[((size_t)b * D.NG + g) * Tp + t]) * inv_d;
+                float z = clampf(vq - (one ? mu1 : mu_at(MU, SA, SL, sf, scn, t)), rs.LB(q), rs.UB(q));
+                float x = (rho1 * (2.f * z - vq) + hg_at(q)) * inv_d;
                 rs.V(q) = vq + alpha * (x - z);
                 if constexpr (!DYN) zo[q] = z;
                 e1 = fmaxf(e1, fabsf(x - z));
@@ -291,13 +342,22 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                 for (int step = 0; step < 16; ++step) {
                     float E = 0.f;
                     int nf = 0;
+                    if (one) {
 #pragma unroll
-                    for (int q = 0; q < nq; ++q) {
-                        const int t = lane + 32 * q;
-                        if (t >= a && t < e) {
-                            float w = rs.V(q) - mu;
+                        for (int q = 0; q < nq; ++q) {
+                            const float w = rs.V(q) - mu;
                             E += clampf(w, rs.LB(q), rs.UB(q));
                             nf += (w > rs.LB(q) && w < rs.UB(q)) ? 1 : 0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < nq; ++q) {
+                            const int t = lane + 32 * q;
+                            if (t >= a && t < e) {
+                                float w = rs.V(q) - mu;
+                                E += clampf(w, rs.LB(q), rs.UB(q));
+                                nf += (w > rs.LB(q) && w < rs.UB(q)) ? 1 : 0;
+                            }
                         }
                     }
                     E = wsum(E);
@@ -318,13 +378,14 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                     mu = mun;
                 }
                 if (lane == 0) MU[s] = mu;
+                mu1 = mu;
                 __syncwarp();
             }
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
                 const int t = lane + 32 * q;
                 const float vq = rs.V(q);
-                float zn = clampf(vq - mu_at(MU, SA, SL, sf, scn, t), rs.LB(q), rs.UB(q));
+                float zn = clampf(vq - (one ? mu1 : mu_at(MU, SA, SL, sf, scn, t)), rs.LB(q), rs.UB(q));
                 add_part(q, 2.f * zn - vq);
                 W.V[base + 32 * q] = vq;
                 if constexpr (!DYN) e2 = fmaxf(e2, fabsf(zn - zo[q]));
@@ -344,7 +405,7 @@ __global__ void __launch_bounds__(256, Q > 0 ? 3 : 1) k_rows(SiteDev S, acb_batc
                     dsum += (double)(c * z + qd * z * z);
                 }
                 if (MODE == 3) {
-                    float rt = AL[t] + kgc * BE[t] + W.HG[((size_t)b * D.NG + g) * Tp + t] + rho1 * mu;
+                    float rt = AL[t] + kgc * BE[t] + hg_at(q) + rho1 * mu;
                     float phi;
                     if (qd > 0.f) { float xs = clampf(-rt / (2.f * qd), lbq, ubq); phi = qd * xs * xs + rt * xs; }
                     else phi = fminf(lbq * rt, ubq * rt);
@@ -647,6 +708,203 @@ __global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_option
         }
 }
 
+// ---------------------------------------------------------------------------- iteration column pass as a blocked product
+// One stage of the Woodbury chain for a tile of 32 periods: out[m][c] = epi(sum_k MatT[k][m] * in[k][c]), m < M, c < 32.
+// MatT is the k-major operand in global memory (row stride ldm, a multiple of 4, zero padded; shared by every instance of
+// the site), staged through `mbuf` in chunks of 32 k-rows with the next chunk's global loads in flight while the current one
+// is multiplied.  256 threads; thread (tr, tc) = (tid / 8, tid % 8) owns rows RPT*tr .. +RPT-1 and periods 4*tc .. +3 of a
+// 32*RPT-row block: per k one 16-byte (RPT = 4) shared-memory load of the matrix, one of the input vector, 4*RPT FMAs
+// (both loads are one wavefront: 4 distinct row quads and 8 distinct period quads per warp).
+constexpr int MM_KC = 32;
+template <int RPT, class Epi>
+__device__ __forceinline__ void mm_stage(const float* __restrict__ MatT, int ldm, int K, int M, const float* __restrict__ in,
+                                         float* __restrict__ mbuf, Epi epi) {
+    constexpr int MB = 32 * RPT, NV = MM_KC * MB / 4 / 256;  // float4 per thread and chunk
+    const int tid = threadIdx.x, tr = tid >> 3, tc = tid & 7;
+    for (int m0 = 0; m0 < M; m0 += MB) {
+        float acc[RPT][4];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        float4 pre[NV];
+        auto fetch = [&](int k0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int j = tid + 256 * i, kk = j / (MB / 4), c4 = j - kk * (MB / 4);
+                const int k = k0 + kk, m = m0 + 4 * c4;
+                pre[i] = (k < K && m < ldm) ? __ldg(reinterpret_cast<const float4*>(MatT + (size_t)k * ldm + m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        fetch(0);
+        for (int k0 = 0; k0 < K; k0 += MM_KC) {
+            __syncthreads();  // the previous chunk (and the previous stage's output) is no longer being read / is complete
+#pragma unroll
+            for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(mbuf)[tid + 256 * i] = pre[i];
+            __syncthreads();
+            if (k0 + MM_KC < K) fetch(k0 + MM_KC);
+            const int kmax = min(MM_KC, K - k0);
+            const float* inp = in + (size_t)k0 * 32 + 4 * tc;
+            const float* mp = mbuf + RPT * tr;
+#pragma unroll 4
+            for (int kk = 0; kk < kmax; ++kk) {
+                const float4 bq = *reinterpret_cast<const float4*>(inp + kk * 32);
+                float a[RPT];
+                if constexpr (RPT == 4) {
+                    const float4 aq = *reinterpret_cast<const float4*>(mp + kk * MB);
+                    a[0] = aq.x; a[1] = aq.y; a[2] = aq.z; a[3] = aq.w;
+                } else {
+                    const float2 aq = *reinterpret_cast<const float2*>(mp + kk * MB);
+                    a[0] = aq.x; a[1] = aq.y;
+                }
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    acc[i][0] = fmaf(a[i], bq.x, acc[i][0]); acc[i][1] = fmaf(a[i], bq.y, acc[i][1]);
+                    acc[i][2] = fmaf(a[i], bq.z, acc[i][2]); acc[i][3] = fmaf(a[i], bq.w, acc[i][3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int m = m0 + RPT * tr + i;
+            if (m < M) epi(m, 4 * tc, acc[i]);
+        }
+    }
+}
+
+// Iteration column pass: block per (tile of 32 periods, instance), 256 threads.
+//   b = C sa - (d/rho) g,  y1 = diag(1/(d/rho+lam)) U' b,  h = -U y1,  hg = C' h - c,  Kx = (g - h)/rho,  v_c += alpha (Kx - z_c)
+// The four products are mm_stage calls (shared-memory blocked, FMA bound); everything else is one pass over the tile.
+__global__ void __launch_bounds__(256, 3) k_cols_it(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
+    constexpr int TW = 32;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    if (W.status[b] >= 0) return;
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int R = D.R, NG = D.NG, Tp = D.Tp, t = tile * TW + lane, Tb = B.T[b], Rp = S.Rp;
+    float* mbuf = sm;                               // [MM_KC][128] matrix chunk
+    float* sa = mbuf + MM_KC * 128;                 // [max(NG, Rp)][TW]  group inputs, later y1
+    float* gg = sa + (size_t)max(NG, Rp) * TW;      // [R][TW]   rho (2 z_c - v_c)
+    float* bv = gg + (size_t)R * TW;                // [Rp][TW]  b, later h
+    float* y1 = sa;
+    const float* sc = W.scal + (size_t)b * GS_N;
+    const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, dr = dd / rho;
+    const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], plevel = sc[GS_PLEVEL];
+    const float su = D.has_u ? S.row_scale[D.rU] : 1.f;
+    const float linLo = D.lin_two_sided ? -1.f : -3.0e38f;
+    const float* AL = W.AL + (size_t)b * Tp;
+    const float* BE = W.BE + (size_t)b * Tp;
+    const float* ext = B.ext ? B.ext + (size_t)b * Tp : nullptr;
+    float* VC = W.VC + (size_t)b * R * Tp;
+    float* KX = W.KX + (size_t)b * R * Tp;
+    // ---- inputs.  The tile of the coupling rows' v is staged through `bv` (free until the first product's epilogue) and the
+    // group sums go straight into `sa`: every thread issues its (up to four) 16-byte loads before it uses any of them, so
+    // the tile costs one memory round trip instead of one per row.
+    const int t4 = tile * TW;
+    {
+        const int n = R * 8;
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            float4 tmp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + tid + 256 * u;
+                if (i < n) tmp[u] = *reinterpret_cast<const float4*>(VC + (size_t)(i >> 3) * Tp + t4 + 4 * (i & 7));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + tid + 256 * u;
+                if (i < n) reinterpret_cast<float4*>(bv)[i] = tmp[u];
+            }
+        }
+        const int ng8 = NG * 8;
+        const float* SGb = W.SG + (size_t)b * NG * Tp;
+        for (int i0 = 0; i0 < ng8; i0 += 1024) {
+            float4 tmp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + tid + 256 * u;
+                if (i < ng8) tmp[u] = *reinterpret_cast<const float4*>(SGb + (size_t)(i >> 3) * Tp + t4 + 4 * (i & 7));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + tid + 256 * u;
+                if (i < ng8) {
+                    const int g = i >> 3, c = 4 * (i & 7);
+                    const float4 al4 = *reinterpret_cast<const float4*>(AL + t4 + c), be4 = *reinterpret_cast<const float4*>(BE + t4 + c);
+                    const float ng = S.ngrp[g], k = S.kg[g];
+                    reinterpret_cast<float4*>(sa)[i] = make_float4(rho1 * tmp[u].x - ng * (al4.x + k * be4.x), rho1 * tmp[u].y - ng * (al4.y + k * be4.y),
+                                                                   rho1 * tmp[u].z - ng * (al4.z + k * be4.z), rho1 * tmp[u].w - ng * (al4.w + k * be4.w));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < R; r += nw) {
+        const float v = bv[r * TW + lane];
+        float z;
+        if (r < 2 * D.nDisc) {
+            const int r0 = r & ~1;
+            float za, zb;
+            proj_disc(bv[r0 * TW + lane], bv[(r0 + 1) * TW + lane], S.lim[r0], za, zb);
+            z = (r & 1) ? zb : za;
+        } else if (r < 2 * D.nDisc + D.nLin) z = clampf(v, (linLo < -1.0e30f) ? linLo : linLo * S.lim[r], S.lim[r]);
+        else if (D.has_pl && r == D.rPL) z = fminf(v, (B.peak_limit && t < Tb) ? B.peak_limit[(size_t)b * Tp + t] / S.row_scale[D.rPL] : 3.0e38f);
+        else {
+            const float rp = rho / (su * su), a = (rp * (v * su) - 2.f * Gamma * ((ext && t < Tb) ? ext[t] : 0.f)) / (rp + 2.f * Gamma);
+            z = ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+        }
+        gg[r * TW + lane] = rho * (2.f * z - v);
+    }
+    // (mm_stage starts with a barrier)
+    mm_stage<4>(S.Ct, Rp, NG, R, sa, mbuf, [&](int m, int c, const float* a) {
+        const float4 g4 = *reinterpret_cast<const float4*>(gg + m * TW + c);
+        *reinterpret_cast<float4*>(bv + m * TW + c) = make_float4(a[0] - dr * g4.x, a[1] - dr * g4.y, a[2] - dr * g4.z, a[3] - dr * g4.w);
+    });
+    mm_stage<4>(S.Up, Rp, R, R, bv, mbuf, [&](int m, int c, const float* a) {
+        const float inv = 1.f / (dr + S.lam[m]);
+        *reinterpret_cast<float4*>(y1 + m * TW + c) = make_float4(a[0] * inv, a[1] * inv, a[2] * inv, a[3] * inv);
+    });
+    mm_stage<4>(S.Ut, Rp, R, R, y1, mbuf, [&](int m, int c, const float* a) {
+        *reinterpret_cast<float4*>(bv + m * TW + c) = make_float4(-a[0], -a[1], -a[2], -a[3]);
+    });
+    auto hg_out = [&](int m, int c, const float* a) {
+        const int tt = tile * TW + c;
+        const float4 al4 = *reinterpret_cast<const float4*>(AL + tt), be4 = *reinterpret_cast<const float4*>(BE + tt);
+        const float k = S.kg[m];
+        *reinterpret_cast<float4*>(W.HG + ((size_t)b * NG + m) * Tp + tt) =
+            make_float4(a[0] - (al4.x + k * be4.x), a[1] - (al4.y + k * be4.y), a[2] - (al4.z + k * be4.z), a[3] - (al4.w + k * be4.w));
+    };
+    if (NG <= 64) mm_stage<2>(S.Cp, S.NGp, R, NG, bv, mbuf, hg_out);
+    else mm_stage<4>(S.Cp, S.NGp, R, NG, bv, mbuf, hg_out);
+    // bv (h) was complete before the last stage's first barrier.  Kx and the over-relaxed v of the coupling rows, 16 bytes
+    // per thread and row segment, loads first:
+    {
+        const int n = R * 8;
+        const float inv_rho = 1.f / rho, alpha = opt.alpha;
+        for (int i0 = 0; i0 < n; i0 += 1024) {
+            float4 tmp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + tid + 256 * u;
+                if (i < n) tmp[u] = *reinterpret_cast<const float4*>(VC + (size_t)(i >> 3) * Tp + t4 + 4 * (i & 7));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + tid + 256 * u;
+                if (i < n) {
+                    const float4 g4 = reinterpret_cast<const float4*>(gg)[i], h4 = reinterpret_cast<const float4*>(bv)[i], v4 = tmp[u];
+                    const size_t o = (size_t)(i >> 3) * Tp + t4 + 4 * (i & 7);
+                    // g = rho (2z - v):  z = (g/rho + v)/2
+                    const float4 kx = make_float4((g4.x - h4.x) * inv_rho, (g4.y - h4.y) * inv_rho, (g4.z - h4.z) * inv_rho, (g4.w - h4.w) * inv_rho);
+                    *reinterpret_cast<float4*>(KX + o) = kx;
+                    *reinterpret_cast<float4*>(VC + o) = make_float4(v4.x + alpha * (kx.x - 0.5f * (g4.x * inv_rho + v4.x)), v4.y + alpha * (kx.y - 0.5f * (g4.y * inv_rho + v4.y)),
+                                                                     v4.z + alpha * (kx.z - 0.5f * (g4.z * inv_rho + v4.z)), v4.w + alpha * (kx.w - 0.5f * (g4.w * inv_rho + v4.w)));
+                }
+            }
+        }
+    }
+}
+
 // one warp per instance: peak-epigraph level of the aggregate-power row
 __global__ void k_level(SiteDev S, acb_batch B, GenWork W, GenDims D) {
     const int b = blockIdx.x, lane = threadIdx.x;
@@ -873,8 +1131,9 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     ACB_CUDA(cudaMemsetAsync(W.HG, 0, nGT * sizeof(float), st));
     // row kernels: registers (Q > 0: 8 warps, Tp floats of partial sums each) or shared-memory staging (Q = 0: as many
     // warps as fit, 4 Tp floats each)
-    int row_threads = 256;
-    size_t row_smem = (size_t)8 * Tp * sizeof(float);
+    // (register path: 4 warps per block — a group of ~20 identical EVSEs divides evenly, and the block-level sum waits less)
+    int row_threads = 128;
+    size_t row_smem = (size_t)4 * Tp * sizeof(float);
     if (Q == 0) {
         const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)232448 / ((size_t)16 * Tp)));
         row_threads = 32 * nw;
@@ -894,8 +1153,9 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
     const dim3 grow(NG, B), gcol((Tp + 32 * ACB_CPL - 1) / (32 * ACB_CPL), B);
     const size_t smem_cols = (size_t)(NG + std::max(R, 1) + 2 * std::max(d.Rp, 4)) * 32 * ACB_CPL * sizeof(float);
+    const size_t smem_it = ((size_t)MM_KC * 128 + (size_t)(std::max(NG, std::max(d.Rp, 4)) + std::max(R, 1) + std::max(d.Rp, 4)) * 32) * sizeof(float);
+    if (smem_it > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k_cols_it, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_it));
     if (smem_cols > 48 * 1024) {
-        ACB_CUDA(cudaFuncSetAttribute(k_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
         ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     }
     ROWS(1);
@@ -903,7 +1163,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     while (it < opt.max_iter) {
         const int burst = std::min(it == 0 ? std::min(ACB_FIRST_CHECK, opt.check_every) : opt.check_every, opt.max_iter - it);
         for (int k = 0; k < burst; ++k) {
-            k_cols<0><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
+            k_cols_it<<<gcol, 256, smem_it, st>>>(d, *batch, opt, W, D);
             k_level<<<B, 32, 0, st>>>(d, *batch, W, D);
             if (k == burst - 1) k_clear_check<<<(B + 127) / 128, 128, 0, st>>>(W, B);
             ROWS(0);
