@@ -41,6 +41,12 @@ struct SiteDev {
     const float* Cp;        // [R*NGp] C with rows padded to NGp = roundup(NG, 4) (general path: k-major operand of hg = C'h)
     const float* Ct;        // [NG*Rp] C' padded the same way (k-major operand of b = C sa)
     int NGp;
+    // rank-reduced form of the Woodbury solve (general path): Khat = C G has rank <= NG, so most eigenvalues of
+    // Khat Khat' are exactly 0 and S^-1 = I/(d/rho) + Ur diag(1/(d/rho+lam) - 1/(d/rho)) Ur' over the nEig others
+    int nEig, nEigp;        // nEigp = roundup(nEig, 4)
+    const float* Urp;       // [R*nEigp]  Urp[r][j] = U[r][e_j]
+    const float* Urt;       // [nEig*Rp]  Urt[j][r] = U[r][e_j]
+    const float* lamr;      // [nEig]
     const float* lam;       // [R] eigenvalues
     const float* row_scale; // [R]
     const float* lim;       // [R] limit / row_scale (disc rows: both entries; 0 for pl/u rows)

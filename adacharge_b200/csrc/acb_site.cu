@@ -291,6 +291,23 @@ extern "C" int acb_site_create(acb_site** out, int device, int N, int M, const d
             for (int g = 0; g < NG; ++g) { cp[(size_t)a * NGp + g] = Cf[(size_t)a * NG + g]; ct[(size_t)g * Rp + a] = Cf[(size_t)a * NG + g]; }
         if ((rc = upload(s, cp, &d.Cp)) != ACB_OK) { acb_site_destroy(s); return rc; }
         if ((rc = upload(s, ct, &d.Ct)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        // eigenvectors with a non-zero eigenvalue (the others are null directions of Khat Khat': rank <= NG)
+        double wmax = 0.0;
+        for (int e = 0; e < R; ++e) wmax = std::max(wmax, w[e]);
+        std::vector<int> nz;
+        for (int e = 0; e < R; ++e)
+            if (w[e] > 1e-9 * wmax) nz.push_back(e);
+        const int nE = (int)nz.size(), nEp = (nE + 3) & ~3;
+        d.nEig = nE;
+        d.nEigp = nEp;
+        std::vector<float> urp((size_t)std::max(R, 1) * std::max(nEp, 4), 0.f), urt((size_t)std::max(nE, 1) * std::max(Rp, 4), 0.f), lamr(std::max(nE, 1), 0.f);
+        for (int j = 0; j < nE; ++j) {
+            lamr[j] = lamf[nz[j]];
+            for (int a = 0; a < R; ++a) { urp[(size_t)a * nEp + j] = Uf[(size_t)a * R + nz[j]]; urt[(size_t)j * Rp + a] = Uf[(size_t)a * R + nz[j]]; }
+        }
+        if ((rc = upload(s, urp, &d.Urp)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        if ((rc = upload(s, urt, &d.Urt)) != ACB_OK) { acb_site_destroy(s); return rc; }
+        if ((rc = upload(s, lamr, &d.lamr)) != ACB_OK) { acb_site_destroy(s); return rc; }
     }
     UP(acos_, a_cos) UP(asin_, a_sin) UP(lim64, limits) UP(mp, max_pilot) UP(aoff, allow_off) UP(avals, allow_vals)
     {

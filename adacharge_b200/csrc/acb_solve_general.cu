@@ -50,7 +50,7 @@ enum { GS_RHO = 0, GS_PLEVEL, GS_CS, GS_QD, GS_GAMMA, GS_PKW, GS_PKP0, GS_E1, GS
 enum { GD_P = 0, GD_D, GD_UQ, GD_DBEST, GD_PMAX, GD_BESTGAP, GD_N };
 
 struct GenWork {
-    float *V, *LB, *UB, *VC, *KX, *SG, *SGZ, *HG, *MU, *AL, *BE;  // AL/BE: cost-scaled alpha, beta [B][Tp]
+    float *V, *VC, *KX, *SG, *SGZ, *HG, *MU, *AL, *BE;  // AL/BE: cost-scaled alpha, beta [B][Tp]
     float* scal;     // [B][GS_N]
     double* dacc;    // [B][GD_N]
     int* status;     // [B] -1 = running
@@ -69,8 +69,6 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int nS = B.n_sessions[b], Tb = B.T[b], Tp = D.Tp;
     __shared__ float red[32];
-    __shared__ int infeas;
-    if (tid == 0) infeas = 0;
     for (int i = tid; i < D.N; i += blockDim.x) { W.row_first[(size_t)b * D.N + i] = 0; W.row_cnt[(size_t)b * D.N + i] = 0; }
     __syncthreads();
     // per-row session runs (sessions are sorted by row)
@@ -106,61 +104,26 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
         W.AL[(size_t)b * Tp + t] = ok ? B.alpha[(size_t)b * Tp + t] * cs : 0.f;
         W.BE[(size_t)b * Tp + t] = ok ? B.beta[(size_t)b * Tp + t] * cs : 0.f;
     }
-    // row-level infeasibility (same rule as the on-chip kernel)
-    for (int s = warp; s < nS; s += nw) {
-        size_t k = (size_t)b * B.S_max + s;
-        int row = B.sess_row[k], a = B.sess_start[k], e = min(a + B.sess_len[k], Tp);
-        float slo = 0.f, shi = 0.f;
-        for (int t = a + lane; t < e; t += 32) { slo += W.LB[((size_t)b * D.N + row) * Tp + t]; shi += W.UB[((size_t)b * D.N + row) * Tp + t]; }
-        slo = wsum(slo); shi = wsum(shi);
-        float Eb = B.sess_energy[k], tol = 1e-5f * (fabsf(Eb) + 1.f);
-        if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol))) infeas = 1;
-    }
-    __syncthreads();
-    // infeasibility certificate (see the on-chip kernel): maximum of the objective over the box, in scaled units
+    // (row-level infeasibility, the initial v and the box maximum of the objective are row work: k_rows<Q, 6>)
     __shared__ double redd[32];
-    __shared__ float redu[32];
     {
-        double pm = 0.0;
-        float cmax = 0.f;
-        const float qd_s = B.qd[b] * cs, gam_s = B.gamma[b] * cs;
-        for (int i = tid; i < S.nSlots * Tp; i += blockDim.x) {
-            const int s = i / Tp, t = i - s * Tp, row = S.slot_row[s];
-            if (row < 0) continue;
-            const float c = W.AL[(size_t)b * Tp + t] + S.kg[S.slot_grp[s]] * W.BE[(size_t)b * Tp + t];
-            const float lo = W.LB[((size_t)b * D.N + row) * Tp + t], hi = W.UB[((size_t)b * D.N + row) * Tp + t];
-            pm += (double)fmaxf(c * lo, c * hi) + (double)qd_s * (double)fmaxf(lo * lo, hi * hi);
-        }
-        if (D.has_u && (gam_s > 0.f || B.peak_w[b] > 0.f)) {
-            for (int t = tid; t < Tb; t += blockDim.x) {
-                float umax = 0.f, umin = 0.f;
-                for (int s = 0; s < S.nSlots; ++s) {
-                    const int row = S.slot_row[s];
-                    if (row < 0) continue;
-                    const float k = S.kg[S.slot_grp[s]];
-                    umax += k * W.UB[((size_t)b * D.N + row) * Tp + t]; umin += k * W.LB[((size_t)b * D.N + row) * Tp + t];
-                }
-                const float e = B.ext ? B.ext[(size_t)b * Tp + t] : 0.f;
-                pm += (double)gam_s * (double)fmaxf((umax + e) * (umax + e), (umin + e) * (umin + e));
-                cmax = fmaxf(cmax, umax);
+        // soft energy rows: their part of the box maximum of the objective (see the on-chip kernel), in scaled units
+        double pq = 0.0;
+        if (B.sess_quad)
+            for (int s2 = tid; s2 < nS; s2 += blockDim.x) {
+                const double Eb = (double)B.sess_energy[(size_t)b * B.S_max + s2];
+                pq += (double)(B.sess_quad[(size_t)b * B.S_max + s2] * cs) * Eb * Eb;
             }
-        }
-        pm = wsumd(pm); cmax = wmax(cmax);
-        if (lane == 0) { redd[warp] = pm; redu[warp] = cmax; }
+        pq = wsumd(pq);
+        if (lane == 0) redd[warp] = pq;
         __syncthreads();
     }
     if (tid == 0) {
         float* sc = W.scal + (size_t)b * GS_N;
         {
             double tot = 0.0;
-            float um = 0.f;
-            for (int w = 0; w < nw; ++w) { tot += redd[w]; um = fmaxf(um, redu[w]); }
-            if (B.sess_quad)
-                for (int s2 = 0; s2 < nS; ++s2) {
-                    const double Eb = (double)B.sess_energy[(size_t)b * B.S_max + s2];
-                    tot += (double)(B.sess_quad[(size_t)b * B.S_max + s2] * cs) * Eb * Eb;
-                }
-            W.dacc[(size_t)b * GD_N + GD_PMAX] = tot + (double)(B.peak_w[b] * cs) * (double)fmaxf(um, B.peak_p0[b]);
+            for (int w = 0; w < nw; ++w) tot += redd[w];
+            W.dacc[(size_t)b * GD_N + GD_PMAX] = tot;  // k_rows<Q, 6> and k_setup_agg add the rest
         }
         // cold start: rho0, raised to the curvature of the aggregate quadratic seen through the scaled aggregate row
         // (2 Gamma u^2 with u = su * (Khat r)_u): at rho ~ Gamma su^2 the row's prox is balanced; a 1000-EVSE
@@ -177,24 +140,51 @@ __global__ void k_setup(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenD
         da[GD_DBEST] = -1.0e300;
         da[GD_BESTGAP] = 1.0e300;
         sc[GS_STALL] = 0.f; sc[GS_NRESCUE] = 0.f; sc[GS_NFEAS] = 0.f; sc[GS_BESTVIOL] = 3.0e38f; sc[GS_VSTALL] = 0.f;
-        W.status[b] = infeas ? ACB_INFEASIBLE : -1;
+        W.status[b] = -1;
         W.iters[b] = 0;
-        if (infeas) atomicAdd(W.ndone, 1);
     }
-    // state
+    // state of the coupling rows (the EVSE rows' v: k_rows<Q, 6>)
     // (warm_shift / warm_had: see the on-chip kernel)
     const int wsh = B.warm_shift;
     const bool hadW = !B.warm_had || B.warm_had[b] != 0;
-    for (int i = tid; i < D.N * Tp; i += blockDim.x) {
-        size_t k = (size_t)b * D.N * Tp + i;
-        const int t = i % Tp;
-        W.V[k] = B.warm_v1 ? ((hadW && t + wsh < Tp) ? B.warm_v1[k + wsh] : 0.f) : clampf(0.f, W.LB[k], W.UB[k]);
-    }
     for (int i = tid; i < D.R * Tp; i += blockDim.x) {
         size_t k = (size_t)b * D.R * Tp + i;
         const int t = i % Tp;
         W.VC[k] = (B.warm_vc && hadW && t + wsh < Tp) ? B.warm_vc[k + wsh] : 0.f;
         W.KX[k] = 0.f;
+    }
+}
+
+// per instance, after k_rows<Q, 6 / 7>: the aggregate-power terms of the box maximum of the objective from the group sums
+// of the bounds (SG: upper, SGZ: lower or absent)
+__global__ void k_setup_agg(SiteDev S, acb_batch B, GenWork W, GenDims D, int have_lb) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const float* sc = W.scal + (size_t)b * GS_N;
+    const float gam_s = sc[GS_GAMMA], pkw_s = sc[GS_PKW];
+    if (!D.has_u || !(gam_s > 0.f || pkw_s > 0.f)) return;
+    const int Tp = D.Tp, Tb = B.T[b];
+    __shared__ double redd[32];
+    __shared__ float redu[32];
+    double pm = 0.0;
+    float cmax = 0.f;
+    for (int t = tid; t < Tb; t += blockDim.x) {
+        float umax = 0.f, umin = 0.f;
+        for (int g = 0; g < D.NG; ++g) {
+            umax += S.kg[g] * W.SG[((size_t)b * D.NG + g) * Tp + t];
+            if (have_lb) umin += S.kg[g] * W.SGZ[((size_t)b * D.NG + g) * Tp + t];
+        }
+        const float e = B.ext ? B.ext[(size_t)b * Tp + t] : 0.f;
+        pm += (double)gam_s * (double)fmaxf((umax + e) * (umax + e), (umin + e) * (umin + e));
+        cmax = fmaxf(cmax, umax);
+    }
+    pm = wsumd(pm); cmax = wmax(cmax);
+    if (lane == 0) { redd[warp] = pm; redu[warp] = cmax; }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        float um = 0.f;
+        for (int w = 0; w < nw; ++w) { tot += redd[w]; um = fmaxf(um, redu[w]); }
+        W.dacc[(size_t)b * GD_N + GD_PMAX] += tot + (double)pkw_s * (double)fmaxf(um, sc[GS_PKP0]);
     }
 }
 
@@ -208,7 +198,9 @@ __device__ __forceinline__ float mu_at(const float* MU, const int* SA, const int
 
 // MODE 0: iteration (x, v update, projection, SG <- sums of q);  MODE 1: init (SG <- sums of q from V);
 // MODE 2: check (SGZ <- sums of z, P_lin);  MODE 3: check (Lagrangian inner terms with HG = C'y);
-// MODE 4: write the schedule;  MODE 5: rescale V for a new rho (scal[GS_E1] holds rho_old/rho_new)
+// MODE 4: write the schedule;  MODE 5: rescale V for a new rho (scal[GS_E1] holds rho_old/rho_new);
+// MODE 6: setup (initial v, row-level infeasibility, the rows' part of the box maximum of the objective, SG <- group sums
+//         of the upper bounds);  MODE 7: setup (SGZ <- group sums of the lower bounds; only when some minimum rate is not 0)
 //
 // Q > 0: padded horizon 32*Q known at compile time, a row lives in registers (Q values per lane).
 // Q = 0: any horizon that is a multiple of 32 (the offline algorithm, sessions longer than a day; reference
@@ -234,7 +226,7 @@ struct RowStore<0> {
 template <int Q, int MODE>
 __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
     const int g = blockIdx.x, b = blockIdx.y;
-    if (W.status[b] >= 0 && MODE != 4) return;
+    if (W.status[b] >= 0 && MODE != 4 && MODE < 6) return;
     constexpr bool DYN = (Q == 0);
     const int Tp = DYN ? D.Tp : 32 * Q, nq = DYN ? D.Tp / 32 : Q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -272,7 +264,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
     // register path: the next row's v is requested before the current row's multiplier search starts
     const int kend = grp_off[g + 1];
     float vnx[Q > 0 ? Q : 1];
-    if constexpr (!DYN) {
+    if constexpr (!DYN && MODE < 6) {
         const int k0 = grp_off[g] + warp;
         if (k0 < kend) {
             const size_t bn = ((size_t)b * D.N + S.slot_row[k0]) * Tp + lane;
@@ -284,7 +276,8 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
         const int row = S.slot_row[k];
         const size_t base = ((size_t)b * D.N + row) * Tp + lane;
         const int sf = W.row_first[(size_t)b * D.N + row], scn = W.row_cnt[(size_t)b * D.N + row];
-        if constexpr (DYN) {
+        if constexpr (MODE >= 6) {
+        } else if constexpr (DYN) {
             for (int q = 0; q < nq; ++q) rs.V(q) = W.V[base + 32 * q];
         } else {
 #pragma unroll
@@ -311,7 +304,39 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
                 }
             }
         }
-        if (MODE == 0) {
+        if (MODE >= 6) {
+            if (MODE == 6) {
+                // (warm_shift / warm_had: see the on-chip kernel)
+                const int wsh = B.warm_shift;
+                const bool hadW = !B.warm_had || B.warm_had[b] != 0;
+#pragma unroll
+                for (int q = 0; q < nq; ++q) {
+                    const int t = lane + 32 * q;
+                    const float lo = rs.LB(q), hi = rs.UB(q);
+                    W.V[base + 32 * q] = B.warm_v1 ? ((hadW && t + wsh < Tp) ? B.warm_v1[base + 32 * q + wsh] : 0.f) : clampf(0.f, lo, hi);
+                    const float c = AL[t] + kgc * BE[t];
+                    dsum += (double)fmaxf(c * lo, c * hi) + (double)qd * (double)fmaxf(lo * lo, hi * hi);
+                    add_part(q, hi);
+                }
+                // row-level infeasibility (same rule as the on-chip kernel)
+                for (int s = sf; s < sf + scn; ++s) {
+                    const int a = SA[s], e = min(a + SL[s], Tp);
+                    float slo = 0.f, shi = 0.f;
+#pragma unroll
+                    for (int q = 0; q < nq; ++q) {
+                        const int t = lane + 32 * q;
+                        if (t >= a && t < e) { slo += rs.LB(q); shi += rs.UB(q); }
+                    }
+                    slo = wsum(slo); shi = wsum(shi);
+                    const float Eb = B.sess_energy[(size_t)b * B.S_max + s], tol = 1e-5f * (fabsf(Eb) + 1.f);
+                    if (lane == 0 && (slo > Eb + tol || (opt.equality && shi < Eb - tol)) && atomicCAS(W.status + b, -1, (int)ACB_INFEASIBLE) == -1)
+                        atomicAdd(W.ndone, 1);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < nq; ++q) add_part(q, rs.LB(q));
+            }
+        } else if (MODE == 0) {
             float zo[Q > 0 ? Q : 1];  // previous z for the dual residual (register path only; long horizons report r_dual = 0)
             // one session on the row (the usual case): the bounds are zero outside its window, so clamp(v - mu, lb, ub) is
             // already 0 there and neither the multiplier lookup nor the window tests are needed
@@ -449,13 +474,13 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
             }
         }
     }
-    if (MODE <= 2) {
+    if (MODE <= 2 || MODE >= 6) {
         if constexpr (!DYN) {
 #pragma unroll
             for (int q = 0; q < nq; ++q) part[lane + 32 * q] = acc[q];
         }
         __syncthreads();
-        float* out = (MODE == 2 ? W.SGZ : W.SG) + ((size_t)b * D.NG + g) * Tp;
+        float* out = ((MODE == 2 || MODE == 7) ? W.SGZ : W.SG) + ((size_t)b * D.NG + g) * Tp;
         const float* p0 = DYN ? dsm + 3 * Tp : dsm;
         for (int t = tid; t < Tp; t += blockDim.x) {
             float s = 0.f;
@@ -470,9 +495,9 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
             atomic_max_pos(s + GS_E1, e1); atomic_max_pos(s + GS_E2, e2); atomic_max_pos(s + GS_XMAX, xm); atomic_max_pos(s + GS_YMAX, ym);
         }
     }
-    if (MODE == 2 || MODE == 3) {
+    if (MODE == 2 || MODE == 3 || MODE == 6) {
         dsum = wsumd(dsum);
-        if (lane == 0) atomicAdd(W.dacc + (size_t)b * GD_N + (MODE == 2 ? GD_P : GD_D), dsum);
+        if (lane == 0) atomicAdd(W.dacc + (size_t)b * GD_N + (MODE == 2 ? GD_P : MODE == 3 ? GD_D : GD_PMAX), dsum);
     }
 }
 
@@ -773,9 +798,9 @@ __device__ __forceinline__ void mm_stage(const float* __restrict__ MatT, int ldm
 }
 
 // Iteration column pass: block per (tile of 32 periods, instance), 256 threads.
-//   b = C sa - (d/rho) g,  y1 = diag(1/(d/rho+lam)) U' b,  h = -U y1,  hg = C' h - c,  Kx = (g - h)/rho,  v_c += alpha (Kx - z_c)
+//   b = C sa - (d/rho) g,  h = -U diag(1/(d/rho+lam)) U' b (rank-reduced, SiteDev::nEig),  hg = C' h - c,  Kx = (g - h)/rho,  v_c += alpha (Kx - z_c)
 // The four products are mm_stage calls (shared-memory blocked, FMA bound); everything else is one pass over the tile.
-__global__ void __launch_bounds__(256, 3) k_cols_it(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
+__global__ void __launch_bounds__(256, 4) k_cols_it(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
     constexpr int TW = 32;
     const int tile = blockIdx.x, b = blockIdx.y;
     if (W.status[b] >= 0) return;
@@ -783,8 +808,8 @@ __global__ void __launch_bounds__(256, 3) k_cols_it(SiteDev S, acb_batch B, acb_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int R = D.R, NG = D.NG, Tp = D.Tp, t = tile * TW + lane, Tb = B.T[b], Rp = S.Rp;
     float* mbuf = sm;                               // [MM_KC][128] matrix chunk
-    float* sa = mbuf + MM_KC * 128;                 // [max(NG, Rp)][TW]  group inputs, later y1
-    float* gg = sa + (size_t)max(NG, Rp) * TW;      // [R][TW]   rho (2 z_c - v_c)
+    float* sa = mbuf + MM_KC * 128;                 // [max(NG, nEigp)][TW]  group inputs, later y1
+    float* gg = sa + (size_t)max(NG, S.nEigp) * TW; // [R][TW]   rho (2 z_c - v_c)
     float* bv = gg + (size_t)R * TW;                // [Rp][TW]  b, later h
     float* y1 = sa;
     const float* sc = W.scal + (size_t)b * GS_N;
@@ -860,12 +885,19 @@ __global__ void __launch_bounds__(256, 3) k_cols_it(SiteDev S, acb_batch B, acb_
         const float4 g4 = *reinterpret_cast<const float4*>(gg + m * TW + c);
         *reinterpret_cast<float4*>(bv + m * TW + c) = make_float4(a[0] - dr * g4.x, a[1] - dr * g4.y, a[2] - dr * g4.z, a[3] - dr * g4.w);
     });
-    mm_stage<4>(S.Up, Rp, R, R, bv, mbuf, [&](int m, int c, const float* a) {
-        const float inv = 1.f / (dr + S.lam[m]);
-        *reinterpret_cast<float4*>(y1 + m * TW + c) = make_float4(a[0] * inv, a[1] * inv, a[2] * inv, a[3] * inv);
-    });
-    mm_stage<4>(S.Ut, Rp, R, R, y1, mbuf, [&](int m, int c, const float* a) {
-        *reinterpret_cast<float4*>(bv + m * TW + c) = make_float4(-a[0], -a[1], -a[2], -a[3]);
+    // y1 = diag(1/(d/rho+lam) - 1/(d/rho)) Ur' b over the nEig non-null eigenvectors, then h = -(b/(d/rho) + Ur y1) in place
+    const float inv_dr = 1.f / dr;
+    const int nE = S.nEig;
+    auto y_out = [&](int m, int c, const float* a) {
+        const float w = 1.f / (dr + S.lamr[m]) - inv_dr;
+        *reinterpret_cast<float4*>(y1 + m * TW + c) = make_float4(a[0] * w, a[1] * w, a[2] * w, a[3] * w);
+    };
+    if (nE <= 64) mm_stage<2>(S.Urp, S.nEigp, R, nE, bv, mbuf, y_out);
+    else mm_stage<4>(S.Urp, S.nEigp, R, nE, bv, mbuf, y_out);
+    mm_stage<4>(S.Urt, Rp, nE, R, y1, mbuf, [&](int m, int c, const float* a) {
+        float4* o = reinterpret_cast<float4*>(bv + m * TW + c);
+        const float4 b4 = *o;
+        *o = make_float4(-(b4.x * inv_dr + a[0]), -(b4.y * inv_dr + a[1]), -(b4.z * inv_dr + a[2]), -(b4.w * inv_dr + a[3]));
     });
     auto hg_out = [&](int m, int c, const float* a) {
         const int tt = tile * TW + c;
@@ -1076,25 +1108,6 @@ __global__ void k_finish(acb_batch B, GenWork W, GenDims D) {
     if (B.out_mu) for (int s = 0; s < B.S_max; ++s) B.out_mu[(size_t)b * B.S_max + s] = W.MU[(size_t)b * B.S_max + s];
 }
 
-__global__ void k_bounds_general(SiteDev S, acb_batch B, float* lb, float* ub) {
-    const int b = blockIdx.x, N = S.N, Tp = B.Tp;
-    const int nS = B.n_sessions[b];
-    float* lbb = lb + (size_t)b * N * Tp;
-    float* ubb = ub + (size_t)b * N * Tp;
-    for (int i = threadIdx.x; i < N * Tp; i += blockDim.x) { lbb[i] = 0.f; ubb[i] = 0.f; }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int s = warp; s < nS; s += nwarps) {
-        size_t k = (size_t)b * B.S_max + s;
-        int row = B.sess_row[k], a = B.sess_start[k], len = B.sess_len[k], off = B.sess_rate_off[k];
-        for (int j = lane; j < len; j += 32) {
-            const int ri = off >= 0 ? off + j : -(off + 1);  // off < 0: one (min, max) pair for the whole session
-            float lo = B.min_rates[ri], hi = B.max_rates[ri];
-            if (a + j < Tp) { lbb[row * Tp + a + j] = lo; ubb[row * Tp + a + j] = fmaxf(hi, lo); }
-        }
-    }
-}
-
 template <int Q>
 int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, cudaStream_t st) {
     const SiteDev& d = site->d;
@@ -1102,7 +1115,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     GenDims D{N, R, NG, Tp, Tp / 32, batch->S_max, d.nDisc, d.nLin, d.has_pl, d.has_u, 2 * d.nDisc + d.nLin, 2 * d.nDisc + d.nLin + d.has_pl, d.lin_two_sided};
     // workspace
     const size_t nNT = (size_t)B * N * Tp, nRT = (size_t)B * std::max(R, 1) * Tp, nGT = (size_t)B * NG * Tp;
-    const size_t floats = 3 * nNT + 2 * nRT + 3 * nGT + (size_t)B * batch->S_max + 2 * (size_t)B * Tp + (size_t)B * GS_N;
+    const size_t floats = nNT + 2 * nRT + 3 * nGT + (size_t)B * batch->S_max + 2 * (size_t)B * Tp + (size_t)B * GS_N;
     const size_t bytes = floats * sizeof(float) + (size_t)B * GD_N * sizeof(double) + ((size_t)B * (2 + 2 * N) + 4) * sizeof(int) + 256;
     {
         // keep the stream-ordered pool's memory across calls (the default threshold of 0 gives it back at every sync)
@@ -1118,7 +1131,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     char* p = base;
     auto take = [&](size_t n, size_t sz) { void* r = p; p += ((n * sz + 15) / 16) * 16; return r; };
     W.dacc = (double*)take((size_t)B * GD_N, 8);
-    W.V = (float*)take(nNT, 4); W.LB = (float*)take(nNT, 4); W.UB = (float*)take(nNT, 4);
+    W.V = (float*)take(nNT, 4);
     W.VC = (float*)take(nRT, 4); W.KX = (float*)take(nRT, 4);
     W.SG = (float*)take(nGT, 4); W.SGZ = (float*)take(nGT, 4); W.HG = (float*)take(nGT, 4);
     W.MU = (float*)take((size_t)B * batch->S_max, 4);
@@ -1147,13 +1160,17 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
         ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
         ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
         ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     }
 #define ROWS(MODE) k_rows<Q, MODE><<<grow, row_threads, row_smem, st>>>(d, *batch, opt, W, D, site->grp_off_dev)
-    k_bounds_general<<<B, 256, 0, st>>>(d, *batch, W.LB, W.UB);
-    k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
     const dim3 grow(NG, B), gcol((Tp + 32 * ACB_CPL - 1) / (32 * ACB_CPL), B);
+    k_setup<<<B, 256, 0, st>>>(d, *batch, opt, W, D);
+    ROWS(6);
+    if (!batch->lb_zero) ROWS(7);
+    k_setup_agg<<<B, 256, 0, st>>>(d, *batch, W, D, batch->lb_zero ? 0 : 1);
     const size_t smem_cols = (size_t)(NG + std::max(R, 1) + 2 * std::max(d.Rp, 4)) * 32 * ACB_CPL * sizeof(float);
-    const size_t smem_it = ((size_t)MM_KC * 128 + (size_t)(std::max(NG, std::max(d.Rp, 4)) + std::max(R, 1) + std::max(d.Rp, 4)) * 32) * sizeof(float);
+    const size_t smem_it = ((size_t)MM_KC * 128 + (size_t)(std::max(NG, std::max(d.nEigp, 4)) + std::max(R, 1) + std::max(d.Rp, 4)) * 32) * sizeof(float);
     if (smem_it > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k_cols_it, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_it));
     if (smem_cols > 48 * 1024) {
         ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
