@@ -261,46 +261,68 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
         }
     }
     auto hg_at = [&](int q) -> float { if constexpr (DYN) return HGg[lane + 32 * q]; else return hgq[q]; };
-    // register path: the next row's v is requested before the current row's multiplier search starts
+    // The warp's rows are walked in chunks of 32: lane j first fetches the table entries of the chunk's j-th row (row index,
+    // session run and, for a single session with constant limits — the usual case — its window, limits, energy and
+    // multiplier), so the chain of dependent loads is paid once per chunk instead of once per row; the row loop then takes
+    // them by shuffle.  Register path: the next row's v is requested before the current row's multiplier search starts.
     const int kend = grp_off[g + 1];
     float vnx[Q > 0 ? Q : 1];
-    if constexpr (!DYN && MODE < 6) {
-        const int k0 = grp_off[g] + warp;
-        if (k0 < kend) {
-            const size_t bn = ((size_t)b * D.N + S.slot_row[k0]) * Tp + lane;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) vnx[q] = W.V[bn + 32 * q];
+    for (int kc = grp_off[g] + warp; kc < kend; kc += 32 * nw) {
+    int m_row = 0, m_sf = 0, m_scn = 0, m_a = 0, m_len = 0, m_off = 0;
+    float m_lo = 0.f, m_hi = 0.f, m_mu = 0.f;
+    if (kc + lane * nw < kend) {
+        m_row = S.slot_row[kc + lane * nw];
+        m_sf = W.row_first[(size_t)b * D.N + m_row];
+        m_scn = W.row_cnt[(size_t)b * D.N + m_row];
+        if (m_scn == 1) {
+            m_a = SA[m_sf]; m_len = SL[m_sf]; m_off = SO[m_sf];
+            m_mu = MU[m_sf];
+            if (m_off < 0) { m_lo = B.min_rates[-(m_off + 1)]; m_hi = fmaxf(B.max_rates[-(m_off + 1)], m_lo); }
         }
     }
-    for (int k = grp_off[g] + warp; k < kend; k += nw) {
-        const int row = S.slot_row[k];
+    if constexpr (!DYN && MODE < 6) {
+        const size_t bn = ((size_t)b * D.N + __shfl_sync(0xffffffffu, m_row, 0)) * Tp + lane;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) vnx[q] = W.V[bn + 32 * q];
+    }
+    for (int jr = 0; jr < 32 && kc + jr * nw < kend; ++jr) {
+        const int row = __shfl_sync(0xffffffffu, m_row, jr), sf = __shfl_sync(0xffffffffu, m_sf, jr), scn = __shfl_sync(0xffffffffu, m_scn, jr);
+        const int s_a = __shfl_sync(0xffffffffu, m_a, jr), s_len = __shfl_sync(0xffffffffu, m_len, jr), s_off = __shfl_sync(0xffffffffu, m_off, jr);
+        const float s_lo = __shfl_sync(0xffffffffu, m_lo, jr), s_hi = __shfl_sync(0xffffffffu, m_hi, jr), s_mu = __shfl_sync(0xffffffffu, m_mu, jr);
         const size_t base = ((size_t)b * D.N + row) * Tp + lane;
-        const int sf = W.row_first[(size_t)b * D.N + row], scn = W.row_cnt[(size_t)b * D.N + row];
         if constexpr (MODE >= 6) {
         } else if constexpr (DYN) {
             for (int q = 0; q < nq; ++q) rs.V(q) = W.V[base + 32 * q];
         } else {
 #pragma unroll
             for (int q = 0; q < Q; ++q) rs.V(q) = vnx[q];
-            if (k + nw < kend) {
-                const size_t bn = ((size_t)b * D.N + S.slot_row[k + nw]) * Tp + lane;
+            if (jr + 1 < 32 && kc + (jr + 1) * nw < kend) {
+                const size_t bn = ((size_t)b * D.N + __shfl_sync(0xffffffffu, m_row, jr + 1)) * Tp + lane;
 #pragma unroll
                 for (int q = 0; q < Q; ++q) vnx[q] = W.V[bn + 32 * q];
             }
         }
-        // rate bounds straight from the session table (charging_rate_bounds, aco.py:61-79; same rule as k_bounds_general):
-        // a constant (min, max) pair per session costs two warp-uniform loads instead of two streamed rows
-#pragma unroll
-        for (int q = 0; q < nq; ++q) { rs.LB(q) = 0.f; rs.UB(q) = 0.f; }
-        for (int s = sf; s < sf + scn; ++s) {
-            const int a = SA[s], len = SL[s], off = SO[s];
+        // rate bounds straight from the session table (charging_rate_bounds, aco.py:61-79: zero outside the session windows,
+        // ub := lb where ub < lb)
+        if (scn == 1 && s_off < 0) {
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
-                const int j = lane + 32 * q - a;
-                if (j >= 0 && j < len) {
-                    const int ri = off >= 0 ? off + j : -(off + 1);
-                    const float lo = B.min_rates[ri];
-                    rs.LB(q) = lo; rs.UB(q) = fmaxf(B.max_rates[ri], lo);
+                const bool in = (unsigned)(lane + 32 * q - s_a) < (unsigned)s_len;
+                rs.LB(q) = in ? s_lo : 0.f; rs.UB(q) = in ? s_hi : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < nq; ++q) { rs.LB(q) = 0.f; rs.UB(q) = 0.f; }
+            for (int s = sf; s < sf + scn; ++s) {
+                const int a = SA[s], len = SL[s], off = SO[s];
+#pragma unroll
+                for (int q = 0; q < nq; ++q) {
+                    const int j = lane + 32 * q - a;
+                    if (j >= 0 && j < len) {
+                        const int ri = off >= 0 ? off + j : -(off + 1);
+                        const float lo = B.min_rates[ri];
+                        rs.LB(q) = lo; rs.UB(q) = fmaxf(B.max_rates[ri], lo);
+                    }
                 }
             }
         }
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
             // one session on the row (the usual case): the bounds are zero outside its window, so clamp(v - mu, lb, ub) is
             // already 0 there and neither the multiplier lookup nor the window tests are needed
             const bool one = (scn == 1);
-            float mu1 = one ? MU[sf] : 0.f;
+            float mu1 = s_mu;
 #pragma unroll
             for (int q = 0; q < nq; ++q) {
                 const int t = lane + 32 * q;
@@ -357,7 +379,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
                 const int a = SA[s], e = a + SL[s];
                 const float Eb = B.sess_energy[(size_t)b * B.S_max + s];
                 const float tol = 2e-6f * (Eb + 1.f);
-                float mu = MU[s];
+                float mu = one ? s_mu : MU[s];
                 // quadratic shortfall term cq (Eb - E)^2 (non_completion_penalty, norm 2): see newton_mu in acb_solve_kernel.cuh
                 const float cq = B.sess_quad ? B.sess_quad[(size_t)b * B.S_max + s] * sc[GS_CS] : 0.f;
                 const bool soft = cq > 0.f && !opt.equality, freeMu = opt.equality || soft;
@@ -473,6 +495,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
                 }
             }
         }
+    }
     }
     if (MODE <= 2 || MODE >= 6) {
         if constexpr (!DYN) {
