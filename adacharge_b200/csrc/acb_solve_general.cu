@@ -199,6 +199,7 @@ __device__ __forceinline__ float mu_at(const float* MU, const int* SA, const int
 // MODE 0: iteration (x, v update, projection, SG <- sums of q);  MODE 1: init (SG <- sums of q from V);
 // MODE 2: check (SGZ <- sums of z, P_lin);  MODE 3: check (Lagrangian inner terms with HG = C'y);
 // MODE 4: write the schedule;  MODE 5: rescale V for a new rho (scal[GS_E1] holds rho_old/rho_new);
+// MODE 8: iteration without the residual maxima (they are read at checks only: every iteration of a burst but the last);
 // MODE 6: setup (initial v, row-level infeasibility, the rows' part of the box maximum of the objective, SG <- group sums
 //         of the upper bounds);  MODE 7: setup (SGZ <- group sums of the lower bounds; only when some minimum rate is not 0)
 //
@@ -225,8 +226,9 @@ struct RowStore<0> {
 
 template <int Q, int MODE>
 __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D, const int* grp_off) {
+    constexpr bool SETUP = (MODE == 6 || MODE == 7), ITER = (MODE == 0 || MODE == 8), TRACK = (MODE == 0);
     const int g = blockIdx.x, b = blockIdx.y;
-    if (W.status[b] >= 0 && MODE != 4 && MODE < 6) return;
+    if (W.status[b] >= 0 && MODE != 4 && !SETUP) return;
     constexpr bool DYN = (Q == 0);
     const int Tp = DYN ? D.Tp : 32 * Q, nq = DYN ? D.Tp / 32 : Q;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
     const float* HGg = W.HG + ((size_t)b * D.NG + g) * Tp;
     float hgq[Q > 0 ? Q : 1];
     if constexpr (!DYN) {
-        if (MODE == 0 || MODE == 3) {
+        if (ITER || MODE == 3) {
 #pragma unroll
             for (int q = 0; q < Q; ++q) hgq[q] = HGg[lane + 32 * q];
         }
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
             if (m_off < 0) { m_lo = B.min_rates[-(m_off + 1)]; m_hi = fmaxf(B.max_rates[-(m_off + 1)], m_lo); }
         }
     }
-    if constexpr (!DYN && MODE < 6) {
+    if constexpr (!DYN && !SETUP) {
         const size_t bn = ((size_t)b * D.N + __shfl_sync(0xffffffffu, m_row, 0)) * Tp + lane;
 #pragma unroll
         for (int q = 0; q < Q; ++q) vnx[q] = W.V[bn + 32 * q];
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
         const int s_a = __shfl_sync(0xffffffffu, m_a, jr), s_len = __shfl_sync(0xffffffffu, m_len, jr), s_off = __shfl_sync(0xffffffffu, m_off, jr);
         const float s_lo = __shfl_sync(0xffffffffu, m_lo, jr), s_hi = __shfl_sync(0xffffffffu, m_hi, jr), s_mu = __shfl_sync(0xffffffffu, m_mu, jr);
         const size_t base = ((size_t)b * D.N + row) * Tp + lane;
-        if constexpr (MODE >= 6) {
+        if constexpr (SETUP) {
         } else if constexpr (DYN) {
             for (int q = 0; q < nq; ++q) rs.V(q) = W.V[base + 32 * q];
         } else {
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
                 }
             }
         }
-        if (MODE >= 6) {
+        if (SETUP) {
             if (MODE == 6) {
                 // (warm_shift / warm_had: see the on-chip kernel)
                 const int wsh = B.warm_shift;
@@ -358,7 +360,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
 #pragma unroll
                 for (int q = 0; q < nq; ++q) add_part(q, rs.LB(q));
             }
-        } else if (MODE == 0) {
+        } else if (ITER) {
             float zo[Q > 0 ? Q : 1];  // previous z for the dual residual (register path only; long horizons report r_dual = 0)
             // one session on the row (the usual case): the bounds are zero outside its window, so clamp(v - mu, lb, ub) is
             // already 0 there and neither the multiplier lookup nor the window tests are needed
@@ -371,9 +373,11 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
                 float z = clampf(vq - (one ? mu1 : mu_at(MU, SA, SL, sf, scn, t)), rs.LB(q), rs.UB(q));
                 float x = (rho1 * (2.f * z - vq) + hg_at(q)) * inv_d;
                 rs.V(q) = vq + alpha * (x - z);
-                if constexpr (!DYN) zo[q] = z;
-                e1 = fmaxf(e1, fabsf(x - z));
-                xm = fmaxf(xm, fabsf(x));
+                if constexpr (TRACK) {
+                    if constexpr (!DYN) zo[q] = z;
+                    e1 = fmaxf(e1, fabsf(x - z));
+                    xm = fmaxf(xm, fabsf(x));
+                }
             }
             for (int s = sf; s < sf + scn; ++s) {
                 const int a = SA[s], e = a + SL[s];
@@ -435,8 +439,10 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
                 float zn = clampf(vq - (one ? mu1 : mu_at(MU, SA, SL, sf, scn, t)), rs.LB(q), rs.UB(q));
                 add_part(q, 2.f * zn - vq);
                 W.V[base + 32 * q] = vq;
-                if constexpr (!DYN) e2 = fmaxf(e2, fabsf(zn - zo[q]));
-                ym = fmaxf(ym, fabsf(rho1 * (vq - zn)));
+                if constexpr (TRACK) {
+                    if constexpr (!DYN) e2 = fmaxf(e2, fabsf(zn - zo[q]));
+                    ym = fmaxf(ym, fabsf(rho1 * (vq - zn)));
+                }
             }
         } else {
 #pragma unroll
@@ -497,7 +503,7 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
         }
     }
     }
-    if (MODE <= 2 || MODE >= 6) {
+    if (MODE <= 2 || SETUP || MODE == 8) {
         if constexpr (!DYN) {
 #pragma unroll
             for (int q = 0; q < nq; ++q) part[lane + 32 * q] = acc[q];
@@ -1185,6 +1191,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
         ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
         ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
         ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+        ACB_CUDA(cudaFuncSetAttribute(k_rows<Q, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
     }
 #define ROWS(MODE) k_rows<Q, MODE><<<grow, row_threads, row_smem, st>>>(d, *batch, opt, W, D, site->grp_off_dev)
     const dim3 grow(NG, B), gcol((Tp + 32 * ACB_CPL - 1) / (32 * ACB_CPL), B);
@@ -1205,8 +1212,11 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
         for (int k = 0; k < burst; ++k) {
             k_cols_it<<<gcol, 256, smem_it, st>>>(d, *batch, opt, W, D);
             k_level<<<B, 32, 0, st>>>(d, *batch, W, D);
-            if (k == burst - 1) k_clear_check<<<(B + 127) / 128, 128, 0, st>>>(W, B);
-            ROWS(0);
+            if (k == burst - 1) {
+                k_clear_check<<<(B + 127) / 128, 128, 0, st>>>(W, B);
+                ROWS(0);
+            } else
+                ROWS(8);
         }
         it += burst;
         // check
