@@ -45,10 +45,10 @@ __global__ void acb_pack_kernel(SiteDev S, acb_sessions X, acb_objective O, acb_
     for (int s = tid; s < Sm; s += nt) {
         const int k = key[s];
         if (k == 0x7fffffff) continue;
-        int rank = 0, dup = 0;
-        const int row = k / Sm;
-        for (int j = 0; j < Sm; ++j) { const int kj = key[j]; rank += (kj < k) ? 1 : 0; dup |= (j != s && kj != 0x7fffffff && kj / Sm == row) ? 1 : 0; }
-        if (dup) s_dup = 1;
+        int rank = 0, same = 0;
+        const int row = k / Sm, klo = row * Sm, khi = klo + Sm;  // keys of the same EVSE row lie in [klo, khi)
+        for (int j = 0; j < Sm; ++j) { const int kj = key[j]; rank += (kj < k) ? 1 : 0; same += (kj >= klo && kj < khi) ? 1 : 0; }
+        if (same > 1) s_dup = 1;  // (the session itself counts once)
         o_row[rank] = row;
         o_start[rank] = X.arrival_offset[base + s];
         o_len[rank] = X.remaining_time[base + s];
@@ -157,7 +157,10 @@ extern "C" int acb_pack_sessions(acb_site* site, const acb_sessions* sessions, c
     ACB_CUDA(cudaSetDevice(site->device));
     const size_t smem = (size_t)sessions->S_max * sizeof(int);
     if (smem > 48 * 1024) { acb_set_error("acb_pack_sessions: S_max too large"); return ACB_E_TOO_LARGE; }
-    acb_pack_kernel<<<batch->B, 128, smem, (cudaStream_t)stream>>>(site->d, *sessions, *objective, *batch, flags);
+    // the rank sort is S_max^2 comparisons per instance: one thread per session slot up to 1024 (a 1000-session instance took
+    // 0.8 ms on 128 threads, 7 % of a config-5 step)
+    const int threads = std::min(1024, std::max(128, (sessions->S_max + 31) / 32 * 32));
+    acb_pack_kernel<<<batch->B, threads, smem, (cudaStream_t)stream>>>(site->d, *sessions, *objective, *batch, flags);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }

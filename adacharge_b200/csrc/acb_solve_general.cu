@@ -3,12 +3,13 @@
 // duality-gap stopping rule as acb_solve_kernel.cuh, with the state in HBM/L2 and one
 // kernel per phase over the whole batch:
 //   k_rows  block per (group of electrically identical EVSEs, instance): x, over-relaxed v,
-//           box ∩ energy projection (warp per row, Newton on the multiplier), group sums
-//   k_cols  block per (32-period tile, instance): the Woodbury solve in factored form
-//           b = C sa - (d/rho) g,  h = -U diag(1/(d/rho+lam)) U' b,  Kx = (g - h)/rho,
-//           hg = C'h - c, then the coupling-row v update for the tile
+//           box ∩ energy projection (warp per row, Newton on the multiplier), group sums; the rate
+//           bounds come straight from the session table (nothing but v is streamed)
+//   k_cols_it  block per (32-period tile, instance): the Woodbury solve in factored, rank-reduced form
+//           b = C sa - (d/rho) g,  h = -(b/(d/rho) + Ur diag(1/(d/rho+lam) - 1/(d/rho)) Ur' b),  Kx = (g - h)/rho,
+//           hg = C'h - c as four shared-memory blocked products, then the coupling-row v update for the tile
 //   k_level one warp per instance: peak-epigraph level of the aggregate-power row
-// and, every check_every iterations, k_chk_* / k_decide for P (candidate objective), D
+// and, every check_every iterations, k_rows<2/3> / k_cols_check / k_decide for P (candidate objective), D
 // (Lagrangian bound), violation, stopping flags and the rho balance.
 // Replaces the same reference code as the on-chip kernel (aco.py:220-321, 363-408).
 // Differences from the on-chip path: no running average / restarts; scalar reductions use
@@ -530,238 +531,6 @@ __global__ void __launch_bounds__(Q > 0 ? 128 : 256, Q > 0 ? 5 : 1) k_rows(SiteD
     }
 }
 
-// block per (tile of 32*CPL periods, instance); a lane owns CPL columns (t = tile*32*CPL + c*32 + lane), so every
-// matrix element fetched by a warp feeds CPL columns.  CHECK = 0: iteration;  CHECK = 1: evaluation of the
-// candidate (violation, aggregate-power part of P, conjugate terms of D, HG <- C'y).
-#define ACB_CPL 1  // columns per lane; 2 was measured slower on the 1000-EVSE site (566 vs 345 us per launch: half the resident warps, a ragged last tile)
-template <int CHECK>
-__global__ void __launch_bounds__(256) k_cols(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
-    constexpr int CPL = ACB_CPL, TW = 32 * CPL;
-    const int tile = blockIdx.x, b = blockIdx.y;
-    if (W.status[b] >= 0) return;
-    extern __shared__ float sm[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-    const int R = D.R, NG = D.NG, Tp = D.Tp, t0 = tile * TW + lane, Tb = B.T[b];
-    float* sa = sm;                 // [NG][TW]   group inputs / group sums of z
-    float* gg = sa + NG * TW;       // [R][TW]    g (iteration) or y (check)
-    const int Rp = S.Rp;            // R rounded up to a multiple of 4; the padding rows of bv / y1 stay zero
-    float* bv = gg + R * TW;        // [Rp][TW]
-    float* y1 = bv + Rp * TW;       // [Rp][TW]
-    const float* sc = W.scal + (size_t)b * GS_N;
-    const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, dr = dd / rho;
-    const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], pk_p0 = sc[GS_PKP0], plevel = sc[GS_PLEVEL];
-    const float su = D.has_u ? S.row_scale[D.rU] : 1.f;
-    const float linLo = D.lin_two_sided ? -1.f : -3.0e38f;
-    const float* AL = W.AL + (size_t)b * Tp;
-    const float* BE = W.BE + (size_t)b * Tp;
-    const float* ext = B.ext ? B.ext + (size_t)b * Tp : nullptr;
-    float* VC = W.VC + (size_t)b * R * Tp;
-    float* KX = W.KX + (size_t)b * R * Tp;
-    auto ebar = [&](int tt) -> float { return (ext && tt < Tb) ? ext[tt] : 0.f; };
-    auto plim = [&](int tt) -> float { return (B.peak_limit && tt < Tb) ? B.peak_limit[(size_t)b * Tp + tt] / S.row_scale[D.rPL] : 3.0e38f; };
-    auto agg_a = [&](float v, int tt) -> float { float rp = rho / (su * su); return (rp * (v * su) - 2.f * Gamma * ebar(tt)) / (rp + 2.f * Gamma); };
-    // z of coupling row r (disc rows are handled pairwise by the caller)
-    auto proj_row = [&](int r, float v, int tt) -> float {
-        if (r < 2 * D.nDisc + D.nLin) return clampf(v, (linLo < -1.0e30f) ? linLo : linLo * S.lim[r], S.lim[r]);
-        if (D.has_pl && r == D.rPL) return fminf(v, plim(tt));
-        float a = agg_a(v, tt);
-        return ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
-    };
-    double dconj = 0.0, duq = 0.0;
-    float viol = -1.f, umax = 0.f, zumax = 0.f;
-    // (excess allowed on a row of L amperes: min(viol_tol L, viol_abs); see eval_columns of the on-chip kernel)
-    auto vfac = [&](float lim_amps) -> float { return (opt.viol_abs > 0.f) ? fmaxf(1.f, lim_amps * opt.viol_tol / opt.viol_abs) : 1.f; };
-    for (int i = tid; i < (Rp - R) * TW; i += blockDim.x) { bv[R * TW + i] = 0.f; y1[R * TW + i] = 0.f; }
-    // ---- stage 1: inputs (columns beyond Tp read as zero and are never written back)
-    for (int g = warp; g < NG; g += nw) {
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int t = t0 + 32 * c;
-            float val = 0.f;
-            if (t < Tp) {
-                float s = (CHECK ? W.SGZ : W.SG)[((size_t)b * NG + g) * Tp + t];
-                val = CHECK ? s : rho1 * s - S.ngrp[g] * (AL[t] + S.kg[g] * BE[t]);
-            }
-            sa[g * TW + 32 * c + lane] = val;
-        }
-    }
-    for (int r = warp; r < R; r += nw) {
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int t = t0 + 32 * c;
-            if (t >= Tp) { gg[r * TW + 32 * c + lane] = 0.f; continue; }
-            float z;
-            if (r < 2 * D.nDisc) {
-                int r0 = r & ~1;
-                float a = VC[r0 * Tp + t], bb = VC[(r0 + 1) * Tp + t], za, zb;
-                proj_disc(a, bb, S.lim[r0], za, zb);
-                z = (r & 1) ? zb : za;
-            } else z = proj_row(r, VC[r * Tp + t], t);
-            float v = VC[r * Tp + t];
-            gg[r * TW + 32 * c + lane] = CHECK ? rho * (v - z) : rho * (2.f * z - v);
-            if (CHECK) {
-                float y = rho * (v - z);
-                if (r < 2 * D.nDisc) {
-                    // support function of the disc: after the barrier, from both components
-                } else if (r < 2 * D.nDisc + D.nLin + D.has_pl) {
-                    float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
-                    if (y != 0.f && cap < 1.0e30f) dconj -= (double)(cap * fabsf(y));
-                } else {
-                    // aggregate-power row: Fenchel equality -g*(y) = g(z) - <y, z>; the max term is added in k_decide
-                    float zk = z * su;
-                    if (t < Tb) { dconj += (double)Gamma * (double)(zk + ebar(t)) * (double)(zk + ebar(t)); zumax = fmaxf(zumax, zk); }
-                    dconj -= (double)y * (double)z;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (CHECK) {
-        // disc support functions need both components
-        for (int j = warp; j < D.nDisc; j += nw)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                float ya = gg[(2 * j) * TW + 32 * c + lane], yb = gg[(2 * j + 1) * TW + 32 * c + lane];
-                dconj -= (double)(S.lim[2 * j] * sqrtf(ya * ya + yb * yb));
-            }
-        // Kz rows: violation and aggregate power of the candidate
-        for (int r = warp; r < R; r += nw)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                float ka = 0.f;
-                for (int g = 0; g < NG; ++g) ka += S.C[r * NG + g] * sa[g * TW + 32 * c + lane];
-                bv[r * TW + 32 * c + lane] = ka;
-            }
-        __syncthreads();
-        for (int j = warp; j < D.nDisc; j += nw)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                float ka = bv[(2 * j) * TW + 32 * c + lane], kb = bv[(2 * j + 1) * TW + 32 * c + lane];
-                if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, (sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f) * vfac(S.lim[2 * j] * S.row_scale[2 * j]));
-                else viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) * S.row_scale[2 * j]);  // limit 0: the current itself, in amperes
-            }
-        for (int r = 2 * D.nDisc + warp; r < 2 * D.nDisc + D.nLin + D.has_pl; r += nw)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int t = t0 + 32 * c;
-                float ka = bv[r * TW + 32 * c + lane];
-                float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
-                if (r < 2 * D.nDisc + D.nLin && D.lin_two_sided) ka = fabsf(ka);
-                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, (ka / cap - 1.f) * vfac(cap * S.row_scale[r]));
-                else if (cap <= 0.f) viol = fmaxf(viol, fmaxf(ka, 0.f) * S.row_scale[r]);
-            }
-        if (D.has_u && warp == 0)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int t = t0 + 32 * c;
-                if (t < Tb) {
-                    float u = bv[D.rU * TW + 32 * c + lane] * su;
-                    umax = fmaxf(umax, u);
-                    duq += (double)(u + ebar(t)) * (double)(u + ebar(t));
-                }
-            }
-        // HG <- C'y
-        for (int g = warp; g < NG; g += nw)
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) {
-                const int t = t0 + 32 * c;
-                float acc = 0.f;
-                for (int r = 0; r < R; ++r) acc += S.C[r * NG + g] * gg[r * TW + 32 * c + lane];
-                if (t < Tp) W.HG[((size_t)b * NG + g) * Tp + t] = acc;
-            }
-        viol = wmax(viol); umax = wmax(umax); zumax = wmax(zumax);
-        dconj = wsumd(dconj); duq = wsumd(duq);
-        if (lane == 0) {
-            float* s = W.scal + (size_t)b * GS_N;
-            atomic_max_pos(s + GS_VIOL, viol + 4.f);
-            atomic_max_pos(s + GS_UMAX, fmaxf(umax, 0.f));
-            atomic_max_pos(s + GS_ZUMAX, fmaxf(zumax, 0.f));
-            atomicAdd(W.dacc + (size_t)b * GD_N + GD_D, dconj);
-            atomicAdd(W.dacc + (size_t)b * GD_N + GD_UQ, duq);
-        }
-        return;
-    }
-    // ---- stage 2: bv = C sa - (d/rho) g
-    for (int r = warp; r < R; r += nw) {
-        float acc[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) acc[c] = -dr * gg[r * TW + 32 * c + lane];
-        for (int g = 0; g < NG; ++g) {
-            const float w = S.C[r * NG + g];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[c] += w * sa[g * TW + 32 * c + lane];
-        }
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) bv[r * TW + 32 * c + lane] = acc[c];
-    }
-    __syncthreads();
-    // ---- stages 3 and 4: y1 = diag(1/(d/rho+lam)) U' bv,  h = -U y1 (into bv).
-    // Register-blocked: a warp produces 4 output rows x CPL columns per pass from float4 loads of the padded
-    // matrix rows (warp-uniform addresses) and CPL shared-memory values per input row.
-    auto mat_apply = [&](const float* __restrict__ Mat, const float* __restrict__ in, float* __restrict__ out, bool scale) {
-        for (int e0 = warp * 4; e0 < R; e0 += nw * 4) {
-            float a[4][CPL];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) a[i][c] = 0.f;
-            const float4* m0 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 0, R - 1) * Rp);
-            const float4* m1 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 1, R - 1) * Rp);
-            const float4* m2 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 2, R - 1) * Rp);
-            const float4* m3 = reinterpret_cast<const float4*>(Mat + (size_t)min(e0 + 3, R - 1) * Rp);
-            for (int r4 = 0; r4 < Rp / 4; ++r4) {
-                const float4 w0 = __ldg(m0 + r4), w1 = __ldg(m1 + r4), w2 = __ldg(m2 + r4), w3 = __ldg(m3 + r4);
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const float b0 = in[(4 * r4 + 0) * TW + 32 * c + lane], b1 = in[(4 * r4 + 1) * TW + 32 * c + lane];
-                    const float b2 = in[(4 * r4 + 2) * TW + 32 * c + lane], b3 = in[(4 * r4 + 3) * TW + 32 * c + lane];
-                    a[0][c] += w0.x * b0 + w0.y * b1 + w0.z * b2 + w0.w * b3;
-                    a[1][c] += w1.x * b0 + w1.y * b1 + w1.z * b2 + w1.w * b3;
-                    a[2][c] += w2.x * b0 + w2.y * b1 + w2.z * b2 + w2.w * b3;
-                    a[3][c] += w3.x * b0 + w3.y * b1 + w3.z * b2 + w3.w * b3;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (e0 + i < R) {
-                    const float inv = scale ? 1.f / (dr + S.lam[e0 + i]) : -1.f;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) out[(e0 + i) * TW + 32 * c + lane] = a[i][c] * inv;
-                }
-        }
-    };
-    mat_apply(S.Ut, bv, y1, true);
-    __syncthreads();
-    mat_apply(S.Up, y1, bv, false);
-    __syncthreads();
-    for (int g = warp; g < NG; g += nw) {
-        float acc[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) acc[c] = 0.f;
-        for (int r = 0; r < R; ++r) {
-            const float w = S.C[r * NG + g];
-#pragma unroll
-            for (int c = 0; c < CPL; ++c) acc[c] += w * bv[r * TW + 32 * c + lane];
-        }
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int t = t0 + 32 * c;
-            if (t < Tp) W.HG[((size_t)b * NG + g) * Tp + t] = acc[c] - (AL[t] + S.kg[g] * BE[t]);
-        }
-    }
-    for (int r = warp; r < R; r += nw)
-#pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int t = t0 + 32 * c;
-            if (t >= Tp) continue;
-            float g_ = gg[r * TW + 32 * c + lane], v = VC[r * Tp + t];
-            float kx = (g_ - bv[r * TW + 32 * c + lane]) / rho;
-            float z = 0.5f * (g_ / rho + v);  // g = rho (2z - v)
-            KX[r * Tp + t] = kx;
-            VC[r * Tp + t] = v + opt.alpha * (kx - z);
-        }
-}
-
 // ---------------------------------------------------------------------------- iteration column pass as a blocked product
 // One stage of the Woodbury chain for a tile of 32 periods: out[m][c] = epi(sum_k MatT[k][m] * in[k][c]), m < M, c < 32.
 // MatT is the k-major operand in global memory (row stride ldm, a multiple of 4, zero padded; shared by every instance of
@@ -823,6 +592,152 @@ __device__ __forceinline__ void mm_stage(const float* __restrict__ MatT, int ldm
             const int m = m0 + RPT * tr + i;
             if (m < M) epi(m, 4 * tc, acc[i]);
         }
+    }
+}
+
+// Check column pass, block per (tile of 32 periods, instance): evaluation of the candidate (violation, aggregate-power
+// part of P, conjugate terms of D, HG <- C'y).  Runs once per check_every iterations; the iteration's column pass is
+// k_cols_it below.
+#define ACB_CPL 1  // columns per lane
+__global__ void __launch_bounds__(256) k_cols_check(SiteDev S, acb_batch B, acb_options opt, GenWork W, GenDims D) {
+    constexpr int CHECK = 1, CPL = ACB_CPL, TW = 32 * CPL;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    if (W.status[b] >= 0) return;
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int R = D.R, NG = D.NG, Tp = D.Tp, t0 = tile * TW + lane, Tb = B.T[b];
+    float* sa = sm;                 // [NG][TW]   group inputs / group sums of z
+    float* gg = sa + NG * TW;       // [R][TW]    g (iteration) or y (check)
+    const int Rp = S.Rp;            // R rounded up to a multiple of 4
+    float* bv = gg + R * TW;        // [Rp][TW]  K z
+    float* mbuf = bv + Rp * TW;     // [MM_KC][128] matrix chunk of mm_stage
+    const float* sc = W.scal + (size_t)b * GS_N;
+    const float rho = sc[GS_RHO], rho1 = opt.kappa * rho, qd = sc[GS_QD], dd = 2.f * qd + rho1, dr = dd / rho;
+    const float Gamma = sc[GS_GAMMA], pk_w = sc[GS_PKW], pk_p0 = sc[GS_PKP0], plevel = sc[GS_PLEVEL];
+    const float su = D.has_u ? S.row_scale[D.rU] : 1.f;
+    const float linLo = D.lin_two_sided ? -1.f : -3.0e38f;
+    const float* AL = W.AL + (size_t)b * Tp;
+    const float* BE = W.BE + (size_t)b * Tp;
+    const float* ext = B.ext ? B.ext + (size_t)b * Tp : nullptr;
+    float* VC = W.VC + (size_t)b * R * Tp;
+    float* KX = W.KX + (size_t)b * R * Tp;
+    auto ebar = [&](int tt) -> float { return (ext && tt < Tb) ? ext[tt] : 0.f; };
+    auto plim = [&](int tt) -> float { return (B.peak_limit && tt < Tb) ? B.peak_limit[(size_t)b * Tp + tt] / S.row_scale[D.rPL] : 3.0e38f; };
+    auto agg_a = [&](float v, int tt) -> float { float rp = rho / (su * su); return (rp * (v * su) - 2.f * Gamma * ebar(tt)) / (rp + 2.f * Gamma); };
+    // z of coupling row r (disc rows are handled pairwise by the caller)
+    auto proj_row = [&](int r, float v, int tt) -> float {
+        if (r < 2 * D.nDisc + D.nLin) return clampf(v, (linLo < -1.0e30f) ? linLo : linLo * S.lim[r], S.lim[r]);
+        if (D.has_pl && r == D.rPL) return fminf(v, plim(tt));
+        float a = agg_a(v, tt);
+        return ((pk_w > 0.f) ? fminf(a, plevel) : a) / su;
+    };
+    double dconj = 0.0, duq = 0.0;
+    float viol = -1.f, umax = 0.f, zumax = 0.f;
+    // (excess allowed on a row of L amperes: min(viol_tol L, viol_abs); see eval_columns of the on-chip kernel)
+    auto vfac = [&](float lim_amps) -> float { return (opt.viol_abs > 0.f) ? fmaxf(1.f, lim_amps * opt.viol_tol / opt.viol_abs) : 1.f; };
+    // ---- stage 1: inputs (columns beyond Tp read as zero and are never written back)
+    for (int g = warp; g < NG; g += nw) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int t = t0 + 32 * c;
+            float val = 0.f;
+            if (t < Tp) {
+                float s = (CHECK ? W.SGZ : W.SG)[((size_t)b * NG + g) * Tp + t];
+                val = CHECK ? s : rho1 * s - S.ngrp[g] * (AL[t] + S.kg[g] * BE[t]);
+            }
+            sa[g * TW + 32 * c + lane] = val;
+        }
+    }
+    for (int r = warp; r < R; r += nw) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int t = t0 + 32 * c;
+            if (t >= Tp) { gg[r * TW + 32 * c + lane] = 0.f; continue; }
+            float z;
+            if (r < 2 * D.nDisc) {
+                int r0 = r & ~1;
+                float a = VC[r0 * Tp + t], bb = VC[(r0 + 1) * Tp + t], za, zb;
+                proj_disc(a, bb, S.lim[r0], za, zb);
+                z = (r & 1) ? zb : za;
+            } else z = proj_row(r, VC[r * Tp + t], t);
+            float v = VC[r * Tp + t];
+            gg[r * TW + 32 * c + lane] = CHECK ? rho * (v - z) : rho * (2.f * z - v);
+            if (CHECK) {
+                float y = rho * (v - z);
+                if (r < 2 * D.nDisc) {
+                    // support function of the disc: after the barrier, from both components
+                } else if (r < 2 * D.nDisc + D.nLin + D.has_pl) {
+                    float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
+                    if (y != 0.f && cap < 1.0e30f) dconj -= (double)(cap * fabsf(y));
+                } else {
+                    // aggregate-power row: Fenchel equality -g*(y) = g(z) - <y, z>; the max term is added in k_decide
+                    float zk = z * su;
+                    if (t < Tb) { dconj += (double)Gamma * (double)(zk + ebar(t)) * (double)(zk + ebar(t)); zumax = fmaxf(zumax, zk); }
+                    dconj -= (double)y * (double)z;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (CHECK) {
+        // disc support functions need both components
+        for (int j = warp; j < D.nDisc; j += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float ya = gg[(2 * j) * TW + 32 * c + lane], yb = gg[(2 * j + 1) * TW + 32 * c + lane];
+                dconj -= (double)(S.lim[2 * j] * sqrtf(ya * ya + yb * yb));
+            }
+        // Kz rows: violation and aggregate power of the candidate
+        mm_stage<4>(S.Ct, Rp, NG, R, sa, mbuf, [&](int m, int c, const float* a) {
+            *reinterpret_cast<float4*>(bv + m * TW + c) = make_float4(a[0], a[1], a[2], a[3]);
+        });
+        __syncthreads();
+        for (int j = warp; j < D.nDisc; j += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                float ka = bv[(2 * j) * TW + 32 * c + lane], kb = bv[(2 * j + 1) * TW + 32 * c + lane];
+                if (S.lim[2 * j] > 0.f) viol = fmaxf(viol, (sqrtf(ka * ka + kb * kb) / S.lim[2 * j] - 1.f) * vfac(S.lim[2 * j] * S.row_scale[2 * j]));
+                else viol = fmaxf(viol, sqrtf(ka * ka + kb * kb) * S.row_scale[2 * j]);  // limit 0: the current itself, in amperes
+            }
+        for (int r = 2 * D.nDisc + warp; r < 2 * D.nDisc + D.nLin + D.has_pl; r += nw)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int t = t0 + 32 * c;
+                float ka = bv[r * TW + 32 * c + lane];
+                float cap = (D.has_pl && r == D.rPL) ? plim(t) : S.lim[r];
+                if (r < 2 * D.nDisc + D.nLin && D.lin_two_sided) ka = fabsf(ka);
+                if (cap > 0.f && cap < 1.0e30f) viol = fmaxf(viol, (ka / cap - 1.f) * vfac(cap * S.row_scale[r]));
+                else if (cap <= 0.f) viol = fmaxf(viol, fmaxf(ka, 0.f) * S.row_scale[r]);
+            }
+        if (D.has_u && warp == 0)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int t = t0 + 32 * c;
+                if (t < Tb) {
+                    float u = bv[D.rU * TW + 32 * c + lane] * su;
+                    umax = fmaxf(umax, u);
+                    duq += (double)(u + ebar(t)) * (double)(u + ebar(t));
+                }
+            }
+        // HG <- C'y
+        {
+            auto hg_out = [&](int m, int c, const float* a) {
+                *reinterpret_cast<float4*>(W.HG + ((size_t)b * NG + m) * Tp + tile * TW + c) = make_float4(a[0], a[1], a[2], a[3]);
+            };
+            if (NG <= 64) mm_stage<2>(S.Cp, S.NGp, R, NG, gg, mbuf, hg_out);
+            else mm_stage<4>(S.Cp, S.NGp, R, NG, gg, mbuf, hg_out);
+        }
+        viol = wmax(viol); umax = wmax(umax); zumax = wmax(zumax);
+        dconj = wsumd(dconj); duq = wsumd(duq);
+        if (lane == 0) {
+            float* s = W.scal + (size_t)b * GS_N;
+            atomic_max_pos(s + GS_VIOL, viol + 4.f);
+            atomic_max_pos(s + GS_UMAX, fmaxf(umax, 0.f));
+            atomic_max_pos(s + GS_ZUMAX, fmaxf(zumax, 0.f));
+            atomicAdd(W.dacc + (size_t)b * GD_N + GD_D, dconj);
+            atomicAdd(W.dacc + (size_t)b * GD_N + GD_UQ, duq);
+        }
+        return;
     }
 }
 
@@ -1199,11 +1114,11 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     ROWS(6);
     if (!batch->lb_zero) ROWS(7);
     k_setup_agg<<<B, 256, 0, st>>>(d, *batch, W, D, batch->lb_zero ? 0 : 1);
-    const size_t smem_cols = (size_t)(NG + std::max(R, 1) + 2 * std::max(d.Rp, 4)) * 32 * ACB_CPL * sizeof(float);
+    const size_t smem_cols = ((size_t)(NG + std::max(R, 1) + std::max(d.Rp, 4)) * 32 * ACB_CPL + (size_t)MM_KC * 128) * sizeof(float);
     const size_t smem_it = ((size_t)MM_KC * 128 + (size_t)(std::max(NG, std::max(d.nEigp, 4)) + std::max(R, 1) + std::max(d.Rp, 4)) * 32) * sizeof(float);
     if (smem_it > 48 * 1024) ACB_CUDA(cudaFuncSetAttribute(k_cols_it, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_it));
     if (smem_cols > 48 * 1024) {
-        ACB_CUDA(cudaFuncSetAttribute(k_cols<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+        ACB_CUDA(cudaFuncSetAttribute(k_cols_check, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     }
     ROWS(1);
     int h_done = 0, it = 0;
@@ -1221,7 +1136,7 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
         it += burst;
         // check
         ROWS(2);
-        k_cols<1><<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
+        k_cols_check<<<gcol, 256, smem_cols, st>>>(d, *batch, opt, W, D);
         ROWS(3);
         k_decide<<<(B + 127) / 128, 128, 0, st>>>(*batch, opt, W, D, it, it >= opt.max_iter ? 1 : 0);
         ROWS(5);

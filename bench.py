@@ -464,8 +464,12 @@ def main():
     achieved = alg_bytes_rank / (kern_ms / 1e3) / 1e9  # algorithmic bytes of one launch / that launch's duration (isolated)
     traffic = None
     try:
-        # measured DRAM bytes per instance (ncu, profiles/) x instances per launch on this rank
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_dram.json")))["dram_bytes_per_instance"] * per_gpu
+        if args.config == "c5":
+            # general path: measured DRAM bytes per instance-iteration (ncu, k_rows + k_cols_it + k_level) x the launch's instance-iterations
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "general_path_dram.json")))["dram_bytes_per_instance_iteration"] * float((iters + 1).sum())
+        else:
+            # measured DRAM bytes per instance (ncu, profiles/) x instances per launch on this rank
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "solve_kernel_dram.json")))["dram_bytes_per_instance"] * per_gpu
     except Exception:
         pass
     if rank == 0:
