@@ -1088,9 +1088,10 @@ int run_general(acb_site* site, const acb_batch* batch, const acb_options& opt, 
     ACB_CUDA(cudaMemsetAsync(W.HG, 0, nGT * sizeof(float), st));
     // row kernels: registers (Q > 0: 8 warps, Tp floats of partial sums each) or shared-memory staging (Q = 0: as many
     // warps as fit, 4 Tp floats each)
-    // (register path: 4 warps per block — a group of ~20 identical EVSEs divides evenly, and the block-level sum waits less)
-    int row_threads = 128;
-    size_t row_smem = (size_t)4 * Tp * sizeof(float);
+    // (register path: 2 warps per block, measured: 4 warps 134 us, 2 warps 128 us, 1 warp 138 us per launch on the 1000-EVSE site —
+    // a warp pays its chain of dependent table loads once, so more rows per warp amortise it; one warp alone hides too little)
+    int row_threads = 64;
+    size_t row_smem = (size_t)2 * Tp * sizeof(float);
     if (Q == 0) {
         const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)232448 / ((size_t)16 * Tp)));
         row_threads = 32 * nw;
