@@ -24,12 +24,22 @@ for l in sass:
         continue
     m = re.search(r'//## File "(.*?)", line (\d+)', l)
     if m:
-        cur = int(m.group(2))
+        cur = (m.group(1), int(m.group(2)))
         continue
     if re.match(r"\s+/\*[0-9a-f]+\*/", l):
         tab.append(cur)
 assert len(tab) >= len(rows), (len(tab), len(rows))
-src = open(os.path.join(ROOT, "adacharge_b200", "csrc", "acb_solve_general.cu")).read().splitlines()
+_src = {}
+def text(key):
+    if not key:
+        return ""
+    f, ln = key
+    if f not in _src:
+        try:
+            _src[f] = open(f if os.path.isabs(f) else os.path.join(ROOT, "adacharge_b200", "csrc", f)).read().splitlines()
+        except OSError:
+            _src[f] = []
+    return _src[f][ln - 1].strip()[:120] if 0 < ln <= len(_src[f]) else ""
 ins, smp = collections.Counter(), collections.Counter()
 for r, ln in zip(rows, tab):
     ins[ln] += int(r["Instructions Executed"] or 0)
@@ -37,4 +47,4 @@ for r, ln in zip(rows, tab):
 ti, ts = sum(ins.values()), sum(smp.values())
 print(f"{len(rows)} SASS instructions, {ti} executed, {ts} samples")
 for ln, _ in smp.most_common(top):
-    print(f"{100 * smp[ln] / ts:5.1f}% samples {100 * ins[ln] / ti:5.1f}% inst  L{ln}: {src[ln - 1].strip()[:120] if ln and ln <= len(src) else ''}")
+    print(f"{100 * smp[ln] / ts:5.1f}% samples {100 * ins[ln] / ti:5.1f}% inst  {os.path.basename(ln[0]) if ln else '?'}:{ln[1] if ln else 0}: {text(ln)}")
