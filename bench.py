@@ -160,8 +160,34 @@ def _oracle_one(job):
     S, I = iface.active_sessions(), iface.infrastructure_info()
     spec = [(n, c, dict(k, **({"external_signal": d["external_signal"]} if n == "load_flattening" and "external_signal" in d else {}))) for n, c, k in CONFIGS[cfg]["objective"]]
     t = time.perf_counter()
-    R = mpc.solve_mpc(spec, S, I, iface, "SOC", False, None, iface.get_prev_peak())
+    if _cpu_kind(cfg) == "reference":  # the unmodified reference (cvxpy front end) where it can run: never in this image
+        from oracle import reference_cvxpy
+
+        R = np.asarray(reference_cvxpy.solve_reference(spec, S, I, iface, "SOC", False, None, iface.get_prev_peak()))
+    else:
+        R = mpc.solve_mpc(spec, S, I, iface, "SOC", False, None, iface.get_prev_peak())
     return time.perf_counter() - t, float(mpc.evaluate_objective(R, spec, I, iface, S, iface.get_prev_peak()))
+
+
+def _cpu_what(cfg):
+    if _cpu_kind(cfg) == "reference":
+        return "the unmodified reference's AdaptiveChargingOptimization.solve (cvxpy), loaded by oracle/reference_cvxpy.py"
+    return ("oracle/mpc.py float64 interior-point restatement of the reference's cvxpy/ECOS path, which cannot run here "
+            "(cvxpy, ecos, acnportal not installed)")
+
+
+def _cpu_kind(cfg):
+    """"reference" when the reference's own solve can run (cvxpy importable, its source present, every objective term of the
+    workload defined by it: non_completion_penalty is not), else "port" (oracle/mpc.py)."""
+    try:
+        from oracle import reference_cvxpy
+
+        if not reference_cvxpy.available():
+            return "port"
+        ref = reference_cvxpy.load()
+        return "reference" if all(hasattr(ref, n) for n, _, _ in CONFIGS[cfg]["objective"]) else "port"
+    except Exception:
+        return "port"
 
 
 def _worker_init():
@@ -225,10 +251,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": make_config(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": _cpu_kind(cfg),
                          "sample": f"{n} instances of the workload (seeds 0..{n - 1}) on one persistent pool of {cores} single-threaded workers "
-                                   f"(all host cores), wall {wall:.1f} s{note}; oracle/mpc.py float64 interior-point restatement of the reference's "
-                                   "cvxpy/ECOS path, which cannot run here (cvxpy, ecos, acnportal not installed)"},
+                                   f"(all host cores), wall {wall:.1f} s{note}; {_cpu_what(cfg)}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -503,8 +528,8 @@ def main():
             v, wall, done = pool.run(args.config, list(range(n)), budget_s=120.0)
             pool.close()
             note = "" if len(done) == n else f"; stopped after {wall:.0f} s with {len(done)} of {n} solves finished"
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": pool.cores, "kind": "port",
-                                    "sample": f"first {n} instances of the batch, one per core on all {pool.cores} host cores, oracle/mpc.py (float64 interior point), wall {wall:.1f} s{note}"}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": pool.cores, "kind": _cpu_kind(args.config),
+                                    "sample": f"first {n} instances of the batch, one per core on all {pool.cores} host cores, {_cpu_what(args.config)}, wall {wall:.1f} s{note}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

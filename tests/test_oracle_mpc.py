@@ -224,3 +224,30 @@ def test_mixed_phase_soc_instances_match_slsqp(seed):
     R = mpc.solve_mpc(sc["objective"], S, I, iface, "SOC", sc.get("equality", False), sc.get("peak_limit"), iface.get_prev_peak())
     fo = mpc.evaluate_objective(R, sc["objective"], I, iface, S, iface.get_prev_peak())
     assert abs(fs - fo) <= 1e-6 * max(1.0, abs(fo)), (fs, fo, res.status)
+
+
+# ---- the real reference, where it can run (cvxpy importable): pins the oracle to reference OUTPUTS --------------------------
+from oracle import reference_cvxpy  # noqa: E402
+
+
+def test_reference_hook_reports_availability_consistently():
+    """available() must agree with what the image has: without cvxpy the hook stays off and nothing else is touched."""
+    try:
+        import cvxpy  # noqa: F401
+        have = True
+    except Exception:
+        have = False
+    assert reference_cvxpy.available() == (have and reference_cvxpy._ref_dir() is not None)
+
+
+@pytest.mark.skipif(not reference_cvxpy.available(), reason="cvxpy (the reference's solver front end) is not installed in this image")
+@pytest.mark.parametrize("name", FAST + LARGE)
+def test_oracle_matches_the_reference_solver(name):
+    """Objective of the oracle's schedule within 1e-6 |f*| of the reference's own solve (aco.py:286-321) on the same scenario."""
+    sc = SCENARIOS[name]
+    R, iface, S, I = _solve(sc)
+    Rref = reference_cvxpy.solve_reference(sc["objective"], S, I, iface, sc.get("constraint_type", "SOC"), sc.get("equality", False),
+                                           sc.get("peak_limit"), 0)
+    f = mpc.evaluate_objective(R, sc["objective"], I, iface)
+    fref = mpc.evaluate_objective(np.asarray(Rref), sc["objective"], I, iface)
+    assert abs(f - fref) <= 1e-6 * max(1.0, abs(fref)), (f, fref)
