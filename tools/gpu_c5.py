@@ -21,7 +21,9 @@ print(f"host packing {time.time()-t0:.1f}s")
 site = aco._site_for(I, insts[0])
 print("site R", site.R, "NG", site.NG)
 pb = engine.PackedBatch(site, insts).upload()
-for kw in (dict(), dict(max_iter=310, check_every=300, eps_rel=0.0, eps_abs=0.0)):
+# extra arguments: check_every values to try at the default tolerances (at which iteration does the gap certify?)
+extra = [dict(check_every=int(a)) for a in sys.argv[2:]]
+for kw in [dict(), dict(max_iter=310, check_every=300, eps_rel=0.0, eps_abs=0.0)] + extra:
   opt = _cabi.default_options(**kw)
   pb.solve(opt); torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
